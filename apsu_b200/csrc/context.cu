@@ -1,0 +1,270 @@
+#include "context.hpp"
+#include "hostmath.hpp"
+#include "ntt.cuh"
+#include <algorithm>
+#include <cstring>
+
+namespace apsu_b200 {
+
+using hm::invm;
+using hm::mulm;
+
+static DMod make_mod(uint64_t q)
+{
+    DMod m;
+    m.q = q;
+    // floor(2^128 / q) in two words
+    hm::u128 top = (hm::u128)1 << 64;
+    uint64_t hi = (uint64_t)(top / q);
+    hm::u128 rem = top % q;
+    uint64_t lo = (uint64_t)((rem << 64) / q);
+    m.r0 = lo;
+    m.r1 = hi;
+    return m;
+}
+static DShoup make_shoup(uint64_t v, uint64_t q)
+{
+    v %= q;
+    DShoup s;
+    s.op = v;
+    s.quot = (uint64_t)(((hm::u128)v << 64) / q);
+    return s;
+}
+
+DeviceContext::DeviceContext(const apsu_b200_params &p, int dev) : params(p), device(dev)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw CudaError(std::string("no CUDA device available (apsu_b200 has no CPU fallback): ") + cudaGetErrorString(e));
+    if (dev < 0 || dev >= count) throw std::invalid_argument("device ordinal is out of range");
+    APSU_CUDA_CHECK(cudaSetDevice(dev));
+    N = p.poly_modulus_degree;
+    logN = 0;
+    while ((1u << logN) < N) logN++;
+    if (logN < 11 || logN > 14) throw std::invalid_argument("poly_modulus_degree must be between 2048 and 16384");
+    K = p.coeff_modulus_count;
+    t = p.plain_modulus;
+    if (K > (uint32_t)kMaxKey) throw std::invalid_argument("too many coeff_modulus primes for this build");
+    first_L = K > 1 ? K - 1 : 1;
+    // get_parms_id_for_chain_idx clamps to the first data level; a data level with chain index c has c+1 primes
+    auto level_for_chain = [&](uint32_t c) { return std::min(first_L, c + 1); };
+    low_L = level_for_chain(std::min<uint32_t>(first_L - 1, p.ps_low_degree ? 2 : 1));
+    high_L = level_for_chain(1);
+    APSU_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    owns_stream = true;
+    build_moduli();
+    build_levels();
+    APSU_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+DeviceContext::~DeviceContext()
+{
+    if (owns_stream && stream) cudaStreamDestroy(stream);
+}
+
+void DeviceContext::build_moduli()
+{
+    // BEHZ auxiliary bases (RNSTool::initialize): |B| = L (+1 if 32 + bits(t) + bits(q) >= 61 L + 61)
+    uint32_t maxB = 0;
+    for (uint32_t L = 1; L <= first_L; L++) {
+        hm::Wide q;
+        for (uint32_t i = 0; i < L; i++) q.mul(params.coeff_modulus[i]);
+        uint32_t nb = L + ((32 + hm::bit_length(t) + q.bits() >= 61 * (int)L + 61) ? 1 : 0);
+        maxB = std::max(maxB, nb);
+    }
+    if (maxB + 1 > (uint32_t)kMaxBsk || first_L > (uint32_t)kMaxQ) throw std::invalid_argument("modulus chain too long for this build");
+    nB = maxB;
+    auto aux = hm::primes_below_pow2(2ull * N, 61, maxB + 2); // m_sk, gamma, B_0, B_1, ...
+    mod_values.assign(params.coeff_modulus, params.coeff_modulus + K);
+    idx_msk = (uint32_t)mod_values.size();
+    mod_values.push_back(aux[0]);
+    idx_B0 = (uint32_t)mod_values.size();
+    for (uint32_t i = 0; i < maxB; i++) mod_values.push_back(aux[2 + i]);
+    idx_t = (uint32_t)mod_values.size();
+    mod_values.push_back(t);
+
+    size_t M = mod_values.size();
+    std::vector<ulonglong2> tw(M * 2 * N);
+    mod_host.resize(M);
+    inv_n_host.resize(M);
+    for (size_t m = 0; m < M; m++) {
+        uint64_t q = mod_values[m];
+        mod_host[m] = make_mod(q);
+        uint64_t psi = hm::min_primitive_root(2ull * N, q), ipsi = invm(psi, q);
+        uint64_t f = 1, b = 1;
+        for (uint32_t i = 0; i < N; i++) {
+            unsigned r = hm::bitrev(i, (int)logN);
+            DShoup sf = make_shoup(f, q), sb = make_shoup(b, q);
+            tw[(m * 2 + 0) * N + r] = make_ulonglong2(sf.op, sf.quot);
+            tw[(m * 2 + 1) * N + r] = make_ulonglong2(sb.op, sb.quot);
+            f = mulm(f, psi, q);
+            b = mulm(b, ipsi, q);
+        }
+        inv_n_host[m] = make_shoup(invm(N % q, q), q);
+    }
+    twiddles.upload(tw, stream);
+
+    // BatchEncoder slot -> coefficient-index map
+    std::vector<uint32_t> map(N);
+    uint32_t row = N >> 1, m2 = N << 1;
+    uint64_t pos = 1;
+    for (uint32_t i = 0; i < row; i++) {
+        map[i] = hm::bitrev((unsigned)((pos - 1) >> 1), (int)logN);
+        map[row | i] = hm::bitrev((unsigned)((m2 - pos - 1) >> 1), (int)logN);
+        pos = (pos * 3) & (m2 - 1);
+    }
+    slot_map.upload(map, stream);
+    APSU_CUDA_CHECK(cudaStreamSynchronize(stream)); // host vectors go out of scope
+}
+
+void DeviceContext::build_levels()
+{
+    level.assign(first_L + 1, LevelConsts());
+    ks.assign(first_L + 1, KeySwitchConsts());
+    const uint64_t mt = 1ull << 32;
+    for (uint32_t L = 1; L <= first_L; L++) {
+        LevelConsts &c = level[L];
+        std::memset(&c, 0, sizeof(c));
+        std::vector<uint64_t> q(params.coeff_modulus, params.coeff_modulus + L);
+        hm::Wide qw;
+        for (uint64_t x : q) qw.mul(x);
+        uint32_t nb = L + ((32 + hm::bit_length(t) + qw.bits() >= 61 * (int)L + 61) ? 1 : 0);
+        std::vector<uint64_t> B(mod_values.begin() + idx_B0, mod_values.begin() + idx_B0 + nb);
+        uint64_t msk = mod_values[idx_msk];
+        std::vector<uint64_t> bsk = B;
+        bsk.push_back(msk);
+        c.L = (int)L;
+        c.S = (int)bsk.size();
+        hm::Wide q_div_t = qw.div(t);
+        c.q_mod_t = qw.mod(t);
+        for (uint32_t i = 0; i < L; i++) {
+            c.q[i] = make_mod(q[i]);
+            c.coeff_div_plain[i] = q_div_t.mod(q[i]);
+            if (i + 1 < L) {
+                c.inv_qlast[i] = make_shoup(invm(q[L - 1] % q[i], q[i]), q[i]);
+                c.half_mod[i] = (q[L - 1] >> 1) % q[i];
+            }
+            uint64_t punct = hm::prod_mod(q, q[i], (int)i);
+            uint64_t inv_punct = invm(punct, q[i]);
+            c.inv_punct_q[i] = make_shoup(inv_punct, q[i]);
+            c.t_inv_punct_q[i] = make_shoup(mulm(t % q[i], inv_punct, q[i]), q[i]);
+            c.mtilde_inv_punct_q[i] = make_shoup(mulm(mt % q[i], inv_punct, q[i]), q[i]);
+            c.q_punct_mod_mtilde[i] = (u32)hm::prod_mod(q, mt, (int)i);
+            c.t_mod_q[i] = make_shoup(t, q[i]);
+            uint64_t Bq = hm::prod_mod(B, q[i]);
+            c.B_mod_q[i] = make_shoup(Bq, q[i]);
+            c.neg_B_mod_q[i] = make_shoup((q[i] - Bq) % q[i], q[i]);
+            for (uint32_t k = 0; k < nb; k++) c.B_punct_mod_q[i][k] = hm::prod_mod(B, q[i], (int)k);
+        }
+        c.neg_inv_q_mod_mtilde = (u32)((mt - invm(hm::prod_mod(q, mt), mt)) % mt);
+        for (uint32_t j = 0; j < bsk.size(); j++) {
+            uint64_t p = bsk[j];
+            c.bsk[j] = make_mod(p);
+            for (uint32_t i = 0; i < L; i++) c.q_punct_mod_bsk[j][i] = hm::prod_mod(q, p, (int)i);
+            uint64_t qp = hm::prod_mod(q, p);
+            c.q_mod_bsk[j] = make_shoup(qp, p);
+            c.inv_q_mod_bsk[j] = make_shoup(invm(qp, p), p);
+            c.inv_mtilde_mod_bsk[j] = make_shoup(invm(mt % p, p), p);
+            c.t_mod_bsk[j] = make_shoup(t, p);
+        }
+        for (uint32_t k = 0; k < nb; k++) {
+            c.inv_punct_B[k] = make_shoup(invm(hm::prod_mod(B, B[k], (int)k), B[k]), B[k]);
+            c.B_punct_mod_msk[k] = hm::prod_mod(B, msk, (int)k);
+        }
+        c.inv_B_mod_msk = make_shoup(invm(hm::prod_mod(B, msk), msk), msk);
+
+        KeySwitchConsts &kc = ks[L];
+        std::memset(&kc, 0, sizeof(kc));
+        kc.L = (int)L;
+        kc.K = (int)K;
+        if (K > 1) {
+            uint64_t P = params.coeff_modulus[K - 1];
+            for (uint32_t i = 0; i < L; i++) {
+                kc.key_mod[i] = make_mod(q[i]);
+                kc.inv_P[i] = make_shoup(invm(P % q[i], q[i]), q[i]);
+                kc.half_P_mod[i] = (P >> 1) % q[i];
+            }
+            kc.key_mod[L] = make_mod(P);
+            kc.half_P = P >> 1;
+        }
+    }
+}
+
+std::vector<uint32_t> DeviceContext::pattern_q(uint32_t L) const
+{
+    std::vector<uint32_t> p(L);
+    for (uint32_t i = 0; i < L; i++) p[i] = i;
+    return p;
+}
+std::vector<uint32_t> DeviceContext::pattern_bsk(uint32_t L) const
+{
+    std::vector<uint32_t> p;
+    for (int k = 0; k + 1 < level[L].S; k++) p.push_back(idx_B0 + (uint32_t)k);
+    p.push_back(idx_msk);
+    return p;
+}
+std::vector<uint32_t> DeviceContext::pattern_ext(uint32_t L) const
+{
+    std::vector<uint32_t> p = pattern_q(L), b = pattern_bsk(L);
+    p.insert(p.end(), b.begin(), b.end());
+    return p;
+}
+std::vector<uint32_t> DeviceContext::pattern_ks(uint32_t L) const
+{
+    std::vector<uint32_t> p = pattern_q(L);
+    p.push_back(K - 1);
+    return p;
+}
+
+NttArgs DeviceContext::make_args(const std::vector<uint32_t> &pattern) const
+{
+    if (pattern.empty() || pattern.size() > (size_t)kMaxPattern) throw std::invalid_argument("NTT modulus pattern length is invalid");
+    NttArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.tw = twiddles.p;
+    a.pattern_len = (int)pattern.size();
+    for (size_t i = 0; i < pattern.size(); i++) {
+        if (pattern[i] >= mod_values.size()) throw std::invalid_argument("NTT modulus index is out of range");
+        a.mod[i] = mod_host[pattern[i]];
+        a.inv_n[i] = inv_n_host[pattern[i]];
+        a.table[i] = (int)pattern[i];
+    }
+    return a;
+}
+
+template <int LOGN>
+static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, bool inverse, cudaStream_t st)
+{
+    constexpr int threads = (1 << LOGN) / 16;
+    constexpr size_t smem = sizeof(u64) << LOGN;
+    static bool configured = false;
+    if (!configured) {
+        APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    if (inverse)
+        ntt_kernel<LOGN, false><<<count, threads, smem, st>>>(in, out, a, s);
+    else
+        ntt_kernel<LOGN, true><<<count, threads, smem, st>>>(in, out, a, s);
+}
+
+void DeviceContext::ntt(const u64 *in, u64 *out, uint32_t count, const std::vector<uint32_t> &pattern, bool inverse,
+                        const uint32_t *src_idx, const uint32_t *dst_idx, bool reduce_input)
+{
+    if (!count) return;
+    NttArgs a = make_args(pattern);
+    NttSrc s{ src_idx, dst_idx, reduce_input ? 1 : 0 };
+    switch (logN) {
+    case 11: launch_ntt<11>(in, out, count, a, s, inverse, stream); break;
+    case 12: launch_ntt<12>(in, out, count, a, s, inverse, stream); break;
+    case 13: launch_ntt<13>(in, out, count, a, s, inverse, stream); break;
+    case 14: launch_ntt<14>(in, out, count, a, s, inverse, stream); break;
+    default: throw std::invalid_argument("unsupported poly_modulus_degree");
+    }
+    APSU_CUDA_CHECK(cudaGetLastError());
+    launches++;
+}
+
+} // namespace apsu_b200

@@ -1,0 +1,1049 @@
+#include "engine.hpp"
+#include "eval_kernels.cuh"
+#include "hostmath.hpp"
+#include "kernels.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+namespace apsu_b200 {
+
+// ------------------------------------------------------------------------------------------------
+// kernel launch wrappers
+// ------------------------------------------------------------------------------------------------
+#define APSU_LAUNCH_CHECK()                                                                                            \
+    do {                                                                                                               \
+        APSU_CUDA_CHECK(cudaGetLastError());                                                                           \
+        note_launch();                                                                                                 \
+    } while (0)
+
+void Engine::run_extend(uint32_t L, uint32_t n, const uint32_t *src, const uint32_t *dst)
+{
+    if (!n) return;
+    k_behz_extend<<<dim3(ctx.N / kEwThreads, n), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N);
+    APSU_LAUNCH_CHECK();
+}
+void Engine::run_tensor(uint32_t L, uint32_t n_ops, const uint32_t *a, const uint32_t *b, const uint32_t *d)
+{
+    if (!n_ops) return;
+    const LevelConsts &c = ctx.level[L];
+    k_tensor<<<dim3(ctx.N / kEwThreads, c.L + c.S, n_ops), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, a, b, d, c, (int)ctx.N);
+    APSU_LAUNCH_CHECK();
+}
+void Engine::run_scale_down(uint32_t L, uint32_t n, const uint32_t *src, const uint32_t *dst)
+{
+    if (!n) return;
+    k_behz_scale_down<<<dim3(ctx.N / kEwThreads, n), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N);
+    APSU_LAUNCH_CHECK();
+}
+void Engine::run_ks_mac(uint32_t L, uint32_t n_ops, const uint32_t *dig, const uint32_t *out)
+{
+    if (!n_ops) return;
+    k_ks_mac<<<dim3(ctx.N / kEwThreads, L + 1, n_ops * 2), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, dig, out, relin_keys_.p, ctx.ks[L], (int)ctx.N);
+    APSU_LAUNCH_CHECK();
+}
+void Engine::run_ks_moddown(uint32_t L, uint32_t n_ops, const uint32_t *acc, const uint32_t *ct, const uint32_t *dst)
+{
+    if (!n_ops) return;
+    k_ks_moddown<<<dim3(ctx.N / kEwThreads, 2, n_ops), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, acc, ct, dst, ctx.ks[L], (int)ctx.N);
+    APSU_LAUNCH_CHECK();
+}
+void Engine::run_mod_switch_next(uint32_t L, uint32_t n, const uint32_t *src, const uint32_t *dst)
+{
+    if (!n) return;
+    k_mod_switch_next<<<dim3(ctx.N / kEwThreads, n), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N);
+    APSU_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Program builder: turns batches of ciphertext operations into kernel launches over index arrays.
+// ------------------------------------------------------------------------------------------------
+struct ProgramBuilder {
+    Engine &e;
+    std::vector<Engine::Step> &prog;
+    DeviceContext &ctx;
+    Arena &arena;
+    IdxPool &idx;
+    ProgramBuilder(Engine &eng, std::vector<Engine::Step> &p) : e(eng), prog(p), ctx(eng.ctx), arena(eng.arena_), idx(eng.idx_) {}
+
+    void step(std::function<void()> f) { prog.push_back(Engine::Step{ std::move(f) }); }
+
+    // NTT over `count` polynomials with explicit source/destination indices
+    void ntt(const std::vector<uint32_t> &src, const std::vector<uint32_t> &dst, const std::vector<uint32_t> &pattern, bool inverse, bool reduce = false)
+    {
+        if (src.empty()) return;
+        size_t so = idx.add(src), dn = idx.add(dst);
+        uint32_t count = (uint32_t)src.size();
+        Engine *en = &e;
+        step([=] { en->ctx.ntt(en->arena_.buf.p, en->arena_.buf.p, count, pattern, inverse, en->idx_.at(so), en->idx_.at(dn), reduce); });
+    }
+    // in-place NTT over a contiguous run of polynomials
+    void ntt_run(uint32_t first, uint32_t count, const std::vector<uint32_t> &pattern, bool inverse)
+    {
+        if (!count) return;
+        Engine *en = &e;
+        step([=] {
+            u64 *base = en->arena_.buf.p + (size_t)first * en->ctx.N;
+            en->ctx.ntt(base, base, count, pattern, inverse);
+        });
+    }
+
+    // BEHZ steps (1)-(3): size-2 ciphertexts at level L (arena idx of [2][L][N]) -> extended NTT form
+    // entries [2][L+S][N]
+    void extend(uint32_t L, const std::vector<uint32_t> &cts, const std::vector<uint32_t> &exts)
+    {
+        if (cts.empty()) return;
+        const uint32_t S = (uint32_t)ctx.level[L].S, LS = L + S;
+        std::vector<uint32_t> esrc, edst, nsrc, ndst;
+        for (size_t k = 0; k < cts.size(); k++)
+            for (uint32_t c = 0; c < 2; c++) {
+                esrc.push_back(cts[k] + c * L);
+                edst.push_back(exts[k] + c * LS + L);
+                for (uint32_t j = 0; j < LS; j++) {
+                    nsrc.push_back(j < L ? cts[k] + c * L + j : exts[k] + c * LS + j);
+                    ndst.push_back(exts[k] + c * LS + j);
+                }
+            }
+        size_t so = idx.add(esrc), dn = idx.add(edst);
+        uint32_t n = (uint32_t)esrc.size();
+        Engine *en = &e;
+        step([=] { en->run_extend(L, n, en->idx_.at(so), en->idx_.at(dn)); });
+        ntt(nsrc, ndst, ctx.pattern_ext(L), false);
+    }
+
+    // BEHZ steps (4)-(8): products of extended entries a[o] x b[o] -> size-3 ciphertexts prod[o] ([3][L][N]).
+    // scratch: arena index of n_ops*3*(L+S) polynomials.
+    void multiply(uint32_t L, const std::vector<uint32_t> &a, const std::vector<uint32_t> &b, const std::vector<uint32_t> &prod, uint32_t scratch)
+    {
+        if (a.empty()) return;
+        const uint32_t S = (uint32_t)ctx.level[L].S, LS = L + S, n_ops = (uint32_t)a.size();
+        std::vector<uint32_t> d(n_ops), ssrc, sdst;
+        for (uint32_t o = 0; o < n_ops; o++) {
+            d[o] = scratch + o * 3 * LS;
+            for (uint32_t c = 0; c < 3; c++) {
+                ssrc.push_back(d[o] + c * LS);
+                sdst.push_back(prod[o] + c * L);
+            }
+        }
+        size_t ao = idx.add(a), bo = idx.add(b), dof = idx.add(d), so = idx.add(ssrc), sd = idx.add(sdst);
+        Engine *en = &e;
+        step([=] { en->run_tensor(L, n_ops, en->idx_.at(ao), en->idx_.at(bo), en->idx_.at(dof)); });
+        ntt_run(scratch, n_ops * 3 * LS, ctx.pattern_ext(L), true);
+        step([=] { en->run_scale_down(L, n_ops * 3, en->idx_.at(so), en->idx_.at(sd)); });
+    }
+    static uint32_t multiply_scratch(const DeviceContext &c, uint32_t L, uint32_t n_ops) { return n_ops * 3 * (L + (uint32_t)c.level[L].S); }
+
+    // relinearize_inplace: size-3 ct3[o] ([3][L][N]) -> size-2 dst[o] ([2][L][N]).
+    // scratch: n_ops*(L + 2)*(L + 1) polynomials
+    void relinearize(uint32_t L, const std::vector<uint32_t> &ct3, const std::vector<uint32_t> &dst, uint32_t scratch)
+    {
+        if (ct3.empty()) return;
+        const uint32_t R = L + 1, n_ops = (uint32_t)ct3.size();
+        const uint32_t dig0 = scratch, acc0 = scratch + n_ops * L * R;
+        std::vector<uint32_t> nsrc, ndst, dig(n_ops), acc(n_ops);
+        for (uint32_t o = 0; o < n_ops; o++) {
+            dig[o] = dig0 + o * L * R;
+            acc[o] = acc0 + o * 2 * R;
+            for (uint32_t J = 0; J < L; J++)
+                for (uint32_t I = 0; I < R; I++) {
+                    nsrc.push_back(ct3[o] + 2 * L + J);
+                    ndst.push_back(dig[o] + J * R + I);
+                }
+        }
+        ntt(nsrc, ndst, ctx.pattern_ks(L), false, /*reduce=*/true);
+        size_t dg = idx.add(dig), ac = idx.add(acc), ct = idx.add(ct3), ds = idx.add(dst);
+        Engine *en = &e;
+        step([=] { en->run_ks_mac(L, n_ops, en->idx_.at(dg), en->idx_.at(ac)); });
+        ntt_run(acc0, n_ops * 2 * R, ctx.pattern_ks(L), true);
+        step([=] { en->run_ks_moddown(L, n_ops, en->idx_.at(ac), en->idx_.at(ct), en->idx_.at(ds)); });
+    }
+    static uint32_t relin_scratch(uint32_t L, uint32_t n_ops) { return n_ops * (L + 2) * (L + 1); }
+
+    // mod_switch_to_next on RNS polynomials: src[k] ([L][N]) -> dst[k] ([L-1][N])
+    void mod_switch_next(uint32_t L, const std::vector<uint32_t> &src, const std::vector<uint32_t> &dst)
+    {
+        if (src.empty()) return;
+        size_t so = idx.add(src), dn = idx.add(dst);
+        uint32_t n = (uint32_t)src.size();
+        Engine *en = &e;
+        step([=] { en->run_mod_switch_next(L, n, en->idx_.at(so), en->idx_.at(dn)); });
+    }
+
+    // dst[k] = sum of the RNS polynomials ([L][N]) listed in terms[k]
+    void sum_polys(uint32_t L, const std::vector<std::vector<uint32_t>> &terms, const std::vector<uint32_t> &dst)
+    {
+        if (dst.empty()) return;
+        std::vector<uint32_t> flat, first, cnt;
+        for (auto &tl : terms) {
+            first.push_back((uint32_t)flat.size());
+            cnt.push_back((uint32_t)tl.size());
+            flat.insert(flat.end(), tl.begin(), tl.end());
+        }
+        if (flat.empty()) flat.push_back(0);
+        size_t fo = idx.add(flat), fi = idx.add(first), cn = idx.add(cnt), ds = idx.add(dst);
+        uint32_t n = (uint32_t)dst.size();
+        Engine *en = &e;
+        step([=] {
+            k_sum_polys<<<dim3(en->ctx.N / kEwThreads, L, n), kEwThreads, 0, en->ctx.stream>>>(
+                en->arena_.buf.p, en->idx_.at(fo), en->idx_.at(fi), en->idx_.at(cn), en->idx_.at(ds), en->ctx.level[L], (int)en->ctx.N);
+            APSU_CUDA_CHECK(cudaGetLastError());
+            en->ctx.launches++;
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Engine
+// ------------------------------------------------------------------------------------------------
+Engine::Engine(const apsu_b200_params &p, int device) : ctx(p, device)
+{
+    std::set<uint32_t> sources(p.query_powers, p.query_powers + p.query_power_count);
+    if (!dag.configure(sources, create_powers_set(p.ps_low_degree, p.max_items_per_bin)))
+        throw std::invalid_argument("failed to configure PowersDag");
+    if (dag.depth() > 0 && !ctx.using_keyswitching())
+        throw std::invalid_argument("parameters need ciphertext multiplications but provide no key-switching prime");
+    db.resize(p.bundle_idx_count);
+    levels_dev_.upload(ctx.level, ctx.stream);
+    for (auto &ev : ev_) APSU_CUDA_CHECK(cudaEventCreate(&ev));
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+
+Engine::~Engine()
+{
+    for (auto &e : ev_)
+        if (e) cudaEventDestroy(e);
+    for (auto &pr : mac_events_) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+}
+
+uint32_t Engine::total_bundles() const
+{
+    uint32_t n = 0;
+    for (auto &v : db) n += (uint32_t)v.size();
+    return n;
+}
+
+uint64_t Engine::stream_bytes() const
+{
+    uint64_t words = 0;
+    for (auto &v : db)
+        for (auto &s : v) words += (uint64_t)s->n_ntt * ctx.low_L * ctx.N + (uint64_t)s->n_plain * ctx.N;
+    return words * 8;
+}
+
+void Engine::clear_db()
+{
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    for (auto &v : db) v.clear();
+    invalidate_plan();
+}
+
+// lifts + NTTs the high-degree coefficient-form plaintexts once (multiply_plain_normal operand)
+void Engine::prepare_plain_high(BinBundleStore &s)
+{
+    const uint32_t N = ctx.N, Lh = ctx.high_L;
+    if (!ctx.params.ps_low_degree || s.n_plain <= 1) return;
+    uint32_t cnt = s.n_plain - 1;
+    s.plain_high_ntt.alloc((size_t)cnt * Lh * N);
+    k_plain_lift<<<dim3(N / kEwThreads, Lh, cnt), kEwThreads, 0, ctx.stream>>>(s.plain_coeffs.p + N, s.plain_high_ntt.p, ctx.level[Lh], ctx.t, (int)N);
+    APSU_LAUNCH_CHECK();
+    ctx.ntt(s.plain_high_ntt.p, s.plain_high_ntt.p, cnt * Lh, ctx.pattern_q(Lh), false);
+}
+
+uint32_t Engine::add_binbundle(uint32_t bundle_idx, const uint64_t *const *coeffs, uint32_t ncoeffs)
+{
+    if (bundle_idx >= db.size()) throw std::invalid_argument("bundle_idx is out of range");
+    if (!coeffs || !ncoeffs) throw std::invalid_argument("a BinBundle needs at least the constant coefficient");
+    if (ncoeffs > ctx.params.max_items_per_bin) throw std::invalid_argument("too many coefficients: degree exceeds max_items_per_bin - 1");
+    const uint32_t N = ctx.N, Ll = ctx.low_L;
+    auto s = std::make_unique<BinBundleStore>();
+    s->bundle_idx = bundle_idx;
+    s->cache_idx = (uint32_t)db[bundle_idx].size();
+    s->ncoeffs = ncoeffs;
+    for (uint32_t k = 0; k < ncoeffs; k++) (is_ntt_degree(k) ? s->n_ntt : s->n_plain)++;
+    s->ntt_coeffs.alloc((size_t)s->n_ntt * Ll * N);
+    s->plain_coeffs.alloc((size_t)s->n_plain * N);
+    uint32_t in = 0, ip = 0;
+    for (uint32_t k = 0; k < ncoeffs; k++) {
+        if (!coeffs[k]) throw std::invalid_argument("null plaintext pointer");
+        if (is_ntt_degree(k))
+            APSU_CUDA_CHECK(cudaMemcpyAsync(s->ntt_coeffs.p + (size_t)(in++) * Ll * N, coeffs[k], (size_t)Ll * N * 8, cudaMemcpyHostToDevice, ctx.stream));
+        else
+            APSU_CUDA_CHECK(cudaMemcpyAsync(s->plain_coeffs.p + (size_t)(ip++) * N, coeffs[k], (size_t)N * 8, cudaMemcpyHostToDevice, ctx.stream));
+    }
+    prepare_plain_high(*s);
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    uint32_t ci = s->cache_idx;
+    db[bundle_idx].push_back(std::move(s));
+    invalidate_plan();
+    return ci;
+}
+
+uint32_t Engine::add_binbundle_synthetic(uint32_t bundle_idx, uint32_t ncoeffs, uint64_t seed)
+{
+    if (bundle_idx >= db.size()) throw std::invalid_argument("bundle_idx is out of range");
+    if (!ncoeffs || ncoeffs > ctx.params.max_items_per_bin) throw std::invalid_argument("ncoeffs is out of range");
+    const uint32_t N = ctx.N, Ll = ctx.low_L, ps = ctx.params.ps_low_degree;
+    auto s = std::make_unique<BinBundleStore>();
+    s->bundle_idx = bundle_idx;
+    s->cache_idx = (uint32_t)db[bundle_idx].size();
+    s->ncoeffs = ncoeffs;
+    for (uint32_t k = 0; k < ncoeffs; k++) (is_ntt_degree(k) ? s->n_ntt : s->n_plain)++;
+    s->ntt_coeffs.alloc((size_t)s->n_ntt * Ll * N);
+    s->plain_coeffs.alloc((size_t)s->n_plain * N);
+    FillMods fm;
+    std::memset(&fm, 0, sizeof(fm));
+    for (uint32_t j = 0; j < Ll; j++) fm.q[j] = ctx.params.coeff_modulus[j];
+    fm.t = ctx.t;
+    fm.L = (int)Ll;
+    size_t cn = s->ntt_coeffs.n, cp = s->plain_coeffs.n;
+    if (cn) {
+        k_fill_db<<<(unsigned)((cn + 255) / 256), 256, 0, ctx.stream>>>(s->ntt_coeffs.p, cn, seed, 0, ps ? ps + 1 : 0, fm, (int)N);
+        APSU_LAUNCH_CHECK();
+    }
+    k_fill_db<<<(unsigned)((cp + 255) / 256), 256, 0, ctx.stream>>>(s->plain_coeffs.p, cp, seed, 1, ps ? ps + 1 : 0, fm, (int)N);
+    APSU_LAUNCH_CHECK();
+    prepare_plain_high(*s);
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    uint32_t ci = s->cache_idx;
+    db[bundle_idx].push_back(std::move(s));
+    invalidate_plan();
+    return ci;
+}
+
+uint32_t Engine::add_binbundle_from_bins(uint32_t, const uint32_t *, const uint64_t *)
+{
+    throw std::logic_error("device-side BinBundle construction from raw bins is not implemented yet (SURVEY.md §8 row f1)");
+}
+
+// ------------------------------------------------------------------------------------------------
+// query inputs
+// ------------------------------------------------------------------------------------------------
+void Engine::set_relin_keys(const void *keys, bool on_device)
+{
+    if (!ctx.using_keyswitching()) {
+        have_keys_ = false;
+        return;
+    }
+    if (!keys) throw std::invalid_argument("relinearization keys are required for this parameter set");
+    size_t words = (size_t)(ctx.K - 1) * 2 * ctx.K * ctx.N;
+    relin_keys_.ensure(words);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(relin_keys_.p, keys, words * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
+    have_keys_ = true;
+}
+
+void Engine::set_masks(const void *masks, uint32_t npack, bool on_device)
+{
+    if (!masks || !npack) throw std::invalid_argument("masks are required");
+    masks_.ensure((size_t)npack * ctx.N);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(masks_.p, masks, (size_t)npack * ctx.N * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
+    npack_ = npack;
+}
+
+void Engine::encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t *out)
+{
+    if (!slot_values || !out || !npack) throw std::invalid_argument("encode_masks: bad arguments");
+    const uint32_t N = ctx.N;
+    DBuf<u64> in, enc;
+    in.alloc((size_t)npack * N);
+    enc.alloc((size_t)npack * N);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(in.p, slot_values, (size_t)npack * N * 8, cudaMemcpyHostToDevice, ctx.stream));
+    k_slot_scatter<<<dim3(N / 256, npack), 256, 0, ctx.stream>>>(in.p, enc.p, ctx.slot_map.p, (int)N);
+    APSU_LAUNCH_CHECK();
+    ctx.ntt(enc.p, enc.p, npack, { ctx.idx_t }, true);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(out, enc.p, (size_t)npack * N * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+
+void Engine::query_begin(const uint32_t *src_powers, uint32_t nsrc, const void *cts, bool on_device)
+{
+    const apsu_b200_params &p = ctx.params;
+    if (!src_powers || !cts) throw std::invalid_argument("query is invalid");
+    std::set<uint32_t> given(src_powers, src_powers + nsrc), want(p.query_powers, p.query_powers + p.query_power_count);
+    if (given.size() != nsrc || given != want) throw std::invalid_argument("query powers do not match the query_powers of the parameters");
+    if (!plan_valid_) build_plan();
+    // the uploaded block keeps the caller's order [k][bundle_idx]; the plan addresses sources by sorted rank
+    std::vector<uint32_t> sorted(want.begin(), want.end());
+    const size_t ct_words = (size_t)2 * ctx.first_L * ctx.N, row = (size_t)p.bundle_idx_count * ct_words;
+    for (uint32_t k = 0; k < nsrc; k++) {
+        uint32_t rank = (uint32_t)(std::lower_bound(sorted.begin(), sorted.end(), src_powers[k]) - sorted.begin());
+        const u64 *src = (const u64 *)cts + (size_t)k * row;
+        u64 *dst = arena_.buf.p + (size_t)query_region_ * ctx.N + (size_t)rank * row;
+        APSU_CUDA_CHECK(cudaMemcpyAsync(dst, src, row * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
+    }
+    query_loaded_ = true;
+    powers_done_ = eval_done_ = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: arena layout + the two kernel programs.  Depends on the parameter set and on which
+// BinBundles exist, so it is rebuilt lazily after DB changes.
+// ------------------------------------------------------------------------------------------------
+void Engine::build_plan()
+{
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    const apsu_b200_params &p = ctx.params;
+    const uint32_t N = ctx.N, bic = p.bundle_idx_count, Lf = ctx.first_L, Ll = ctx.low_L, Lh = ctx.high_L;
+    const uint32_t ps = p.ps_low_degree, h = ps + 1;
+    const uint32_t Sf = (uint32_t)ctx.level[Lf].S, LSf = Lf + Sf;
+    const uint32_t Sh = (uint32_t)ctx.level[Lh].S, LSh = Lh + Sh;
+    arena_.top = 0;
+    arena_.high_water = 0;
+    idx_.clear();
+    desc_host_.clear();
+    powers_prog_.clear();
+    eval_prog_.clear();
+    mac_step_bytes_.clear();
+
+    const std::set<uint32_t> &targets = dag.target_powers();
+    std::vector<uint32_t> sources(p.query_powers, p.query_powers + p.query_power_count);
+    const uint32_t nsrc = (uint32_t)sources.size();
+    std::vector<bool> active(bic);
+    for (uint32_t b = 0; b < bic; b++) active[b] = !db[b].empty(); // receiver_ddh.cpp:399-402
+
+    // ---- persistent regions ----
+    query_region_ = arena_.take((size_t)nsrc * bic * 2 * Lf);
+    const uint32_t maxp = p.max_items_per_bin;
+    std::vector<std::vector<uint32_t>> loc(bic, std::vector<uint32_t>(maxp + 1, kNoSrc)); // [2][Lf][N] at first level
+    for (uint32_t k = 0; k < nsrc; k++)
+        for (uint32_t b = 0; b < bic; b++) loc[b][sources[k]] = query_region_ + (k * bic + b) * 2 * Lf;
+    std::set<uint32_t> parents;
+    for (uint32_t e : targets) {
+        const PowersNode &nd = dag.node(e);
+        if (nd.is_source()) continue;
+        parents.insert(nd.parent1);
+        parents.insert(nd.parent2);
+        for (uint32_t b = 0; b < bic; b++)
+            if (active[b]) loc[b][e] = arena_.take(2 * Lf);
+    }
+    std::vector<std::map<uint32_t, uint32_t>> ext_loc(bic);
+    for (uint32_t b = 0; b < bic; b++)
+        if (active[b])
+            for (uint32_t e : parents) ext_loc[b][e] = arena_.take(2 * LSf);
+
+    // final powers as the evaluation reads them
+    const uint32_t nlow = ps ? ps : maxp;          // powers 1..nlow in NTT form at the low level
+    const uint32_t nhigh = ps ? maxp / h : 0;      // powers h, 2h, .. in coefficient form at the high level
+    std::vector<uint32_t> low_base(bic, kNoSrc), highext_base(bic, kNoSrc);
+    std::vector<std::vector<uint32_t>> highc_loc(bic, std::vector<uint32_t>(nhigh + 1, kNoSrc));
+    for (uint32_t b = 0; b < bic; b++) {
+        if (!active[b]) continue;
+        low_base[b] = arena_.take((size_t)nlow * 2 * Ll);
+        if (nhigh) highext_base[b] = arena_.take((size_t)nhigh * 2 * LSh);
+    }
+    final_power_.assign(bic, std::vector<PowerLoc>(maxp + 1));
+
+    const uint32_t persistent_top = (uint32_t)arena_.top;
+
+    // ---- ComputePowers program (receiver_ddh.cpp:390-483) ----
+    {
+        ProgramBuilder pb(*this, powers_prog_);
+        std::set<uint32_t> extended;
+        auto levels = dag.levels();
+        for (uint32_t d = 1; d < levels.size(); d++) {
+            arena_.top = persistent_top;
+            std::vector<uint32_t> ext_cts, ext_dst, a, bb, prod, dst;
+            std::set<uint32_t> need;
+            for (auto &nd : levels[d]) {
+                if (!extended.count(nd.parent1)) need.insert(nd.parent1);
+                if (!extended.count(nd.parent2)) need.insert(nd.parent2);
+            }
+            for (uint32_t b = 0; b < bic; b++) {
+                if (!active[b]) continue;
+                for (uint32_t e : need) {
+                    ext_cts.push_back(loc[b][e]);
+                    ext_dst.push_back(ext_loc[b][e]);
+                }
+            }
+            extended.insert(need.begin(), need.end());
+            uint32_t n_ops = 0;
+            for (uint32_t b = 0; b < bic; b++)
+                if (active[b]) n_ops += (uint32_t)levels[d].size();
+            uint32_t prod0 = arena_.take((size_t)n_ops * 3 * Lf);
+            uint32_t mscr = arena_.take(ProgramBuilder::multiply_scratch(ctx, Lf, n_ops));
+            uint32_t rscr = arena_.take(ProgramBuilder::relin_scratch(Lf, n_ops));
+            uint32_t o = 0;
+            for (uint32_t b = 0; b < bic; b++) {
+                if (!active[b]) continue;
+                for (auto &nd : levels[d]) {
+                    a.push_back(ext_loc[b][nd.parent1]);
+                    bb.push_back(ext_loc[b][nd.parent2]);
+                    prod.push_back(prod0 + o * 3 * Lf);
+                    dst.push_back(loc[b][nd.power]);
+                    o++;
+                }
+            }
+            pb.extend(Lf, ext_cts, ext_dst);
+            pb.multiply(Lf, a, bb, prod, mscr);
+            pb.relinearize(Lf, prod, dst, rscr); // relinearize == using_keyswitching (checked in ctor)
+        }
+        // tail: mod-switch every target to its level; low powers to NTT form (:446-478)
+        arena_.top = persistent_top;
+        std::vector<uint32_t> ntt_src, ntt_dst, hx_cts, hx_dst;
+        // cur[b][e] = (arena idx, level) while switching down
+        struct Cur {
+            uint32_t idx, L, b, e, target_L;
+            bool low;
+        };
+        std::vector<Cur> curs;
+        for (uint32_t b = 0; b < bic; b++) {
+            if (!active[b]) continue;
+            for (uint32_t e : targets) {
+                bool low = !ps || e <= ps;
+                curs.push_back(Cur{ loc[b][e], Lf, b, e, low ? Ll : Lh, low });
+            }
+        }
+        for (uint32_t L = Lf; L > 1; L--) {
+            std::vector<uint32_t> ms_src, ms_dst;
+            for (auto &c : curs) {
+                if (c.L != L || c.target_L >= L) continue;
+                uint32_t nxt = arena_.take(2 * (L - 1));
+                for (uint32_t comp = 0; comp < 2; comp++) {
+                    ms_src.push_back(c.idx + comp * L);
+                    ms_dst.push_back(nxt + comp * (L - 1));
+                }
+                c.idx = nxt;
+                c.L = L - 1;
+            }
+            pb.mod_switch_next(L, ms_src, ms_dst);
+        }
+        // note: the switched-down high powers live in the scratch area above persistent_top; everything the
+        // evaluation needs from them (extended NTT forms) is produced below, before eval scratch reuses it —
+        // except the coefficient-form high powers themselves, which no later step reads.
+        for (auto &c : curs) {
+            PowerLoc &fl = final_power_[c.b][c.e];
+            fl.valid = true;
+            fl.L = c.L;
+            if (c.low) {
+                uint32_t dstp = low_base[c.b] + (c.e - 1) * 2 * Ll;
+                for (uint32_t k = 0; k < 2 * Ll; k++) {
+                    ntt_src.push_back(c.idx + k);
+                    ntt_dst.push_back(dstp + k);
+                }
+                fl.idx = dstp;
+                fl.ntt = true;
+            } else {
+                uint32_t i = c.e / h;
+                highc_loc[c.b][i] = c.idx;
+                hx_cts.push_back(c.idx);
+                hx_dst.push_back(highext_base[c.b] + (i - 1) * 2 * LSh);
+                fl.idx = c.idx;
+                fl.ntt = false;
+            }
+        }
+        pb.ntt(ntt_src, ntt_dst, ctx.pattern_q(Ll), false);
+        pb.extend(Lh, hx_cts, hx_dst);
+    }
+    const uint32_t powers_top = (uint32_t)arena_.high_water;
+    // coefficient-form high powers must survive for get_power(); keep eval scratch above the powers scratch
+    // only if they were produced by a mod-switch (otherwise they alias persistent memory).
+    const uint32_t eval_base = (Lf != Lh && nhigh) ? powers_top : persistent_top;
+
+    // ---- evaluation program (receiver_ddh.cpp:485-535, bin_bundle.cpp:106-360) ----
+    {
+        ProgramBuilder pb(*this, eval_prog_);
+        result_order_.clear();
+        struct BRef {
+            BinBundleStore *s;
+            uint32_t k; // result slot
+        };
+        std::vector<BRef> all;
+        for (uint32_t b = 0; b < bic; b++)
+            for (auto &s : db[b]) {
+                all.push_back(BRef{ s.get(), (uint32_t)result_order_.size() });
+                result_order_.emplace_back(b, s->cache_idx);
+            }
+        results_.ensure((size_t)all.size() * 2 * N);
+        uint32_t alpha_max = 0;
+        for (auto &v : db) alpha_max = std::max<uint32_t>(alpha_max, (uint32_t)v.size());
+        npack_needed_ = alpha_max * bic;
+
+        uint32_t chunk = 2;
+        if (const char *ev = std::getenv("APSU_B200_CHUNK")) chunk = (uint32_t)std::max(1, atoi(ev));
+        const uint32_t drops = Ll - Lh;
+        uint32_t lazy_bound = 0xFFFFFFFFu;
+        {
+            int maxbits = 0;
+            for (uint32_t j = 0; j < Ll; j++) maxbits = std::max(maxbits, hm::bit_length(p.coeff_modulus[j]));
+            int room = 128 - 2 * maxbits;
+            if (room < 31) lazy_bound = 1u << room;
+        }
+
+        for (size_t c0 = 0; c0 < all.size(); c0 += chunk) {
+            arena_.top = eval_base;
+            size_t c1 = std::min(all.size(), c0 + chunk);
+            std::vector<FinalizeJob> fin_direct, fin_ps;
+            std::vector<MacGroup> groups;     // stage A (low level)
+            std::vector<MacGroup> k8groups;   // K8 (high level)
+            std::vector<MulTermsJob> mulj;
+            uint64_t mac_bytes = 0;
+
+            struct Job {
+                BinBundleStore *s;
+                uint32_t bslot; // PS bundle slot within the chunk
+                uint32_t i, nterms;
+            };
+            std::vector<Job> jobs;                 // PS inner polynomials i >= 1
+            std::vector<BRef> psb, direct;         // PS bundles / direct-evaluation bundles
+            for (size_t k = c0; k < c1; k++) {
+                uint32_t degree = all[k].s->ncoeffs - 1;
+                bool using_ps = ps > 1 && ps < degree; // receiver_ddh.cpp:515-517
+                (using_ps ? psb : direct).push_back(all[k]);
+            }
+            // -------- direct evaluation (bin_bundle.cpp:106-174) --------
+            // MAC over degrees 1..D, iNTT, finalize
+            const uint32_t acc0 = arena_.take((size_t)direct.size() * 2 * Ll);
+            auto add_job = [&](std::vector<MacGroup> &gs, uint32_t pow_idx, uint32_t tstride, uint32_t cstride, const u64 *coeff, uint32_t nterms, uint32_t out) {
+                if (gs.empty() || gs.back().njobs == kMacJobs || gs.back().pow_idx != pow_idx) {
+                    MacGroup g;
+                    std::memset(&g, 0, sizeof(g));
+                    g.pow_idx = pow_idx;
+                    g.pow_term_stride = tstride;
+                    g.pow_comp_stride = cstride;
+                    gs.push_back(g);
+                }
+                MacGroup &g = gs.back();
+                g.coeff[g.njobs] = coeff;
+                g.nterms[g.njobs] = nterms;
+                g.out_idx[g.njobs] = out;
+                g.njobs++;
+                g.max_terms = std::max(g.max_terms, nterms);
+            };
+            for (size_t k = 0; k < direct.size(); k++) {
+                BinBundleStore *s = direct[k].s;
+                uint32_t degree = s->ncoeffs - 1;
+                if (degree > nlow) throw std::logic_error("not enough ciphertext powers available");
+                uint32_t out = acc0 + (uint32_t)k * 2 * Ll;
+                // degree 0: the accumulator is the zero ciphertext (a job with no terms writes zeros)
+                add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, s->ntt_coeffs.p, degree, out);
+                mac_bytes += (uint64_t)degree * Ll * N * 8;
+                FinalizeJob f;
+                std::memset(&f, 0, sizeof(f));
+                f.src[0] = out;
+                f.src[1] = f.src[2] = kNoSrc;
+                f.coeff0 = s->plain_coeffs.p;
+                f.pack = s->bundle_idx + s->cache_idx * bic;
+                f.slot = direct[k].k;
+                fin_direct.push_back(f);
+            }
+            // -------- Paterson-Stockmeyer (bin_bundle.cpp:192-360) --------
+            for (size_t k = 0; k < psb.size(); k++) {
+                uint32_t degree = psb[k].s->ncoeffs - 1, H = degree / h, rem = degree % h;
+                for (uint32_t i = 1; i < H; i++) jobs.push_back(Job{ psb[k].s, (uint32_t)k, i, h - 1 });
+                if (rem) jobs.push_back(Job{ psb[k].s, (uint32_t)k, H, rem });
+            }
+            const uint32_t nj = (uint32_t)jobs.size(), nb = (uint32_t)psb.size();
+            // contiguous low-level region: TIN[job][2][Ll], then R0[bundle][2][Ll] (drops==0) or T0[bundle][ps][2][Ll]
+            const uint32_t tin0 = arena_.take((size_t)nj * 2 * Ll);
+            const uint32_t r00 = arena_.take(drops ? (size_t)nb * ps * 2 * Ll : (size_t)nb * 2 * Ll);
+            const uint32_t low_run_first = acc0, low_run_count = (uint32_t)(arena_.top - acc0);
+            for (uint32_t j = 0; j < nj; j++) {
+                BinBundleStore *s = jobs[j].s;
+                // NTT-form rank of degree i*h + 1 is i*(h-1)
+                const u64 *coeff = s->ntt_coeffs.p + (size_t)jobs[j].i * (h - 1) * Ll * N;
+                add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, coeff, jobs[j].nterms, tin0 + j * 2 * Ll);
+                mac_bytes += (uint64_t)jobs[j].nterms * Ll * N * 8;
+            }
+            for (uint32_t k = 0; k < nb; k++) {
+                BinBundleStore *s = psb[k].s;
+                if (!drops) {
+                    add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, s->ntt_coeffs.p, ps, r00 + k * 2 * Ll);
+                } else {
+                    MulTermsJob mj;
+                    std::memset(&mj, 0, sizeof(mj));
+                    mj.coeff = s->ntt_coeffs.p;
+                    mj.out_idx = r00 + k * ps * 2 * Ll;
+                    mj.pow_idx = low_base[s->bundle_idx];
+                    mj.pow_term_stride = 2 * Ll;
+                    mj.pow_comp_stride = Ll;
+                    mj.nterms = ps;
+                    mulj.push_back(mj);
+                }
+                mac_bytes += (uint64_t)ps * Ll * N * 8;
+            }
+            // stage A launch
+            emit_mac(pb, Ll, groups, lazy_bound, mac_bytes);
+            emit_mul_terms(pb, Ll, mulj, ps);
+            // stage B: back to coefficient form
+            pb.ntt_run(low_run_first, low_run_count, ctx.pattern_q(Ll), true);
+
+            if (nb) {
+                // stage C: to the high level
+                uint32_t tinh0 = tin0, r0h0 = r00;
+                std::vector<uint32_t> tinh(nj), r0h(nb);
+                if (drops) {
+                    if (drops != 1) throw std::logic_error("unexpected level gap between low and high powers");
+                    tinh0 = arena_.take((size_t)nj * 2 * Lh);
+                    uint32_t t0h0 = arena_.take((size_t)nb * ps * 2 * Lh);
+                    r0h0 = arena_.take((size_t)nb * 2 * Lh);
+                    std::vector<uint32_t> ms_src, ms_dst;
+                    for (uint32_t j = 0; j < nj; j++)
+                        for (uint32_t c = 0; c < 2; c++) {
+                            ms_src.push_back(tin0 + (j * 2 + c) * Ll);
+                            ms_dst.push_back(tinh0 + (j * 2 + c) * Lh);
+                        }
+                    for (uint32_t k = 0; k < nb * ps; k++)
+                        for (uint32_t c = 0; c < 2; c++) {
+                            ms_src.push_back(r00 + (k * 2 + c) * Ll);
+                            ms_dst.push_back(t0h0 + (k * 2 + c) * Lh);
+                        }
+                    pb.mod_switch_next(Ll, ms_src, ms_dst);
+                    std::vector<std::vector<uint32_t>> terms;
+                    std::vector<uint32_t> sdst;
+                    for (uint32_t k = 0; k < nb; k++)
+                        for (uint32_t c = 0; c < 2; c++) {
+                            std::vector<uint32_t> tl;
+                            for (uint32_t j = 0; j < ps; j++) tl.push_back(t0h0 + ((k * ps + j) * 2 + c) * Lh);
+                            terms.push_back(tl);
+                            sdst.push_back(r0h0 + (k * 2 + c) * Lh);
+                        }
+                    pb.sum_polys(Lh, terms, sdst);
+                }
+                for (uint32_t j = 0; j < nj; j++) tinh[j] = tinh0 + j * 2 * Lh;
+                for (uint32_t k = 0; k < nb; k++) r0h[k] = r0h0 + k * 2 * Lh;
+                // stage D/E: inner polynomial x high power
+                const uint32_t ext0 = arena_.take((size_t)nj * 2 * LSh);
+                const uint32_t prod0 = arena_.take((size_t)nj * 3 * Lh);
+                const uint32_t mscr = arena_.take(ProgramBuilder::multiply_scratch(ctx, Lh, nj));
+                std::vector<uint32_t> exts(nj), hp(nj), prods(nj);
+                for (uint32_t j = 0; j < nj; j++) {
+                    exts[j] = ext0 + j * 2 * LSh;
+                    prods[j] = prod0 + j * 3 * Lh;
+                    hp[j] = highext_base[jobs[j].s->bundle_idx] + (jobs[j].i - 1) * 2 * LSh;
+                }
+                pb.extend(Lh, tinh, exts);
+                pb.multiply(Lh, exts, hp, prods, mscr);
+                // stage F: sum of the products per bundle (size 3)
+                const uint32_t res30 = arena_.take((size_t)nb * 3 * Lh), res20 = arena_.take((size_t)nb * 2 * Lh);
+                {
+                    std::vector<std::vector<uint32_t>> terms(nb * 3);
+                    std::vector<uint32_t> sdst(nb * 3);
+                    for (uint32_t k = 0; k < nb; k++)
+                        for (uint32_t c = 0; c < 3; c++) sdst[k * 3 + c] = res30 + (k * 3 + c) * Lh;
+                    for (uint32_t j = 0; j < nj; j++)
+                        for (uint32_t c = 0; c < 3; c++) terms[jobs[j].bslot * 3 + c].push_back(prods[j] + c * Lh);
+                    pb.sum_polys(Lh, terms, sdst);
+                }
+                // stage G: one relinearisation per bundle
+                std::vector<uint32_t> res3(nb), res2(nb);
+                for (uint32_t k = 0; k < nb; k++) res3[k] = res30 + k * 3 * Lh, res2[k] = res20 + k * 2 * Lh;
+                const uint32_t rscr = arena_.take(ProgramBuilder::relin_scratch(Lh, nb));
+                pb.relinearize(Lh, res3, res2, rscr);
+                // stage H: constant coefficients of the inner polynomials x high powers (coefficient-form
+                // operands): accumulate in NTT form at the high level, one inverse transform per bundle
+                const uint32_t k80 = arena_.take((size_t)nb * 2 * Lh);
+                for (uint32_t k = 0; k < nb; k++) {
+                    BinBundleStore *s = psb[k].s;
+                    uint32_t H = (s->ncoeffs - 1) / h;
+                    add_job(k8groups, highext_base[s->bundle_idx], 2 * LSh, LSh, s->plain_high_ntt.p, H, k80 + k * 2 * Lh);
+                }
+                emit_mac(pb, Lh, k8groups, lazy_bound, 0);
+                pb.ntt_run(k80, nb * 2 * Lh, ctx.pattern_q(Lh), true);
+                for (uint32_t k = 0; k < nb; k++) {
+                    FinalizeJob f;
+                    std::memset(&f, 0, sizeof(f));
+                    f.src[0] = res2[k];
+                    f.src[1] = r0h[k];
+                    f.src[2] = k80 + k * 2 * Lh;
+                    f.coeff0 = psb[k].s->plain_coeffs.p;
+                    f.pack = psb[k].s->bundle_idx + psb[k].s->cache_idx * bic;
+                    f.slot = psb[k].k;
+                    fin_ps.push_back(f);
+                }
+            }
+            emit_finalize(pb, Ll, fin_direct);
+            emit_finalize(pb, Lh, fin_ps);
+        }
+    }
+
+    arena_.buf.ensure(arena_.high_water * (size_t)N);
+    idx_.upload(ctx.stream);
+    desc_dev_.upload(desc_host_, ctx.stream);
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    plan_valid_ = true;
+    query_loaded_ = powers_done_ = eval_done_ = false;
+}
+
+size_t Engine::add_desc(const void *data, size_t bytes)
+{
+    size_t off = (desc_host_.size() + 15) & ~size_t(15);
+    desc_host_.resize(off + bytes);
+    std::memcpy(desc_host_.data() + off, data, bytes);
+    return off;
+}
+
+void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &groups, uint32_t lazy_bound, uint64_t bytes)
+{
+    if (groups.empty()) return;
+    size_t off = add_desc(groups.data(), groups.size() * sizeof(MacGroup));
+    uint32_t n = (uint32_t)groups.size();
+    groups.clear();
+    size_t slot = mac_step_bytes_.size();
+    mac_step_bytes_.push_back(bytes);
+    pb.step([=] {
+        const bool timed = profiling && mac_step_bytes_[slot] > 0;
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (timed) {
+            if (mac_events_used_ == mac_events_.size()) {
+                cudaEvent_t x, y;
+                APSU_CUDA_CHECK(cudaEventCreate(&x));
+                APSU_CUDA_CHECK(cudaEventCreate(&y));
+                mac_events_.emplace_back(x, y);
+            }
+            a = mac_events_[mac_events_used_].first;
+            b = mac_events_[mac_events_used_].second;
+            mac_events_used_++;
+            APSU_CUDA_CHECK(cudaEventRecord(a, ctx.stream));
+        }
+        k_db_mac<<<dim3(L * ctx.N / kMacThreads, n), kMacThreads, 0, ctx.stream>>>(
+            arena_.buf.p, reinterpret_cast<const MacGroup *>(desc_dev_.p + off), ctx.level[L], (int)ctx.N, lazy_bound);
+        APSU_CUDA_CHECK(cudaGetLastError());
+        ctx.launches++;
+        if (timed) {
+            APSU_CUDA_CHECK(cudaEventRecord(b, ctx.stream));
+            timed_mac_bytes_ += mac_step_bytes_[slot];
+        }
+    });
+}
+
+void Engine::emit_mul_terms(ProgramBuilder &pb, uint32_t L, std::vector<MulTermsJob> &jobs, uint32_t nterms)
+{
+    if (jobs.empty()) return;
+    size_t off = add_desc(jobs.data(), jobs.size() * sizeof(MulTermsJob));
+    uint32_t n = (uint32_t)jobs.size();
+    jobs.clear();
+    pb.step([=] {
+        k_db_mul<<<dim3(L * ctx.N / kMacThreads, nterms, n), kMacThreads, 0, ctx.stream>>>(
+            arena_.buf.p, reinterpret_cast<const MulTermsJob *>(desc_dev_.p + off), ctx.level[L], (int)ctx.N);
+        APSU_CUDA_CHECK(cudaGetLastError());
+        ctx.launches++;
+    });
+}
+
+void Engine::emit_finalize(ProgramBuilder &pb, uint32_t Ls, std::vector<FinalizeJob> &jobs)
+{
+    if (jobs.empty()) return;
+    const apsu_b200_params &p = ctx.params;
+    size_t off = add_desc(jobs.data(), jobs.size() * sizeof(FinalizeJob));
+    uint32_t n = (uint32_t)jobs.size();
+    jobs.clear();
+    // try_clear_irrelevant_bits (bin_bundle.cpp:67-97): the last level always has exactly one prime
+    int keep = hm::bit_length(ctx.t) + ((int)ctx.logN + 1) - 1;
+    int drop = hm::bit_length(p.coeff_modulus[0]) - keep;
+    u64 clear_mask = drop > 0 ? ~((1ull << drop) - 1) : ~0ull;
+    pb.step([=] {
+        k_finalize<<<dim3(ctx.N / kEwThreads, 2, n), kEwThreads, 0, ctx.stream>>>(
+            arena_.buf.p, reinterpret_cast<const FinalizeJob *>(desc_dev_.p + off), levels_dev_.p, masks_.p, results_.p, (int)Ls, ctx.t,
+            clear_mask, (int)ctx.N);
+        APSU_CUDA_CHECK(cudaGetLastError());
+        ctx.launches++;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// running the programs
+// ------------------------------------------------------------------------------------------------
+void Engine::compute_powers()
+{
+    if (!plan_valid_ || !query_loaded_) throw std::logic_error("compute_powers called before query_begin (or the DB changed since)");
+    if (ctx.using_keyswitching() && dag.depth() > 0 && !have_keys_) throw std::invalid_argument("relinearization keys have not been set");
+    ctx.launches = 0;
+    APSU_CUDA_CHECK(cudaEventRecord(ev_[0], ctx.stream));
+    for (auto &s : powers_prog_) s.run();
+    APSU_CUDA_CHECK(cudaEventRecord(ev_[1], ctx.stream));
+    powers_done_ = true;
+    eval_done_ = false;
+    powers_launches_ = ctx.launches;
+}
+
+void Engine::eval_all()
+{
+    if (!plan_valid_ || !powers_done_) throw std::logic_error("eval_all called before compute_powers");
+    if (npack_ < npack_needed_) throw std::invalid_argument("mask table is smaller than alpha_max_cache_count * bundle_idx_count");
+    ctx.launches = 0;
+    mac_events_used_ = 0;
+    timed_mac_bytes_ = 0;
+    APSU_CUDA_CHECK(cudaEventRecord(ev_[2], ctx.stream));
+    for (auto &s : eval_prog_) s.run();
+    APSU_CUDA_CHECK(cudaEventRecord(ev_[3], ctx.stream));
+    eval_done_ = true;
+    eval_launches_ = ctx.launches;
+}
+
+void Engine::collect_timings()
+{
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    std::memset(&timings, 0, sizeof(timings));
+    if (powers_done_) {
+        float ms = 0;
+        APSU_CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+        timings.compute_powers_ms = ms;
+    }
+    if (eval_done_) {
+        float ms = 0;
+        APSU_CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
+        timings.eval_ms = ms;
+        float mac = 0;
+        for (size_t k = 0; k < mac_events_used_; k++) {
+            float x = 0;
+            APSU_CUDA_CHECK(cudaEventElapsedTime(&x, mac_events_[k].first, mac_events_[k].second));
+            mac += x;
+        }
+        timings.db_stream_ms = mac;
+        timings.db_stream_bytes = timed_mac_bytes_;
+        timings.db_stream_launches = (uint32_t)mac_events_used_;
+    }
+    timings.kernel_launches = powers_launches_ + eval_launches_;
+}
+
+void Engine::fetch_results(uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx)
+{
+    if (!eval_done_) throw std::logic_error("fetch_results called before eval_all");
+    size_t n = result_order_.size();
+    if (out && n) APSU_CUDA_CHECK(cudaMemcpyAsync(out, results_.p, n * 2 * ctx.N * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    for (size_t k = 0; k < n; k++) {
+        if (bundle_idx) bundle_idx[k] = result_order_[k].first;
+        if (cache_idx) cache_idx[k] = result_order_[k].second;
+    }
+}
+
+void Engine::results_device(void **ptr, uint64_t *bytes)
+{
+    if (!plan_valid_) build_plan();
+    if (ptr) *ptr = results_.p;
+    if (bytes) *bytes = (uint64_t)result_order_.size() * 2 * ctx.N * 8;
+}
+
+void Engine::get_power(uint32_t bundle_idx, uint32_t power, uint64_t *out, uint32_t *L, int *is_ntt)
+{
+    if (!powers_done_) throw std::logic_error("get_power called before compute_powers");
+    if (bundle_idx >= final_power_.size() || power >= final_power_[bundle_idx].size() || !final_power_[bundle_idx][power].valid)
+        throw std::invalid_argument("power is not available");
+    const PowerLoc &pl = final_power_[bundle_idx][power];
+    if (L) *L = pl.L;
+    if (is_ntt) *is_ntt = pl.ntt ? 1 : 0;
+    if (out) {
+        APSU_CUDA_CHECK(cudaMemcpyAsync(out, arena_.buf.p + (size_t)pl.idx * ctx.N, (size_t)2 * pl.L * ctx.N * 8, cudaMemcpyDeviceToHost, ctx.stream));
+        APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone batched evaluator operations (tests, and the "SEAL Evaluator calls" row of the scope)
+// ------------------------------------------------------------------------------------------------
+void Engine::op_ntt(uint64_t *polys, uint32_t count, const uint32_t *modulus_index, uint32_t pattern_len, bool inverse)
+{
+    if (!polys || !modulus_index || !pattern_len) throw std::invalid_argument("op_ntt: bad arguments");
+    std::vector<uint32_t> pattern(modulus_index, modulus_index + pattern_len);
+    DBuf<u64> buf;
+    buf.alloc((size_t)count * ctx.N);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(buf.p, polys, buf.n * 8, cudaMemcpyHostToDevice, ctx.stream));
+    ctx.ntt(buf.p, buf.p, count, pattern, inverse);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(polys, buf.p, buf.n * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+
+template <typename Build>
+void Engine::run_scratch_program(Build &&build)
+{
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    Arena saved_arena = std::move(arena_);
+    IdxPool saved_idx = std::move(idx_);
+    arena_ = Arena();
+    idx_ = IdxPool();
+    std::vector<Step> prog;
+    try {
+        build(prog);
+    } catch (...) {
+        arena_ = std::move(saved_arena);
+        idx_ = std::move(saved_idx);
+        throw;
+    }
+    arena_ = std::move(saved_arena);
+    idx_ = std::move(saved_idx);
+}
+
+void Engine::op_multiply(uint32_t L, const uint64_t *a, const uint64_t *b, uint64_t *out, uint32_t n_ops)
+{
+    if (L < 1 || L > ctx.first_L) throw std::invalid_argument("op_multiply: level is out of range");
+    if (!a || !b || !out || !n_ops) throw std::invalid_argument("op_multiply: bad arguments");
+    const uint32_t N = ctx.N, LS = L + (uint32_t)ctx.level[L].S;
+    run_scratch_program([&](std::vector<Step> &prog) {
+        ProgramBuilder pb(*this, prog);
+        uint32_t a0 = arena_.take((size_t)n_ops * 2 * L), b0 = arena_.take((size_t)n_ops * 2 * L);
+        uint32_t ea = arena_.take((size_t)n_ops * 2 * LS), eb = arena_.take((size_t)n_ops * 2 * LS);
+        uint32_t pr = arena_.take((size_t)n_ops * 3 * L);
+        uint32_t scr = arena_.take(ProgramBuilder::multiply_scratch(ctx, L, n_ops));
+        std::vector<uint32_t> cts, exts, av, bv, pv;
+        for (uint32_t o = 0; o < n_ops; o++) {
+            cts.push_back(a0 + o * 2 * L);
+            exts.push_back(ea + o * 2 * LS);
+            av.push_back(ea + o * 2 * LS);
+            bv.push_back(eb + o * 2 * LS);
+            pv.push_back(pr + o * 3 * L);
+        }
+        for (uint32_t o = 0; o < n_ops; o++) {
+            cts.push_back(b0 + o * 2 * L);
+            exts.push_back(eb + o * 2 * LS);
+        }
+        pb.extend(L, cts, exts);
+        pb.multiply(L, av, bv, pv, scr);
+        arena_.buf.alloc(arena_.high_water * (size_t)N);
+        idx_.upload(ctx.stream);
+        size_t w = (size_t)n_ops * 2 * L * N;
+        APSU_CUDA_CHECK(cudaMemcpyAsync(arena_.buf.p + (size_t)a0 * N, a, w * 8, cudaMemcpyHostToDevice, ctx.stream));
+        APSU_CUDA_CHECK(cudaMemcpyAsync(arena_.buf.p + (size_t)b0 * N, b, w * 8, cudaMemcpyHostToDevice, ctx.stream));
+        for (auto &s : prog) s.run();
+        APSU_CUDA_CHECK(cudaMemcpyAsync(out, arena_.buf.p + (size_t)pr * N, (size_t)n_ops * 3 * L * N * 8, cudaMemcpyDeviceToHost, ctx.stream));
+        APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    });
+}
+
+void Engine::op_relinearize(uint32_t L, const uint64_t *in, uint64_t *out, uint32_t n_ops)
+{
+    if (L < 1 || L > ctx.first_L) throw std::invalid_argument("op_relinearize: level is out of range");
+    if (!ctx.using_keyswitching()) throw std::logic_error("parameters do not support key switching");
+    if (!have_keys_) throw std::invalid_argument("relinearization keys have not been set");
+    if (!in || !out || !n_ops) throw std::invalid_argument("op_relinearize: bad arguments");
+    const uint32_t N = ctx.N;
+    run_scratch_program([&](std::vector<Step> &prog) {
+        ProgramBuilder pb(*this, prog);
+        uint32_t i0 = arena_.take((size_t)n_ops * 3 * L), o0 = arena_.take((size_t)n_ops * 2 * L);
+        uint32_t scr = arena_.take(ProgramBuilder::relin_scratch(L, n_ops));
+        std::vector<uint32_t> iv, ov;
+        for (uint32_t o = 0; o < n_ops; o++) iv.push_back(i0 + o * 3 * L), ov.push_back(o0 + o * 2 * L);
+        pb.relinearize(L, iv, ov, scr);
+        arena_.buf.alloc(arena_.high_water * (size_t)N);
+        idx_.upload(ctx.stream);
+        APSU_CUDA_CHECK(cudaMemcpyAsync(arena_.buf.p + (size_t)i0 * N, in, (size_t)n_ops * 3 * L * N * 8, cudaMemcpyHostToDevice, ctx.stream));
+        for (auto &s : prog) s.run();
+        APSU_CUDA_CHECK(cudaMemcpyAsync(out, arena_.buf.p + (size_t)o0 * N, (size_t)n_ops * 2 * L * N * 8, cudaMemcpyDeviceToHost, ctx.stream));
+        APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    });
+}
+
+void Engine::op_mod_switch_next(uint32_t L, const uint64_t *in, uint64_t *out, uint32_t n_polys)
+{
+    if (L < 2 || L > ctx.first_L) throw std::invalid_argument("op_mod_switch_next: level is out of range");
+    if (!in || !out || !n_polys) throw std::invalid_argument("op_mod_switch_next: bad arguments");
+    const uint32_t N = ctx.N;
+    run_scratch_program([&](std::vector<Step> &prog) {
+        ProgramBuilder pb(*this, prog);
+        uint32_t i0 = arena_.take((size_t)n_polys * L), o0 = arena_.take((size_t)n_polys * (L - 1));
+        std::vector<uint32_t> iv, ov;
+        for (uint32_t k = 0; k < n_polys; k++) iv.push_back(i0 + k * L), ov.push_back(o0 + k * (L - 1));
+        pb.mod_switch_next(L, iv, ov);
+        arena_.buf.alloc(arena_.high_water * (size_t)N);
+        idx_.upload(ctx.stream);
+        APSU_CUDA_CHECK(cudaMemcpyAsync(arena_.buf.p + (size_t)i0 * N, in, (size_t)n_polys * L * N * 8, cudaMemcpyHostToDevice, ctx.stream));
+        for (auto &s : prog) s.run();
+        APSU_CUDA_CHECK(cudaMemcpyAsync(out, arena_.buf.p + (size_t)o0 * N, (size_t)n_polys * (L - 1) * N * 8, cudaMemcpyDeviceToHost, ctx.stream));
+        APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    });
+}
+
+} // namespace apsu_b200

@@ -1,0 +1,161 @@
+// Engine: device-resident ReceiverDB + the query-evaluation programs (ComputePowers and
+// eval/eval_patstock for every BinBundle) of one APSU receiver on one B200.
+// Reference: receiver/apsu/receiver_ddh.cpp:295-369, 390-535; receiver/apsu/bin_bundle.cpp:106-360.
+#pragma once
+#include "context.hpp"
+#include <functional>
+#include <memory>
+
+namespace apsu_b200 {
+
+struct ProgramBuilder;
+struct MacGroup;
+struct MulTermsJob;
+struct FinalizeJob;
+
+// 32-bit index arrays used by the kernels; collected on the host while a program is built and uploaded
+// in one copy.  Handles are offsets into the pool.
+struct IdxPool {
+    std::vector<uint32_t> host;
+    DBuf<uint32_t> dev;
+    size_t add(const std::vector<uint32_t> &v)
+    {
+        size_t off = host.size();
+        host.insert(host.end(), v.begin(), v.end());
+        return off;
+    }
+    void upload(cudaStream_t st) { dev.upload(host, st); }
+    const uint32_t *at(size_t off) const { return dev.p + off; }
+    void clear() { host.clear(); }
+};
+
+// bump allocator over the polynomial arena (units: one polynomial of N words)
+struct Arena {
+    DBuf<u64> buf;
+    size_t top = 0, high_water = 0;
+    uint32_t take(size_t polys)
+    {
+        size_t at = top;
+        top += polys;
+        if (top > high_water) high_water = top;
+        if (top >= (1ull << 32)) throw std::runtime_error("polynomial arena exceeds 2^32 polynomials");
+        return (uint32_t)at;
+    }
+};
+
+struct BinBundleStore {
+    uint32_t bundle_idx = 0, cache_idx = 0;
+    uint32_t ncoeffs = 0;
+    // NTT-form plaintexts, packed in degree order (coefficient-form degrees skipped): [n_ntt][low_L][N]
+    DBuf<u64> ntt_coeffs;
+    // coefficient-form plaintexts (degree 0 and, with PS, multiples of ps_low+1): [n_plain][N]
+    DBuf<u64> plain_coeffs;
+    // PS only: the coefficient-form plaintexts of degree i*(ps_low+1), i>=1, lifted and NTT'd at the high
+    // level once at upload (multiply_plain on coefficient-form operands, bin_bundle.cpp:328-337): [n_plain-1][high_L][N]
+    DBuf<u64> plain_high_ntt;
+    uint32_t n_ntt = 0, n_plain = 0;
+};
+
+class Engine {
+public:
+    Engine(const apsu_b200_params &p, int device);
+    ~Engine();
+
+    DeviceContext ctx;
+    PowersDag dag;
+
+    // ---- DB ----
+    std::vector<std::vector<std::unique_ptr<BinBundleStore>>> db; // [bundle_idx][cache_idx]
+    uint32_t add_binbundle(uint32_t bundle_idx, const uint64_t *const *coeffs, uint32_t ncoeffs);
+    uint32_t add_binbundle_synthetic(uint32_t bundle_idx, uint32_t ncoeffs, uint64_t seed);
+    uint32_t add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bin_sizes, const uint64_t *roots);
+    uint32_t total_bundles() const;
+    uint64_t stream_bytes() const;
+    void clear_db();
+    bool is_ntt_degree(uint32_t k) const
+    {
+        uint32_t ps = ctx.params.ps_low_degree;
+        return ps ? (k % (ps + 1)) != 0 : k != 0;
+    }
+
+    // ---- query ----
+    void set_relin_keys(const void *keys, bool on_device);
+    void query_begin(const uint32_t *src_powers, uint32_t nsrc, const void *cts, bool on_device);
+    void set_masks(const void *masks, uint32_t npack, bool on_device);
+    void encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t *out);
+    void compute_powers();
+    void eval_all();
+    void fetch_results(uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
+    void get_power(uint32_t bundle_idx, uint32_t power, uint64_t *out, uint32_t *L, int *is_ntt);
+    void results_device(void **ptr, uint64_t *bytes);
+    void collect_timings();
+
+    // ---- stand-alone batched evaluator operations ----
+    void op_ntt(uint64_t *polys, uint32_t count, const uint32_t *modulus_index, uint32_t pattern_len, bool inverse);
+    void op_multiply(uint32_t L, const uint64_t *a, const uint64_t *b, uint64_t *out, uint32_t n_ops);
+    void op_relinearize(uint32_t L, const uint64_t *in, uint64_t *out, uint32_t n_ops);
+    void op_mod_switch_next(uint32_t L, const uint64_t *in, uint64_t *out, uint32_t n_polys);
+
+    apsu_b200_timings timings{};
+    bool profiling = false;
+
+    struct Step {
+        std::function<void()> run;
+    };
+
+private:
+    friend struct ProgramBuilder;
+    // device state
+    DBuf<u64> relin_keys_; // [K-1][2][K][N]
+    bool have_keys_ = false;
+    DBuf<u64> masks_; // [npack][N]
+    uint32_t npack_ = 0, npack_needed_ = 0;
+    DBuf<u64> results_; // [total_bundles][2][N]
+    std::vector<std::pair<uint32_t, uint32_t>> result_order_;
+    DBuf<LevelConsts> levels_dev_;
+
+    // the polynomial arena and the two programs
+    Arena arena_;
+    IdxPool idx_;
+    std::vector<uint8_t> desc_host_; // kernel descriptor structs (MacGroup, FinalizeJob, ...)
+    DBuf<uint8_t> desc_dev_;
+    std::vector<Step> powers_prog_, eval_prog_;
+    bool plan_valid_ = false;
+    bool query_loaded_ = false, powers_done_ = false, eval_done_ = false;
+    uint32_t query_region_ = 0; // arena index of the uploaded query [nsrc][bic][2][first_L]
+    // where each power lives after ComputePowers
+    struct PowerLoc {
+        uint32_t idx = 0, L = 0;
+        bool ntt = false, valid = false;
+    };
+    std::vector<std::vector<PowerLoc>> final_power_; // [bic][max_items_per_bin+1]
+
+    // timing
+    cudaEvent_t ev_[4] = { nullptr, nullptr, nullptr, nullptr };
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> mac_events_;
+    size_t mac_events_used_ = 0;
+    std::vector<uint64_t> mac_step_bytes_;
+    uint64_t timed_mac_bytes_ = 0;
+    uint32_t powers_launches_ = 0, eval_launches_ = 0;
+
+    void invalidate_plan() { plan_valid_ = false; }
+    void build_plan();
+    void prepare_plain_high(BinBundleStore &s);
+    size_t add_desc(const void *data, size_t bytes);
+    void emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &groups, uint32_t lazy_bound, uint64_t bytes);
+    void emit_mul_terms(ProgramBuilder &pb, uint32_t L, std::vector<MulTermsJob> &jobs, uint32_t nterms);
+    void emit_finalize(ProgramBuilder &pb, uint32_t Ls, std::vector<FinalizeJob> &jobs);
+    template <typename Build>
+    void run_scratch_program(Build &&build);
+
+    // batched primitives used by the program builder and the op_* API (index arrays on device)
+    void run_extend(uint32_t L, uint32_t n_polys, const uint32_t *src, const uint32_t *dst);
+    void run_tensor(uint32_t L, uint32_t n_ops, const uint32_t *a, const uint32_t *b, const uint32_t *d);
+    void run_scale_down(uint32_t L, uint32_t n_polys, const uint32_t *src, const uint32_t *dst);
+    void run_ks_mac(uint32_t L, uint32_t n_ops, const uint32_t *dig, const uint32_t *out);
+    void run_ks_moddown(uint32_t L, uint32_t n_ops, const uint32_t *acc, const uint32_t *ct, const uint32_t *dst);
+    void run_mod_switch_next(uint32_t L, uint32_t n_polys, const uint32_t *src, const uint32_t *dst);
+    void note_launch() { ctx.launches++; }
+};
+
+} // namespace apsu_b200

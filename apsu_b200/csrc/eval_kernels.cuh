@@ -1,0 +1,250 @@
+// Kernels of the per-BinBundle polynomial evaluation (K1, K7, K8, K9, K10 of SURVEY.md §2.2):
+//   k_db_mac      — the DB stream: sum_j power_j ⊙ plaintext_j over NTT-form plaintexts (HBM-bound)
+//   k_db_mul      — per-term products (Paterson-Stockmeyer i=0 polynomial, bin_bundle.cpp:314-324)
+//   k_finalize    — add_plain(coeff 0) + add_plain(mask) + mod-switch to the last level + clear bits
+//   k_plain_lift  — fast plain lift of a coefficient-form plaintext to RNS (before its NTT)
+//   k_fill_uniform, k_slot_scatter — synthetic DB fill, BatchEncoder slot permutation
+#pragma once
+#include "device_ctx.hpp"
+
+namespace apsu_b200 {
+
+constexpr int kMacJobs = 8;      // jobs per group: share every ciphertext-power load
+constexpr int kMacThreads = 256;
+
+// One group = up to kMacJobs accumulation jobs over the same ciphertext powers.
+// job g: out_g[c][l][n] = sum_{j < nterms_g} power_j[c][l][n] * coeff_g[j][l][n]   (mod q_l)
+struct MacGroup {
+    const u64 *coeff[kMacJobs]; // plaintexts of job g, term j at coeff[g] + j*L*N (HBM-resident DB)
+    u32 nterms[kMacJobs];
+    u32 out_idx[kMacJobs];      // arena index of [2][L][N]
+    u32 pow_idx;                // arena index of power term 0, component 0, prime 0
+    u32 pow_term_stride;        // polynomials between consecutive terms
+    u32 pow_comp_stride;        // polynomials between the two ciphertext components
+    u32 njobs;
+    u32 max_terms;
+    u32 pad_;
+};
+
+// grid (L*N/256, n_groups).  Each thread owns one (prime, coefficient) column: streams the G
+// plaintext words of term j with independent 8-byte coalesced loads, multiplies them into 2G 128-bit
+// lazy accumulators against the two power words (L2-resident, shared by the G jobs), reduces once.
+// lazy_bound = number of products that fit 128 bits for the largest prime (>= 256 for <=60-bit primes).
+__global__ void __launch_bounds__(kMacThreads)
+k_db_mac(u64 *A, const MacGroup *__restrict__ groups, LevelConsts c, int N, u32 lazy_bound)
+{
+    __shared__ MacGroup g;
+    if (threadIdx.x < sizeof(MacGroup) / 4) reinterpret_cast<u32 *>(&g)[threadIdx.x] = reinterpret_cast<const u32 *>(&groups[blockIdx.y])[threadIdx.x];
+    __syncthreads();
+    const u32 col = blockIdx.x * blockDim.x + threadIdx.x; // l*N + n
+    const u32 l = col / N;
+    const DMod m = c.q[l];
+    const size_t LN = (size_t)c.L * N;
+    Acc128 acc[kMacJobs][2];
+#pragma unroll
+    for (int k = 0; k < kMacJobs; k++) acc[k][0] = acc[k][1] = Acc128{ 0, 0 };
+    const u64 *pw = A + (size_t)g.pow_idx * N + col;
+    const size_t tstride = (size_t)g.pow_term_stride * N, cstride = (size_t)g.pow_comp_stride * N;
+    u32 since_reduce = 0;
+    for (u32 j = 0; j < g.max_terms; j++) {
+        const u64 p0 = pw[j * tstride], p1 = pw[j * tstride + cstride];
+        u64 w[kMacJobs];
+#pragma unroll
+        for (int k = 0; k < kMacJobs; k++) w[k] = (j < g.nterms[k]) ? __ldcs(g.coeff[k] + j * LN + col) : 0ull;
+#pragma unroll
+        for (int k = 0; k < kMacJobs; k++) {
+            mac128(acc[k][0], w[k], p0);
+            mac128(acc[k][1], w[k], p1);
+        }
+        if (++since_reduce == lazy_bound) { // never taken for the reference parameter sets
+            since_reduce = 0;
+#pragma unroll
+            for (int k = 0; k < kMacJobs; k++) {
+                acc[k][0] = Acc128{ barrett128(acc[k][0].lo, acc[k][0].hi, m), 0 };
+                acc[k][1] = Acc128{ barrett128(acc[k][1].lo, acc[k][1].hi, m), 0 };
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMacJobs; k++) {
+        if (k < (int)g.njobs) {
+            u64 *o = A + (size_t)g.out_idx[k] * N + col;
+            o[0] = barrett128(acc[k][0].lo, acc[k][0].hi, m);
+            o[LN] = barrett128(acc[k][1].lo, acc[k][1].hi, m);
+        }
+    }
+}
+
+// per-term products: out[term][c][l][n] = power_term[c][l][n] * coeff[term][l][n].
+// grid (L*N/256, nterms, n_bundles); bundle b: coeff[b], out_idx[b] (terms contiguous: [term][2][L][N]).
+struct MulTermsJob {
+    const u64 *coeff;
+    u32 out_idx;
+    u32 pow_idx, pow_term_stride, pow_comp_stride;
+    u32 nterms;
+    u32 pad_;
+};
+__global__ void __launch_bounds__(kMacThreads)
+k_db_mul(u64 *A, const MulTermsJob *__restrict__ jobs, LevelConsts c, int N)
+{
+    const MulTermsJob jb = jobs[blockIdx.z];
+    const u32 j = blockIdx.y;
+    if (j >= jb.nterms) return;
+    const u32 col = blockIdx.x * blockDim.x + threadIdx.x;
+    const DMod m = c.q[col / N];
+    const size_t LN = (size_t)c.L * N;
+    const u64 w = __ldcs(jb.coeff + j * LN + col);
+    const u64 *pw = A + ((size_t)jb.pow_idx + (size_t)j * jb.pow_term_stride) * N + col;
+    u64 *o = A + ((size_t)jb.out_idx) * N + (size_t)j * 2 * LN + col;
+    o[0] = mul_mod(pw[0], w, m);
+    o[LN] = mul_mod(pw[(size_t)jb.pow_comp_stride * N], w, m);
+}
+
+// ---- final assembly of one result ciphertext ----
+struct FinalizeJob {
+    u32 src[3];          // arena indices of size-2 ciphertexts [2][Ls][N] to add up (0xFFFFFFFF = none)
+    u32 pack;            // mask index: bundle_idx + cache_idx * bundle_idx_count (receiver_ddh.cpp:346)
+    const u64 *coeff0;   // constant-coefficient plaintext, coefficient form [N]
+    u32 slot;            // result slot: out = results + slot*2*N
+    u32 pad_;
+};
+constexpr u32 kNoSrc = 0xFFFFFFFFu;
+
+// BFV scaling of one plaintext coefficient at the level described by c (multiply_add_plain_with_scaling_variant)
+__device__ __forceinline__ u64 scaled_plain(u64 mcoef, const LevelConsts &c, int j, u64 t, u64 thr)
+{
+    // fix = floor((m * (q mod t) + (t+1)/2) / t); both factors < 2^61 so the numerator needs 128 bits
+    u64 lo = mcoef * c.q_mod_t, hi = mulhi(mcoef, c.q_mod_t);
+    lo += thr;
+    hi += lo < thr;
+    // mcoef < t and q_mod_t < t  =>  numerator < t^2 + t  =>  quotient < t + 1 fits 64 bits
+    u64 fix;
+    if (hi == 0) {
+        fix = lo / t;
+    } else {
+        // 128/64 division: t < 2^61.  Long division by halves.
+        unsigned __int128 num = ((unsigned __int128)hi << 64) | lo;
+        fix = (u64)(num / t);
+    }
+    const DMod m = c.q[j];
+    u64 s = mul_mod(mcoef, c.coeff_div_plain[j], m);
+    return add_mod(s, barrett64(fix, m), m.q);
+}
+
+// grid (N/256, 2, n_jobs).  levels[L] = constants of the level with L primes; Ls = level of the sources.
+__global__ void __launch_bounds__(kEwThreads)
+k_finalize(u64 *A, const FinalizeJob *__restrict__ jobs, const LevelConsts *__restrict__ levels, const u64 *__restrict__ masks,
+           u64 *__restrict__ results, int Ls, u64 t, u64 clear_mask, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 comp = blockIdx.y;
+    const FinalizeJob jb = jobs[blockIdx.z];
+    u64 v[kMaxQ];
+    {
+        const LevelConsts &c = levels[Ls];
+#pragma unroll
+        for (int i = 0; i < kMaxQ; i++) {
+            if (i < Ls) {
+                u64 s = 0;
+                const u64 q = c.q[i].q;
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    if (jb.src[k] != kNoSrc) s = add_mod(s, A[((size_t)jb.src[k] + (size_t)comp * Ls + i) * N + n], q);
+                v[i] = s;
+            }
+        }
+        if (comp == 0) {
+            const u64 thr = (t + 1) >> 1;
+            const u64 m0 = jb.coeff0[n], m1 = masks[(size_t)jb.pack * N + n];
+#pragma unroll
+            for (int i = 0; i < kMaxQ; i++) {
+                if (i < Ls) {
+                    const u64 q = c.q[i].q;
+                    v[i] = add_mod(v[i], scaled_plain(m0, c, i, t, thr), q);
+                    v[i] = add_mod(v[i], scaled_plain(m1, c, i, t, thr), q);
+                }
+            }
+        }
+    }
+    // mod_switch_to_next down to one prime
+#pragma unroll
+    for (int L = kMaxQ; L > 1; L--) { // compile-time indices keep v[] in registers
+        if (L > Ls) continue;
+        const LevelConsts &c = levels[L];
+        const u64 ql = c.q[L - 1].q;
+        const u64 a = add_mod(v[L - 1], ql >> 1, ql);
+#pragma unroll
+        for (int i = 0; i < kMaxQ - 1; i++) {
+            if (i + 1 < L) {
+                const DMod m = c.q[i];
+                u64 tmp = sub_mod(barrett64(a, m), c.half_mod[i], m.q);
+                v[i] = mul_shoup(sub_mod(v[i], tmp, m.q), c.inv_qlast[i], m.q);
+            }
+        }
+    }
+    results[((size_t)jb.slot * 2 + comp) * N + n] = v[0] & clear_mask; // try_clear_irrelevant_bits
+}
+
+// fast plain lift: coefficient-form plaintext [N] mod t -> RNS [L][N] (then NTT'd by the caller).
+// grid (N/256, L, n_plain): src plaintext p at in + p*N, dst at out + p*L*N
+__global__ void __launch_bounds__(kEwThreads)
+k_plain_lift(const u64 *__restrict__ in, u64 *__restrict__ out, LevelConsts c, u64 t, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const size_t p = blockIdx.z;
+    const u64 v = in[p * N + n];
+    const u64 thr = (t + 1) >> 1;
+    out[(p * c.L + j) * N + n] = v >= thr ? v + (c.q[j].q - t) : v;
+}
+
+// counter-based splitmix64: word k of the stream seeded with `seed` (state after k+1 increments)
+__device__ __forceinline__ u64 splitmix64_at(u64 seed, u64 k)
+{
+    u64 z = seed + (k + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// Synthetic BinBundle fill.  The stream visits the plaintexts in degree order (coefficient-form ones are
+// N words mod t, NTT-form ones L*N words mod q_l) and word k of the stream is
+// (splitmix64_at(seed, k) * modulus) >> 64 — the same words the oracle's synthetic fill produces.
+// mode 0: `out` is the packed NTT-form buffer [n_ntt][L][N]; mode 1: the coefficient-form buffer [n_plain][N].
+// h = ps_low_degree + 1 (0 when Paterson-Stockmeyer is off).
+struct FillMods {
+    u64 q[kMaxQ];
+    u64 t;
+    int L;
+};
+__global__ void k_fill_db(u64 *__restrict__ out, size_t count, u64 seed, int mode, u32 h, FillMods mods, int N)
+{
+    size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= count) return;
+    const size_t LN = (size_t)mods.L * N;
+    u64 pos, q;
+    if (mode == 0) {
+        size_t r = w / LN, within = w % LN;
+        q = mods.q[within / N];
+        if (h) {
+            size_t blk = r / (h - 1), in_blk = r % (h - 1);
+            pos = blk * (N + (h - 1) * LN) + N + in_blk * LN + within;
+        } else {
+            pos = N + r * LN + within;
+        }
+    } else {
+        size_t r = w / N, within = w % N;
+        q = mods.t;
+        pos = (h ? r * (N + (size_t)(h - 1) * LN) : 0) + within;
+    }
+    out[w] = mulhi(splitmix64_at(seed, pos), q);
+}
+
+// BatchEncoder::encode scatter: out[p][map[i]] = values[p][i]
+__global__ void k_slot_scatter(const u64 *__restrict__ values, u64 *__restrict__ out, const u32 *__restrict__ map, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t p = blockIdx.y;
+    out[p * N + map[i]] = values[p * N + i];
+}
+
+} // namespace apsu_b200

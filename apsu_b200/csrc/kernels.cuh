@@ -1,0 +1,201 @@
+// Element-wise RNS kernels of the path (K4-K9 of SURVEY.md §2.2): BEHZ base extension, tensor
+// product, scale-and-round back to base q, key-switch inner product and mod-down, mod-switch,
+// plaintext addition, final bit clearing.  One thread per coefficient; all polynomials live in one
+// device arena and are addressed by 32-bit polynomial indices (units of N words), so that a whole
+// batch of independent ciphertext operations is one launch.
+//
+// Every kernel returns canonical residues and follows SEAL 3.7's formulas —
+// intermediate laziness is free, the reduced outputs are what must match bit-for-bit.
+#pragma once
+#include "device_ctx.hpp"
+
+namespace apsu_b200 {
+
+
+
+// ---- BEHZ steps (1)-(2): base q -> base Bsk, Montgomery-reduced (fastbconv_m_tilde + sm_mrq) ----
+// grid (N/256, n_polys).  src[rp] -> first prime of an RNS polynomial [L][N]; dst[rp] -> [S][N].
+__global__ void __launch_bounds__(kEwThreads)
+k_behz_extend(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst, LevelConsts c, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 rp = blockIdx.y;
+    const u64 *x = A + (size_t)src[rp] * N + n;
+    u64 *o = A + (size_t)dst[rp] * N + n;
+    u64 tmp[kMaxQ];
+    u32 ymt = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxQ; i++) {
+        if (i < c.L) {
+            tmp[i] = mul_shoup(x[(size_t)i * N], c.mtilde_inv_punct_q[i], c.q[i].q);
+            ymt += (u32)tmp[i] * c.q_punct_mod_mtilde[i];
+        }
+    }
+    const u32 r = ymt * c.neg_inv_q_mod_mtilde; // arithmetic mod m_tilde = 2^32
+    for (int j = 0; j < c.S; j++) {
+        const DMod m = c.bsk[j];
+        Acc128 acc{ 0, 0 };
+#pragma unroll
+        for (int i = 0; i < kMaxQ; i++)
+            if (i < c.L) mac128(acc, tmp[i], c.q_punct_mod_bsk[j][i]);
+        u64 y = barrett128(acc.lo, acc.hi, m);
+        u64 rr = r;
+        if (r >= 0x80000000u) rr += m.q - 0x100000000ull; // centred lift of r
+        u64 v = add_mod(mul_shoup(rr, c.q_mod_bsk[j], m.q), y, m.q);
+        o[(size_t)j * N] = mul_shoup(v, c.inv_mtilde_mod_bsk[j], m.q);
+    }
+}
+
+// ---- BEHZ step (4): size-2 x size-2 tensor product in NTT form over the extended base q ∪ Bsk ----
+// grid (N/256, L+S, n_ops).  Extended ciphertext = [2][L+S][N]; output [3][L+S][N].
+__global__ void __launch_bounds__(kEwThreads)
+k_tensor(u64 *A, const u32 *__restrict__ a_idx, const u32 *__restrict__ b_idx, const u32 *__restrict__ d_idx, LevelConsts c, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, LS = c.L + c.S;
+    const u32 o = blockIdx.z;
+    const DMod m = j < c.L ? c.q[j] : c.bsk[j - c.L];
+    const u64 *a = A + ((size_t)a_idx[o] + j) * N + n;
+    const u64 *b = A + ((size_t)b_idx[o] + j) * N + n;
+    u64 *d = A + ((size_t)d_idx[o] + j) * N + n;
+    const size_t cs = (size_t)LS * N; // component stride
+    u64 a0 = a[0], a1 = a[cs], b0 = b[0], b1 = b[cs];
+    d[0] = mul_mod(a0, b0, m);
+    Acc128 acc{ 0, 0 };
+    mac128(acc, a0, b1);
+    mac128(acc, a1, b0);
+    d[cs] = barrett128(acc.lo, acc.hi, m);
+    d[2 * cs] = mul_mod(a1, b1, m);
+}
+
+// ---- BEHZ steps (6)-(8): multiply by t, fast floor (divide by q), Shenoy-Kumaresan back to q ----
+// grid (N/256, n_polys).  src[rp] -> [L+S][N] coefficient form; dst[rp] -> [L][N].
+__global__ void __launch_bounds__(kEwThreads)
+k_behz_scale_down(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst, LevelConsts c, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 rp = blockIdx.y;
+    const u64 *d = A + (size_t)src[rp] * N + n;
+    u64 *o = A + (size_t)dst[rp] * N + n;
+    const int L = c.L, S = c.S, nb = c.S - 1;
+    u64 tmp[kMaxQ], f[kMaxBsk];
+#pragma unroll
+    for (int i = 0; i < kMaxQ; i++)
+        if (i < L) tmp[i] = mul_shoup(d[(size_t)i * N], c.t_inv_punct_q[i], c.q[i].q);
+#pragma unroll
+    for (int j = 0; j < kMaxBsk; j++) {
+        if (j < S) {
+            const DMod m = c.bsk[j];
+            Acc128 acc{ 0, 0 };
+#pragma unroll
+            for (int i = 0; i < kMaxQ; i++)
+                if (i < L) mac128(acc, tmp[i], c.q_punct_mod_bsk[j][i]);
+            u64 conv = barrett128(acc.lo, acc.hi, m);
+            u64 tB = mul_shoup(d[(size_t)(L + j) * N], c.t_mod_bsk[j], m.q);
+            f[j] = mul_shoup(sub_mod(tB, conv, m.q), c.inv_q_mod_bsk[j], m.q);
+        }
+    }
+    // Shenoy-Kumaresan
+    u64 g[kMaxBsk];
+    Acc128 aacc{ 0, 0 };
+    const DMod msk = c.bsk[S - 1];
+#pragma unroll
+    for (int k = 0; k < kMaxBsk; k++) {
+        if (k < nb) {
+            g[k] = mul_shoup(f[k], c.inv_punct_B[k], c.bsk[k].q);
+            mac128(aacc, g[k], c.B_punct_mod_msk[k]);
+        }
+    }
+    u64 alpha = barrett128(aacc.lo, aacc.hi, msk);
+    alpha = mul_shoup(sub_mod(alpha, f[S - 1], msk.q), c.inv_B_mod_msk, msk.q);
+    const bool neg = alpha > (msk.q >> 1);
+    const u64 corr = neg ? msk.q - alpha : alpha;
+    for (int i = 0; i < L; i++) {
+        const DMod m = c.q[i];
+        Acc128 acc{ 0, 0 };
+#pragma unroll
+        for (int k = 0; k < kMaxBsk; k++)
+            if (k < nb) mac128(acc, g[k], c.B_punct_mod_q[i][k]);
+        u64 conv = barrett128(acc.lo, acc.hi, m);
+        u64 adj = neg ? mul_shoup(corr, c.B_mod_q[i], m.q) : mul_shoup(corr, c.neg_B_mod_q[i], m.q);
+        o[(size_t)i * N] = add_mod(adj, conv, m.q);
+    }
+}
+
+// ---- key switching: inner product of the NTT'd digits with the relinearisation keys ----
+// grid (N/256, R, n_ops*2).  digits[o] -> [L][R][N] (digit J, modulus slot I); keys [K-1][2][K][N];
+// out[o] -> [2][R][N].
+__global__ void __launch_bounds__(kEwThreads)
+k_ks_mac(u64 *A, const u32 *__restrict__ dig_idx, const u32 *__restrict__ out_idx, const u64 *__restrict__ keys, KeySwitchConsts c, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int I = blockIdx.y, R = c.L + 1;
+    const u32 o = blockIdx.z >> 1, comp = blockIdx.z & 1;
+    const int key_index = I == c.L ? c.K - 1 : I;
+    const u64 *dg = A + ((size_t)dig_idx[o] + I) * N + n;
+    Acc128 acc{ 0, 0 };
+    for (int J = 0; J < c.L; J++) {
+        u64 kv = keys[(((size_t)J * 2 + comp) * c.K + key_index) * N + n];
+        mac128(acc, dg[(size_t)J * R * N], kv);
+    }
+    A[((size_t)out_idx[o] + (size_t)comp * R + I) * N + n] = barrett128(acc.lo, acc.hi, c.key_mod[I]);
+}
+
+// ---- key switching: divide by the special prime with rounding and add to (c0, c1) ----
+// grid (N/256, 2, n_ops).  acc[o] -> [2][R][N] coefficient form; ct[o] -> [>=2][L][N] (c0,c1 read);
+// dst[o] -> [2][L][N].
+__global__ void __launch_bounds__(kEwThreads)
+k_ks_moddown(u64 *A, const u32 *__restrict__ acc_idx, const u32 *__restrict__ ct_idx, const u32 *__restrict__ dst_idx, KeySwitchConsts c, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 comp = blockIdx.y, o = blockIdx.z;
+    const int L = c.L, R = L + 1;
+    const u64 *ac = A + ((size_t)acc_idx[o] + (size_t)comp * R) * N + n;
+    const u64 *ct = A + ((size_t)ct_idx[o] + (size_t)comp * L) * N + n;
+    u64 *dst = A + ((size_t)dst_idx[o] + (size_t)comp * L) * N + n;
+    const u64 P = c.key_mod[L].q;
+    u64 u = add_mod(ac[(size_t)L * N], c.half_P, P);
+    for (int i = 0; i < L; i++) {
+        const DMod m = c.key_mod[i];
+        u64 delta = sub_mod(barrett64(u, m), c.half_P_mod[i], m.q);
+        u64 v = mul_shoup(sub_mod(ac[(size_t)i * N], delta, m.q), c.inv_P[i], m.q);
+        dst[(size_t)i * N] = add_mod(ct[(size_t)i * N], v, m.q);
+    }
+}
+
+// ---- mod_switch_to_next (divide_and_round_q_last): [L][N] -> [L-1][N] ----
+// grid (N/256, n_polys)
+__global__ void __launch_bounds__(kEwThreads)
+k_mod_switch_next(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst, LevelConsts c, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 rp = blockIdx.y;
+    const u64 *x = A + (size_t)src[rp] * N + n;
+    u64 *o = A + (size_t)dst[rp] * N + n;
+    const int L = c.L;
+    const u64 ql = c.q[L - 1].q;
+    const u64 a = add_mod(x[(size_t)(L - 1) * N], ql >> 1, ql);
+    for (int i = 0; i + 1 < L; i++) {
+        const DMod m = c.q[i];
+        u64 tmp = sub_mod(barrett64(a, m), c.half_mod[i], m.q);
+        o[(size_t)i * N] = mul_shoup(sub_mod(x[(size_t)i * N], tmp, m.q), c.inv_qlast[i], m.q);
+    }
+}
+
+// ---- sum of `count` RNS polynomials: dst = sum_k A[src[rp*count_stride + k]] (mod q_j) ----
+// grid (N/256, L, n_out).  lists: first[rp], n_terms[rp] into `terms`.
+__global__ void __launch_bounds__(kEwThreads)
+k_sum_polys(u64 *A, const u32 *__restrict__ terms, const u32 *__restrict__ first, const u32 *__restrict__ n_terms,
+            const u32 *__restrict__ dst, LevelConsts c, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const u32 rp = blockIdx.z;
+    const u64 q = c.q[j].q;
+    u64 s = 0;
+    const u32 f = first[rp], cnt = n_terms[rp];
+    for (u32 k = 0; k < cnt; k++) s = add_mod(s, A[((size_t)terms[f + k] + j) * N + n], q);
+    A[((size_t)dst[rp] + j) * N + n] = s;
+}
+
+} // namespace apsu_b200

@@ -1,0 +1,85 @@
+// 64-bit modular arithmetic for sm_100a.  Moduli are < 2^61 (user primes <= 60 bits, BEHZ auxiliary
+// primes 61 bits, m_tilde = 2^32), so lazy Harvey ranges [0,4q) fit a u64.  B200 has no native 64x64
+// multiplier: mul.hi.u64 / mul.lo.u64 compile to IMAD.WIDE.U32 chains on the FMA pipe, which is the
+// integer roofline these kernels run against.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace apsu_b200 {
+
+using u64 = unsigned long long;
+using u32 = unsigned int;
+
+// modulus with its Barrett constant floor(2^128 / q) (two words)
+struct DMod {
+    u64 q;
+    u64 r0, r1;
+};
+
+// constant multiplicand in Shoup form: quot = floor(op * 2^64 / q)
+struct DShoup {
+    u64 op, quot;
+};
+
+__device__ __forceinline__ u64 mulhi(u64 a, u64 b) { return __umul64hi(a, b); }
+
+// x * w mod q for x < 2^64, result in [0, 2q)
+__device__ __forceinline__ u64 mul_shoup_lazy(u64 x, u64 w, u64 wq, u64 q) { return w * x - mulhi(x, wq) * q; }
+// result in [0, q)
+__device__ __forceinline__ u64 mul_shoup(u64 x, u64 w, u64 wq, u64 q)
+{
+    u64 r = mul_shoup_lazy(x, w, wq, q);
+    return r >= q ? r - q : r;
+}
+__device__ __forceinline__ u64 mul_shoup(u64 x, const DShoup &s, u64 q) { return mul_shoup(x, s.op, s.quot, q); }
+
+// (hi:lo) mod q, any 128-bit input, canonical result.  Barrett with ratio floor(2^128/q); the
+// quotient estimate is at most 2 short, hence two conditional subtractions.
+__device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, const DMod &m)
+{
+    // qhat = floor((hi:lo) * (r1:r0) / 2^128), low carries of lo*r0 dropped
+    u64 carry = mulhi(lo, m.r0);
+    u64 t_lo = lo * m.r1, t_hi = mulhi(lo, m.r1);
+    u64 s1 = t_lo + carry;
+    u64 c1 = s1 < t_lo;
+    u64 tmp3 = t_hi + c1;
+    u64 u_lo = hi * m.r0, u_hi = mulhi(hi, m.r0);
+    u64 s2 = s1 + u_lo;
+    u64 c2 = s2 < u_lo;
+    u64 qhat = hi * m.r1 + tmp3 + u_hi + c2;
+    u64 r = lo - qhat * m.q;
+    if (r >= m.q) r -= m.q;
+    if (r >= m.q) r -= m.q;
+    return r;
+}
+// x mod q for a single word
+__device__ __forceinline__ u64 barrett64(u64 x, const DMod &m)
+{
+    u64 r = x - mulhi(x, m.r1) * m.q;
+    if (r >= m.q) r -= m.q;
+    if (r >= m.q) r -= m.q;
+    return r;
+}
+__device__ __forceinline__ u64 mul_mod(u64 a, u64 b, const DMod &m) { return barrett128(a * b, mulhi(a, b), m); }
+__device__ __forceinline__ u64 add_mod(u64 a, u64 b, u64 q)
+{
+    u64 s = a + b;
+    return s >= q ? s - q : s;
+}
+__device__ __forceinline__ u64 sub_mod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+
+// 128-bit accumulator: acc += a*b  (products < 2^122, callers bound the number of summands)
+struct Acc128 {
+    u64 lo, hi;
+};
+__device__ __forceinline__ void mac128(Acc128 &acc, u64 a, u64 b)
+{
+    u64 pl = a * b, ph = mulhi(a, b);
+    asm("add.cc.u64 %0, %0, %2;\n\t"
+        "addc.u64 %1, %1, %3;"
+        : "+l"(acc.lo), "+l"(acc.hi)
+        : "l"(pl), "l"(ph));
+}
+
+} // namespace apsu_b200

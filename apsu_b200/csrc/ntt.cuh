@@ -1,0 +1,147 @@
+// Negacyclic NTT / inverse NTT over one RNS prime, N in {2048, 4096, 8192, ...}: one CTA per
+// polynomial, the whole polynomial staged in shared memory, radix-2^R butterflies done in
+// registers between shared-memory exchanges (kernels K2/K3 of SURVEY.md §2.2).
+//
+// Convention (SEAL 3.7): psi = minimal primitive 2N-th root; forward = Cooley-Tukey,
+// natural-order input, bit-reversed output, out[k] = a(psi^(2*bitrev(k)+1)); inverse =
+// Gentleman-Sande incl. N^-1; both return canonical residues.
+// Twiddle table: tw[i] = psi^bitrev(i) in Shoup form, stage with m groups uses tw[m + group].
+#pragma once
+#include "device_ctx.hpp"
+
+namespace apsu_b200 {
+
+// How a CTA finds its polynomials: optional gather/scatter index arrays (units of one polynomial).
+struct NttSrc {
+    const unsigned *src_idx; // null: p
+    const unsigned *dst_idx; // null: p
+    int reduce_input;        // reduce every input word modulo the target modulus first
+};
+
+template <int R>
+__device__ __forceinline__ void fwd_group(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, unsigned hi, int s, u64 q, u64 two_q)
+{
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int d = 1 << (R - 1 - r);          // pair distance inside the register group
+        const unsigned mbase = (1u << (s + r)) + (hi << r);
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) {
+            if (k & d) continue;
+            ulonglong2 w = __ldg(&tw[mbase + (k >> (R - r))]);
+            u64 u = x[k];
+            if (u >= two_q) u -= two_q;
+            u64 v = mul_shoup_lazy(x[k + d], w.x, w.y, q);
+            x[k] = u + v;
+            x[k + d] = u + two_q - v;
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void inv_group(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, unsigned hi, int s, u64 q, u64 two_q)
+{
+#pragma unroll
+    for (int r = R - 1; r >= 0; r--) {
+        const int d = 1 << (R - 1 - r);
+        const unsigned mbase = (1u << (s + r)) + (hi << r);
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) {
+            if (k & d) continue;
+            ulonglong2 w = __ldg(&tw[mbase + (k >> (R - r))]);
+            u64 u = x[k], v = x[k + d];
+            u64 sum = u + v;
+            if (sum >= two_q) sum -= two_q;
+            x[k] = sum;
+            x[k + d] = mul_shoup_lazy(u + two_q - v, w.x, w.y, q);
+        }
+    }
+}
+
+// one pass over stages [s, s+R) on the shared-memory polynomial
+template <int LOGN, int R, bool FWD>
+__device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict__ tw, int s, u64 q, u64 two_q)
+{
+    constexpr int N = 1 << LOGN;
+    const int log_stride = LOGN - s - R;
+    const unsigned stride = 1u << log_stride;
+    for (unsigned g = threadIdx.x; g < (N >> R); g += blockDim.x) {
+        unsigned lo = g & (stride - 1), hi = g >> log_stride;
+        unsigned base = (hi << (LOGN - s)) + lo;
+        u64 x[1 << R];
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) x[k] = sm[base + k * stride];
+        if (FWD)
+            fwd_group<R>(x, tw, hi, s, q, two_q);
+        else
+            inv_group<R>(x, tw, hi, s, q, two_q);
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) sm[base + k * stride] = x[k];
+    }
+}
+
+template <int LOGN, bool FWD, int S, int REM>
+struct PassRunner {
+    // runs stages [S, LOGN) forward (ascending) — or the same stages descending for the inverse
+    __device__ static __forceinline__ void run(u64 *sm, const ulonglong2 *tw, u64 q, u64 two_q)
+    {
+        constexpr int R = REM >= 3 ? 3 : REM;
+        if (FWD) {
+            smem_pass<LOGN, R, true>(sm, tw, S, q, two_q);
+            __syncthreads();
+            PassRunner<LOGN, FWD, S + R, REM - R>::run(sm, tw, q, two_q);
+        } else {
+            PassRunner<LOGN, FWD, S + R, REM - R>::run(sm, tw, q, two_q);
+            smem_pass<LOGN, R, false>(sm, tw, S, q, two_q);
+            __syncthreads();
+        }
+    }
+};
+template <int LOGN, bool FWD, int S>
+struct PassRunner<LOGN, FWD, S, 0> {
+    __device__ static __forceinline__ void run(u64 *, const ulonglong2 *, u64, u64) {}
+};
+
+template <int LOGN, bool FWD>
+__global__ void __launch_bounds__((1 << LOGN) / 16) ntt_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, NttArgs a, NttSrc src)
+{
+    constexpr int N = 1 << LOGN;
+    extern __shared__ u64 sm[];
+    const unsigned p = blockIdx.x;
+    const int slot = p % a.pattern_len;
+    const DMod m = a.mod[slot];
+    const u64 q = m.q, two_q = 2 * m.q;
+    const ulonglong2 *tw = a.tw + ((size_t)a.table[slot] * 2 + (FWD ? 0 : 1)) * N;
+
+    const u64 *ip = in + (size_t)(src.src_idx ? src.src_idx[p] : p) * N;
+    const bool reduce = src.reduce_input != 0;
+    const ulonglong2 *ip2 = reinterpret_cast<const ulonglong2 *>(ip);
+    ulonglong2 *sm2 = reinterpret_cast<ulonglong2 *>(sm);
+    for (unsigned i = threadIdx.x; i < N / 2; i += blockDim.x) {
+        ulonglong2 v = ip2[i];
+        if (reduce) {
+            v.x = barrett64(v.x, m);
+            v.y = barrett64(v.y, m);
+        }
+        sm2[i] = v;
+    }
+    __syncthreads();
+    PassRunner<LOGN, FWD, 0, LOGN>::run(sm, tw, q, two_q);
+    ulonglong2 *op2 = reinterpret_cast<ulonglong2 *>(out + (size_t)(src.dst_idx ? src.dst_idx[p] : p) * N);
+    const DShoup inv_n = a.inv_n[slot];
+    for (unsigned i = threadIdx.x; i < N / 2; i += blockDim.x) {
+        ulonglong2 v = sm2[i];
+        if (FWD) {
+            if (v.x >= two_q) v.x -= two_q;
+            if (v.x >= q) v.x -= q;
+            if (v.y >= two_q) v.y -= two_q;
+            if (v.y >= q) v.y -= q;
+        } else {
+            v.x = mul_shoup(v.x, inv_n, q);
+            v.y = mul_shoup(v.y, inv_n, q);
+        }
+        op2[i] = v;
+    }
+}
+
+} // namespace apsu_b200

@@ -1,0 +1,270 @@
+"""Host-side mirror of the reference's receiver surface for the query-evaluation path, over the C ABI.
+
+Names follow the reference (common/apsu/psu_params.h, common/apsu/powers.h,
+receiver/apsu/receiver_db.h, receiver/apsu/receiver_ddh.h, common/apsu/network/result_package.h);
+the C++ facade with the same names lives in apsu_b200/host/apsu_b200.hpp.  This module is glue for
+tests, bench.py and torch.distributed sharding — all arithmetic happens in libapsu_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+
+
+class PSUParams:
+    """common/apsu/psu_params.h:31-222 — parameters + derived bundle geometry."""
+
+    def __init__(self, c: capi.CParams):
+        self._c = c
+
+    @staticmethod
+    def Load(json_text: str) -> "PSUParams":
+        """PSUParams::Load(const std::string&), common/apsu/psu_params.cpp:290-374"""
+        c = capi.CParams()
+        capi.check(capi.lib().apsu_b200_params_load_json(json_text.encode(), C.byref(c)))
+        return PSUParams(c)
+
+    @staticmethod
+    def from_fields(N, plain_modulus, coeff_modulus, hash_func_count, table_size, max_items_per_bin, felts_per_item,
+                    ps_low_degree, query_powers) -> "PSUParams":
+        c = capi.CParams()
+        c.poly_modulus_degree, c.plain_modulus = N, plain_modulus
+        c.coeff_modulus_count = len(coeff_modulus)
+        for i, q in enumerate(coeff_modulus):
+            c.coeff_modulus[i] = q
+        c.hash_func_count, c.table_size, c.max_items_per_bin = hash_func_count, table_size, max_items_per_bin
+        c.felts_per_item, c.ps_low_degree = felts_per_item, ps_low_degree
+        qp = sorted(set([1] + list(query_powers)))
+        c.query_power_count = len(qp)
+        for i, p in enumerate(qp):
+            c.query_powers[i] = p
+        capi.check(capi.lib().apsu_b200_params_validate(C.byref(c)))
+        return PSUParams(c)
+
+    # accessors named as in the reference
+    def poly_modulus_degree(self): return self._c.poly_modulus_degree
+    def plain_modulus(self): return self._c.plain_modulus
+    def coeff_modulus(self): return [self._c.coeff_modulus[i] for i in range(self._c.coeff_modulus_count)]
+    def table_params(self): return dict(hash_func_count=self._c.hash_func_count, table_size=self._c.table_size, max_items_per_bin=self._c.max_items_per_bin)
+    def item_params(self): return dict(felts_per_item=self._c.felts_per_item)
+    def query_params(self): return dict(ps_low_degree=self._c.ps_low_degree, query_powers=self.query_powers())
+    def query_powers(self): return [self._c.query_powers[i] for i in range(self._c.query_power_count)]
+    def item_bit_count(self): return self._c.item_bit_count
+    def item_bit_count_per_felt(self): return self._c.item_bit_count_per_felt
+    def items_per_bundle(self): return self._c.items_per_bundle
+    def bins_per_bundle(self): return self._c.bins_per_bundle
+    def bundle_idx_count(self): return self._c.bundle_idx_count
+
+
+@dataclass
+class PowersNode:
+    power: int
+    depth: int
+    parents: tuple
+
+    def is_source(self):
+        return self.parents == (0, 0)
+
+
+class PowersDag:
+    """common/apsu/powers.h:41-293 (configure / depth / target_powers / source_nodes)."""
+
+    def __init__(self, params: PSUParams):
+        cap = params.table_params()["max_items_per_bin"] + 1
+        a = [np.zeros(cap, dtype=np.uint32) for _ in range(4)]
+        n, d = C.c_uint32(), C.c_uint32()
+        capi.check(capi.lib().apsu_b200_powers_dag(C.byref(params._c), cap, *a, C.byref(n), C.byref(d)))
+        self.nodes = {int(a[0][i]): PowersNode(int(a[0][i]), int(a[1][i]), (int(a[2][i]), int(a[3][i]))) for i in range(n.value)}
+        self._depth = d.value
+
+    def depth(self): return self._depth
+    def target_powers(self): return sorted(self.nodes)
+    def source_nodes(self): return [n for n in self.nodes.values() if n.is_source()]
+    def source_count(self): return len(self.source_nodes())
+
+
+@dataclass
+class ResultPackage:
+    """common/apsu/network/result_package.h:44-62 — one per BinBundle."""
+    bundle_idx: int
+    cache_idx: int
+    psu_result: np.ndarray  # ciphertext [2][1][N] at the last level, coefficient form
+
+
+class ReceiverDB:
+    """Device-resident receiver DB: only the query-time surface of receiver/apsu/receiver_db.h:227-292
+    plus the upload of BinBundle caches (batched_coeffs, receiver/apsu/bin_bundle.h:57)."""
+
+    def __init__(self, params: PSUParams, device: int = 0):
+        self.params = params
+        h = C.c_void_p()
+        capi.check(capi.lib().apsu_b200_ctx_create(C.byref(params._c), device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().apsu_b200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def get_params(self): return self.params
+
+    def level(self, which: int) -> int:
+        v = C.c_uint32()
+        capi.check(capi.lib().apsu_b200_ctx_level(self._h, which, C.byref(v)))
+        return v.value
+
+    def add_bin_bundle(self, bundle_idx: int, batched_coeffs) -> int:
+        """batched_coeffs: list of ndarrays, [low_L][N] for NTT-form degrees, [N] for coefficient-form ones."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in batched_coeffs]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        ci = C.c_uint32()
+        capi.check(capi.lib().apsu_b200_db_add_binbundle(self._h, bundle_idx, ptrs, len(arrs), C.byref(ci)))
+        return ci.value
+
+    def add_bin_bundle_synthetic(self, bundle_idx: int, ncoeffs: int, seed: int) -> int:
+        ci = C.c_uint32()
+        capi.check(capi.lib().apsu_b200_db_add_binbundle_synthetic(self._h, bundle_idx, ncoeffs, seed, C.byref(ci)))
+        return ci.value
+
+    def get_bin_bundle_count(self, bundle_idx: int | None = None) -> int:
+        v = C.c_uint32()
+        if bundle_idx is None:
+            capi.check(capi.lib().apsu_b200_db_total_bin_bundle_count(self._h, C.byref(v)))
+        else:
+            capi.check(capi.lib().apsu_b200_db_bin_bundle_count(self._h, bundle_idx, C.byref(v)))
+        return v.value
+
+    def bin_bundle_coeff(self, bundle_idx: int, cache_idx: int, k: int) -> np.ndarray:
+        L = C.c_uint32()
+        capi.check(capi.lib().apsu_b200_db_binbundle_coeff(self._h, bundle_idx, cache_idx, k, None, C.byref(L)))
+        N = self.params.poly_modulus_degree()
+        out = np.zeros((max(L.value, 1), N), dtype=np.uint64)
+        capi.check(capi.lib().apsu_b200_db_binbundle_coeff(self._h, bundle_idx, cache_idx, k, capi.ptr(out), C.byref(L)))
+        return out if L.value else out[0]
+
+    def stream_bytes(self) -> int:
+        v = C.c_uint64()
+        capi.check(capi.lib().apsu_b200_db_stream_bytes(self._h, C.byref(v)))
+        return v.value
+
+    def clear(self):
+        capi.check(capi.lib().apsu_b200_db_clear(self._h))
+
+
+class Query:
+    """receiver/apsu/query.h:26-89 — the already-deserialised query: source powers -> ciphertexts per
+    bundle index (host arrays), plus relinearisation keys."""
+
+    def __init__(self, src_powers, cts: np.ndarray, relin_keys: np.ndarray | None):
+        self.src_powers = np.ascontiguousarray(list(src_powers), dtype=np.uint32)
+        self.cts = np.ascontiguousarray(cts, dtype=np.uint64)  # [nsrc][bundle_idx_count][2][L][N]
+        self.relin_keys = None if relin_keys is None else np.ascontiguousarray(relin_keys, dtype=np.uint64)
+
+
+class Receiver:
+    """receiver/apsu/receiver_ddh.h:184-243 — the HE part of RunQuery."""
+
+    def __init__(self, db: ReceiverDB):
+        self.db = db
+        self._L = capi.lib()
+
+    # ---- staged API (ComputePowers / ProcessBinBundleCache) ----
+    def load_query(self, query: Query):
+        h = self.db._h
+        capi.check(self._L.apsu_b200_query_begin(h, query.src_powers, len(query.src_powers), query.cts))
+        if query.relin_keys is not None:
+            capi.check(self._L.apsu_b200_set_relin_keys(h, capi.ptr(query.relin_keys)))
+
+    def set_masks(self, masks: np.ndarray):
+        masks = np.ascontiguousarray(masks, dtype=np.uint64)
+        capi.check(self._L.apsu_b200_set_masks(self.db._h, masks, masks.shape[0]))
+
+    def encode_masks(self, slot_values: np.ndarray) -> np.ndarray:
+        v = np.ascontiguousarray(slot_values, dtype=np.uint64)
+        out = np.zeros_like(v)
+        capi.check(self._L.apsu_b200_encode_masks(self.db._h, v, v.shape[0], out))
+        return out
+
+    def ComputePowers(self):
+        capi.check(self._L.apsu_b200_compute_powers(self.db._h))
+
+    def ProcessBinBundleCaches(self):
+        capi.check(self._L.apsu_b200_eval_all(self.db._h))
+
+    def get_power(self, bundle_idx: int, power: int):
+        L, ntt = C.c_uint32(), C.c_int()
+        capi.check(self._L.apsu_b200_get_power(self.db._h, bundle_idx, power, None, C.byref(L), C.byref(ntt)))
+        out = np.zeros((2, L.value, self.db.params.poly_modulus_degree()), dtype=np.uint64)
+        capi.check(self._L.apsu_b200_get_power(self.db._h, bundle_idx, power, capi.ptr(out), C.byref(L), C.byref(ntt)))
+        return L.value, bool(ntt.value), out
+
+    def results(self):
+        n = self.db.get_bin_bundle_count()
+        N = self.db.params.poly_modulus_degree()
+        out = np.zeros((n, 2, N), dtype=np.uint64)
+        b = np.zeros(n, dtype=np.uint32)
+        c = np.zeros(n, dtype=np.uint32)
+        capi.check(self._L.apsu_b200_fetch_results(self.db._h, capi.ptr(out), capi.ptr(b), capi.ptr(c)))
+        return [ResultPackage(int(b[k]), int(c[k]), out[k].reshape(2, 1, N)) for k in range(n)]
+
+    # ---- one-call API: host buffers in, host buffers out ----
+    def RunQuery(self, query: Query, masks: np.ndarray):
+        """HE part of Receiver::RunQuery (receiver_ddh.cpp:295-369): returns one ResultPackage per BinBundle."""
+        n = self.db.get_bin_bundle_count()
+        N = self.db.params.poly_modulus_degree()
+        masks = np.ascontiguousarray(masks, dtype=np.uint64)
+        out = np.zeros((n, 2, N), dtype=np.uint64)
+        b = np.zeros(n, dtype=np.uint32)
+        c = np.zeros(n, dtype=np.uint32)
+        capi.check(self._L.apsu_b200_run_query(
+            self.db._h, query.src_powers, len(query.src_powers), capi.ptr(query.cts), capi.ptr(query.relin_keys),
+            capi.ptr(masks), masks.shape[0], capi.ptr(out), capi.ptr(b), capi.ptr(c)))
+        return [ResultPackage(int(b[k]), int(c[k]), out[k].reshape(2, 1, N)) for k in range(n)]
+
+    def timings(self) -> dict:
+        t = capi.CTimings()
+        capi.check(self._L.apsu_b200_last_timings(self.db._h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in capi.CTimings._fields_}
+
+    def set_profiling(self, on: bool):
+        capi.check(self._L.apsu_b200_set_profiling(self.db._h, int(on)))
+
+    # ---- stand-alone evaluator ops ----
+    def modulus_index(self, kind: int, i: int = 0) -> int:
+        v = C.c_uint32()
+        capi.check(self._L.apsu_b200_ctx_modulus_index(self.db._h, kind, i, C.byref(v)))
+        return v.value
+
+    def op_ntt(self, polys: np.ndarray, pattern, inverse=False) -> np.ndarray:
+        N = self.db.params.poly_modulus_degree()
+        out = np.ascontiguousarray(polys, dtype=np.uint64).copy()
+        pat = np.ascontiguousarray(list(pattern), dtype=np.uint32)
+        capi.check(self._L.apsu_b200_op_ntt(self.db._h, out.reshape(-1), out.size // N, pat, len(pat), int(inverse)))
+        return out
+
+    def op_multiply(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        n_ops, _, L, N = a.shape
+        out = np.zeros((n_ops, 3, L, N), dtype=np.uint64)
+        capi.check(self._L.apsu_b200_op_multiply(self.db._h, L, np.ascontiguousarray(a).reshape(-1), np.ascontiguousarray(b).reshape(-1), out.reshape(-1), n_ops))
+        return out
+
+    def op_relinearize(self, c3: np.ndarray) -> np.ndarray:
+        n_ops, _, L, N = c3.shape
+        out = np.zeros((n_ops, 2, L, N), dtype=np.uint64)
+        capi.check(self._L.apsu_b200_op_relinearize(self.db._h, L, np.ascontiguousarray(c3).reshape(-1), out.reshape(-1), n_ops))
+        return out
+
+    def op_mod_switch_next(self, polys: np.ndarray) -> np.ndarray:
+        n, L, N = polys.shape
+        out = np.zeros((n, L - 1, N), dtype=np.uint64)
+        capi.check(self._L.apsu_b200_op_mod_switch_next(self.db._h, L, np.ascontiguousarray(polys).reshape(-1), out.reshape(-1), n))
+        return out

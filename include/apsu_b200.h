@@ -1,0 +1,203 @@
+/*
+ * apsu_b200 — C ABI of the B200-native receiver-side homomorphic query evaluation of APSU.
+ *
+ * The reference (real-world-cryprography/APSU) has no FFI/plugin seam on this path; the seam is cut
+ * at the C++ calls below.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference tree).  All buffers are caller-owned HOST memory unless
+ * the name ends in _device; all integers are little-endian uint64_t residues in the layouts SEAL
+ * uses at that seam:
+ *     ciphertext            uint64_t[size][L][N]      (poly-major, RNS prime, coefficient)
+ *     NTT-form plaintext    uint64_t[L][N]            (L = plaintext level of the parameter set)
+ *     coefficient plaintext uint64_t[N]               (values mod t)
+ *     relinearisation keys  uint64_t[K-1][2][K][N]    (RelinKeys.data()[0][J] = size-2 ct, key level, NTT form)
+ *
+ * Every function returns 0 on success or a negative apsu_b200_status; apsu_b200_last_error() gives
+ * the message of the last failure on the calling thread.  The status classes map 1:1 onto the C++
+ * exception types the reference throws (std::invalid_argument / logic_error / runtime_error), which
+ * the C++ facade (apsu_b200/host/apsu_b200.hpp) rethrows.  A context is thread-compatible: calls on
+ * one context must be serialised by the caller (the facade does).
+ *
+ * There is NO CPU fallback: without a CUDA device apsu_b200_ctx_create fails with
+ * APSU_B200_ERR_CUDA and nothing else can be called.
+ */
+#ifndef APSU_B200_H
+#define APSU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APSU_B200_MAX_COEFF_MODULUS 8
+#define APSU_B200_MAX_QUERY_POWERS 1024
+
+typedef enum apsu_b200_status {
+    APSU_B200_OK = 0,
+    APSU_B200_ERR_INVALID_ARGUMENT = -1, /* std::invalid_argument */
+    APSU_B200_ERR_LOGIC = -2,            /* std::logic_error      */
+    APSU_B200_ERR_RUNTIME = -3,          /* std::runtime_error    */
+    APSU_B200_ERR_CUDA = -4              /* CUDA runtime failure / no device (fails loudly, no fallback) */
+} apsu_b200_status;
+
+/* PSUParams — common/apsu/psu_params.h:31-222.  Filled by apsu_b200_params_load_json or by hand and
+ * then completed by apsu_b200_params_validate (== PSUParams::initialize, psu_params.cpp:95-180). */
+typedef struct apsu_b200_params {
+    /* seal_params */
+    uint32_t poly_modulus_degree;
+    uint32_t coeff_modulus_count; /* K */
+    uint64_t plain_modulus;
+    uint64_t coeff_modulus[APSU_B200_MAX_COEFF_MODULUS];
+    /* table_params / item_params / query_params */
+    uint32_t hash_func_count;
+    uint32_t table_size;
+    uint32_t max_items_per_bin;
+    uint32_t felts_per_item;
+    uint32_t ps_low_degree;
+    uint32_t query_power_count;
+    uint32_t query_powers[APSU_B200_MAX_QUERY_POWERS]; /* ascending, always contains 1 */
+    /* derived (psu_params.cpp:148-179) */
+    uint32_t item_bit_count_per_felt;
+    uint32_t item_bit_count;
+    uint32_t items_per_bundle;
+    uint32_t bins_per_bundle;
+    uint32_t bundle_idx_count;
+} apsu_b200_params;
+
+typedef struct apsu_b200_ctx apsu_b200_ctx;
+
+const char *apsu_b200_last_error(void);
+const char *apsu_b200_version(void);
+
+/* ---- parameters ---------------------------------------------------------------------------- */
+
+/* PSUParams::Load(const std::string&) — common/apsu/psu_params.cpp:290-374 (same JSON schema;
+ * CoeffModulus::Create / PlainModulus::Batching prime selection restated). */
+int apsu_b200_params_load_json(const char *json_text, apsu_b200_params *out);
+/* PSUParams::initialize — common/apsu/psu_params.cpp:95-180. */
+int apsu_b200_params_validate(apsu_b200_params *params);
+/* seal::CoeffModulus::Create / seal::PlainModulus::Batching (call sites psu_params.cpp:355,363). */
+int apsu_b200_coeff_modulus_create(uint32_t poly_modulus_degree, const int *bit_sizes, uint32_t count, uint64_t *out);
+int apsu_b200_plain_modulus_batching(uint32_t poly_modulus_degree, int bit_size, uint64_t *out);
+
+/* PowersDag::configure(query_powers, create_powers_set(ps_low_degree, max_items_per_bin)) —
+ * common/apsu/powers.cpp:22-107, common/apsu/util/utils.cpp:146-177, call site query.cpp:78.
+ * Writes one entry per target power (ascending); p1==p2==0 marks a source node. */
+int apsu_b200_powers_dag(
+    const apsu_b200_params *params, uint32_t capacity, uint32_t *power, uint32_t *depth, uint32_t *parent1,
+    uint32_t *parent2, uint32_t *count, uint32_t *dag_depth);
+
+/* ---- context (CryptoContext + SEALContext + Evaluator) ------------------------------------- */
+
+/* CryptoContext(SEALContext(parms, true, tc128)) + set_evaluator — common/apsu/crypto_context.h:28-125,
+ * ReceiverDB ctor receiver/apsu/receiver_db.cpp:640-674.  Builds the modulus chain, NTT tables and
+ * BEHZ constants on `device` (a CUDA ordinal). */
+int apsu_b200_ctx_create(const apsu_b200_params *params, int device, apsu_b200_ctx **out);
+void apsu_b200_ctx_destroy(apsu_b200_ctx *ctx);
+/* Run all work of this context on an existing cudaStream_t (e.g. torch's current stream). */
+int apsu_b200_ctx_set_stream(apsu_b200_ctx *ctx, void *cuda_stream);
+int apsu_b200_ctx_synchronize(apsu_b200_ctx *ctx);
+/* number of RNS primes of: 0 = first data level, 1 = DB plaintexts / low powers, 2 = high powers,
+ * 3 = key level (get_parms_id_for_chain_idx, common/apsu/util/utils.cpp:179-189). */
+int apsu_b200_ctx_level(const apsu_b200_ctx *ctx, int which, uint32_t *num_primes);
+
+/* ---- ReceiverDB: device-resident BinBundle caches ------------------------------------------- */
+
+/* One BatchedPlaintextPolyn (receiver/apsu/bin_bundle.h:52-134): coeffs[k] is the k-th entry of
+ * batched_coeffs with the SEAL header stripped — NTT form uint64_t[Lp][N] unless k==0 (ps_low_degree==0)
+ * or k % (ps_low_degree+1)==0 (ps_low_degree>0), in which case coefficient form uint64_t[N]
+ * (bin_bundle.cpp:413).  Appends a BinBundle at bundle_idx (ReceiverDB::bin_bundles_[bundle_idx],
+ * receiver_db.h:375) and returns its cache index. */
+int apsu_b200_db_add_binbundle(
+    apsu_b200_ctx *ctx, uint32_t bundle_idx, const uint64_t *const *coeffs, uint32_t ncoeffs, uint32_t *cache_idx);
+/* Synthetic BinBundle for throughput runs: every plaintext word uniform in [0,q_j) / [0,t), generated on
+ * the device from a counter-based splitmix64 stream (same stream as the oracle's synthetic fill). */
+int apsu_b200_db_add_binbundle_synthetic(
+    apsu_b200_ctx *ctx, uint32_t bundle_idx, uint32_t ncoeffs, uint64_t seed, uint32_t *cache_idx);
+/* "next" row f1 — BinBundle::regen_cache (bin_bundle.cpp:934-1041): build the cache on the device from
+ * raw bins: polyn_with_roots per bin (interpolate.cpp:63-80), column gather, BatchEncoder::encode,
+ * transform_to_ntt (bin_bundle.cpp:366-430).  bin_sizes[bins_per_bundle], roots concatenated. */
+int apsu_b200_db_add_binbundle_from_bins(
+    apsu_b200_ctx *ctx, uint32_t bundle_idx, const uint32_t *bin_sizes, const uint64_t *roots, uint32_t *cache_idx);
+/* ReceiverDB::get_bin_bundle_count(bundle_idx) / () — receiver_db.cpp:742-760. */
+int apsu_b200_db_bin_bundle_count(const apsu_b200_ctx *ctx, uint32_t bundle_idx, uint32_t *count);
+int apsu_b200_db_total_bin_bundle_count(const apsu_b200_ctx *ctx, uint32_t *count);
+/* batched_coeffs.size() of one BinBundle and a copy of one plaintext back to the host (tests). */
+int apsu_b200_db_binbundle_ncoeffs(const apsu_b200_ctx *ctx, uint32_t bundle_idx, uint32_t cache_idx, uint32_t *ncoeffs);
+int apsu_b200_db_binbundle_coeff(
+    const apsu_b200_ctx *ctx, uint32_t bundle_idx, uint32_t cache_idx, uint32_t k, uint64_t *out, uint32_t *num_primes);
+/* bytes of DB plaintext the evaluation stream reads per query (SURVEY.md §8d algorithmic bytes). */
+int apsu_b200_db_stream_bytes(const apsu_b200_ctx *ctx, uint64_t *bytes);
+int apsu_b200_db_clear(apsu_b200_ctx *ctx);
+
+/* ---- query ---------------------------------------------------------------------------------- */
+
+/* CryptoContext::set_evaluator(query.relin_keys()) — receiver/apsu/receiver_ddh.cpp:175-176. */
+int apsu_b200_set_relin_keys(apsu_b200_ctx *ctx, const uint64_t *keys);
+/* Load Q_i^e into all_powers[bundle_idx][e] — receiver_ddh.cpp:295-322.
+ * cts: uint64_t[nsrc][bundle_idx_count][2][L_first][N], coefficient form; src_powers must equal the
+ * parameter set's query_powers (Query validation, receiver/apsu/query.cpp:68-111). */
+int apsu_b200_query_begin(apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts);
+/* Receiver::ComputePowers for every bundle index — receiver_ddh.cpp:325-333, 390-483. */
+int apsu_b200_compute_powers(apsu_b200_ctx *ctx);
+/* Debug/parity: copy all_powers[bundle_idx][power] (size-2 ciphertext) to the host. */
+int apsu_b200_get_power(
+    apsu_b200_ctx *ctx, uint32_t bundle_idx, uint32_t power, uint64_t *out, uint32_t *num_primes, int *is_ntt_form);
+/* Masks: dense table uint64_t[alpha_max_cache_count][bundle_idx_count][N] of coefficient-form
+ * plaintexts, indexed pack_idx = bundle_idx + cache_idx*bundle_idx_count (receiver_ddh.cpp:346;
+ * SURVEY.md Appendix C.1).  apsu_b200_encode_masks does BatchEncoder::encode (receiver_ddh.cpp:275)
+ * on the device from slot values uint64_t[npack][N]. */
+int apsu_b200_set_masks(apsu_b200_ctx *ctx, const uint64_t *masks, uint32_t npack);
+int apsu_b200_encode_masks(apsu_b200_ctx *ctx, const uint64_t *slot_values, uint32_t npack, uint64_t *masks_out);
+/* Receiver::ProcessBinBundleCache for every BinBundle — receiver_ddh.cpp:340-369, 485-535 →
+ * BatchedPlaintextPolyn::eval / eval_patstock (bin_bundle.cpp:106-174, 192-360).  Results stay on the
+ * device until fetched.  Order of results: bundle_idx major, cache_idx minor. */
+int apsu_b200_eval_all(apsu_b200_ctx *ctx);
+/* rp->psu_result for every BinBundle: out = uint64_t[total_bin_bundle_count][2][N] (one prime), plus
+ * the ResultPackage bundle_idx / cache_idx fields (network/result_package.h:44-62). Either index
+ * array may be NULL. */
+int apsu_b200_fetch_results(apsu_b200_ctx *ctx, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
+/* The whole HE part of Receiver::RunQuery (receiver_ddh.cpp:295-369) through host buffers:
+ * query_begin + set_relin_keys + set_masks + compute_powers + eval_all + fetch_results. */
+int apsu_b200_run_query(
+    apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys,
+    const uint64_t *masks, uint32_t npack, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
+/* Device-resident variant used for sharded runs: cts/keys/masks already on this context's GPU. */
+int apsu_b200_query_begin_device(apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const void *cts_device);
+int apsu_b200_set_relin_keys_device(apsu_b200_ctx *ctx, const void *keys_device);
+int apsu_b200_set_masks_device(apsu_b200_ctx *ctx, const void *masks_device, uint32_t npack);
+/* device pointer + byte size of the result buffer filled by eval_all (valid until the next eval_all) */
+int apsu_b200_results_device(apsu_b200_ctx *ctx, void **ptr, uint64_t *bytes);
+
+/* ---- SEAL Evaluator calls on the path, as stand-alone batched device operations (K2–K8) ----- */
+/* modulus selector for apsu_b200_op_ntt: index into [coeff_modulus[0..K-1], m_sk, B_0.., plain_modulus] */
+int apsu_b200_ctx_modulus_index(const apsu_b200_ctx *ctx, int kind /*0=coeff,1=m_sk,2=B,3=plain*/, uint32_t i, uint32_t *index);
+/* Evaluator::transform_to_ntt_inplace / transform_from_ntt_inplace on `count` polynomials uint64_t[count][N],
+ * polynomial p reduced modulo modulus_index[p % pattern_len]. */
+int apsu_b200_op_ntt(apsu_b200_ctx *ctx, uint64_t *polys, uint32_t count, const uint32_t *modulus_index, uint32_t pattern_len, int inverse);
+/* Evaluator::multiply / square (size 2 x size 2 -> size 3) at level `num_primes`, n_ops independent products.
+ * a,b: uint64_t[n_ops][2][L][N]; out: uint64_t[n_ops][3][L][N]; coefficient form. */
+int apsu_b200_op_multiply(apsu_b200_ctx *ctx, uint32_t num_primes, const uint64_t *a, const uint64_t *b, uint64_t *out, uint32_t n_ops);
+/* Evaluator::relinearize_inplace (size 3 -> 2): in uint64_t[n_ops][3][L][N], out uint64_t[n_ops][2][L][N]. */
+int apsu_b200_op_relinearize(apsu_b200_ctx *ctx, uint32_t num_primes, const uint64_t *in, uint64_t *out, uint32_t n_ops);
+/* Evaluator::mod_switch_to_next_inplace on n_polys polynomials uint64_t[n_polys][L][N] -> [n_polys][L-1][N]. */
+int apsu_b200_op_mod_switch_next(apsu_b200_ctx *ctx, uint32_t num_primes, const uint64_t *in, uint64_t *out, uint32_t n_polys);
+
+/* ---- measurement ----------------------------------------------------------------------------- */
+typedef struct apsu_b200_timings {
+    float compute_powers_ms;  /* "Receiver::ComputePowers" scope, device time on the context stream */
+    float eval_ms;            /* all "Receiver::ProcessBinBundleCache" scopes */
+    float db_stream_ms;       /* sum of DB-stream MAC kernel launches inside eval */
+    uint64_t db_stream_bytes; /* algorithmic plaintext bytes those launches covered */
+    uint32_t db_stream_launches;
+    uint32_t kernel_launches; /* kernels launched by the last compute_powers + eval_all */
+} apsu_b200_timings;
+int apsu_b200_last_timings(apsu_b200_ctx *ctx, apsu_b200_timings *out);
+/* when enabled, DB-stream launches are individually timed with CUDA events (adds event overhead only) */
+int apsu_b200_set_profiling(apsu_b200_ctx *ctx, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APSU_B200_H */
