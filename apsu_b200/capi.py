@@ -99,6 +99,7 @@ SIGNATURES = {
     "apsu_b200_set_relin_keys_device": (C.c_int, [vp, vp]),
     "apsu_b200_set_masks_device": (C.c_int, [vp, vp, C.c_uint32]),
     "apsu_b200_results_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]),
+    "apsu_b200_copy_results_device": (C.c_int, [vp, vp]),
     "apsu_b200_ctx_modulus_index": (C.c_int, [vp, C.c_int, C.c_uint32, C.POINTER(C.c_uint32)]),
     "apsu_b200_op_ntt": (C.c_int, [vp, u64p, C.c_uint32, u32p, C.c_uint32, C.c_int]),
     "apsu_b200_op_multiply": (C.c_int, [vp, C.c_uint32, u64p, u64p, u64p, C.c_uint32]),

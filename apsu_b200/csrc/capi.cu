@@ -283,6 +283,16 @@ int apsu_b200_results_device(apsu_b200_ctx *ctx, void **ptr, uint64_t *bytes)
 {
     return guarded([&] { E(ctx).results_device(ptr, bytes); });
 }
+int apsu_b200_copy_results_device(apsu_b200_ctx *ctx, void *dst_device)
+{
+    return guarded([&] {
+        Engine &e = E(ctx);
+        void *src = nullptr;
+        uint64_t bytes = 0;
+        e.results_device(&src, &bytes);
+        if (bytes) APSU_CUDA_CHECK(cudaMemcpyAsync(need(dst_device, "dst_device"), src, bytes, cudaMemcpyDeviceToDevice, e.ctx.stream));
+    });
+}
 int apsu_b200_run_query(
     apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys,
     const uint64_t *masks, uint32_t npack, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx)

@@ -1,0 +1,438 @@
+#!/usr/bin/env python3
+"""bench.py — receiver query evaluation (ComputePowers + eval/eval_patstock over every BinBundle).
+
+Metric (BASELINE.json): BinBundles/s and query-eval ms for parameters/16M-4096.json on synthetic sets
+of the named size (receiver set 2^24), at N = 1/2/4/8 B200 (BinBundles sharded, strong scaling).
+
+  python bench.py --gpus 1 --steps K --warmup W          # this framework, one JSON line
+  python bench.py --impl reference ...                   # the CPU restatement of the reference path
+  torchrun ... bench.py --gpus N ...                     # one rank per GPU
+
+A "step" is one query: powers of the query ciphertexts for every bundle index, then the polynomial
+evaluation of every BinBundle down to the result ciphertexts.  `value` times that with query, keys and
+masks resident in HBM; `e2e` times the C-ABI call apsu_b200_run_query with pinned HOST buffers (H2D of the
+query/keys/masks and D2H of the results inside the timed region, plus the NCCL broadcast/gather for N>1).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = "16M-4096"
+DB_LOG2 = 24
+SEEDS = dict(db=0xD8, query=0x51, key=0x4B, mask=0x4D)
+
+
+# ------------------------------------------------------------------------------------------------
+# workload: bundle shapes of a 2^24-item receiver DB under parameters/16M-4096.json
+# ------------------------------------------------------------------------------------------------
+def load_params_json(name: str) -> dict:
+    table = json.loads((ROOT / "tests" / "golden" / "parameters.json").read_text())
+    return table[name + ".json"]
+
+
+def simulate_bundle_degrees(pj: dict, db_log2: int, seed: int):
+    """Degrees (max bin load) of every BinBundle after inserting 2^db_log2 items with all hash functions
+    (receiver/apsu/receiver_db.cpp:70-79, 280-288) and first-fit over bundles with capacity
+    max_items_per_bin-1 per bin (receiver_db.cpp:370-433).  Items land uniformly on table slots; an item's
+    felts occupy the felts_per_item bins of its slot, so the bins of one slot always carry the same load."""
+    tp, ip, sp = pj["table_params"], pj["item_params"], pj["seal_params"]
+    N = sp["poly_modulus_degree"]
+    items_per_bundle = N // ip["felts_per_item"]
+    bic = tp["table_size"] // items_per_bundle
+    cap = tp["max_items_per_bin"] - 1
+    rng = np.random.default_rng(seed)
+    loads = rng.multinomial((1 << db_log2) * tp["hash_func_count"], np.full(tp["table_size"], 1.0 / tp["table_size"]))
+    degrees = []
+    for b in range(bic):
+        slot_loads = loads[b * items_per_bundle:(b + 1) * items_per_bundle]
+        n_bundles = int(-(-slot_loads.max() // cap))
+        degrees.append([int(np.clip(slot_loads - c * cap, 0, cap).max()) for c in range(n_bundles)])
+    return degrees
+
+
+def bundle_bytes(pj: dict, ncoeffs: int, low_L: int) -> int:
+    ps = pj["query_params"]["ps_low_degree"]
+    N = pj["seal_params"]["poly_modulus_degree"]
+    n_plain = (ncoeffs + ps) // (ps + 1) if ps else 1
+    return ((ncoeffs - n_plain) * low_L + n_plain) * N * 8
+
+
+def shard(degrees, world: int):
+    """contiguous partition of the (bundle_idx, cache_idx) list by cumulative plaintext count, so that a rank
+    touches as few bundle indices as possible (it recomputes the query powers of each index it owns)."""
+    flat = [(b, c, d + 1) for b, row in enumerate(degrees) for c, d in enumerate(row)]
+    total = sum(w for _, _, w in flat)
+    parts = [[] for _ in range(world)]
+    acc = 0
+    for b, c, w in flat:
+        r = min(world - 1, int((acc + w / 2) * world / total))
+        parts[r].append((b, c, w - 1))
+        acc += w
+    return parts
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic query material (uniform residues: timing is data independent; the same arrays feed the
+# oracle for the CPU baseline and the bit-exact spot check)
+# ------------------------------------------------------------------------------------------------
+def synth_query(primes, t, N, first_L, K, nsrc, bic, npack, seed):
+    rng = np.random.default_rng(seed)
+    cts = np.zeros((nsrc, bic, 2, first_L, N), dtype=np.uint64)
+    for j in range(first_L):
+        cts[:, :, :, j, :] = rng.integers(0, primes[j], size=(nsrc, bic, 2, N), dtype=np.uint64)
+    relin = np.zeros((K - 1, 2, K, N), dtype=np.uint64)
+    for j in range(K):
+        relin[:, :, j, :] = rng.integers(0, primes[j], size=(K - 1, 2, N), dtype=np.uint64)
+    masks = rng.integers(0, t, size=(npack, N), dtype=np.uint64)
+    return cts, relin, masks
+
+
+def cpu_baseline(pj, name, degrees, cts, relin, masks, sample_pairs, threads):
+    """Times the oracle (CPU restatement of the reference's SEAL path) on a bounded sample: ComputePowers
+    for ONE bundle index + evaluation of `sample_pairs` BinBundles; extrapolates linearly in the number of
+    bundle indices and in plaintext count.  Returns (dict, {pair: result ndarray})."""
+    from oracle import oracle as O
+    p = O.Params(pj, name + ".json")
+    ctx = O.Context.from_params(p)
+    bic = p.bundle_idx_count
+    db = O.ReceiverDB(ctx, p)
+    b0 = sample_pairs[0][0]
+    # oracle DB holds only bundle index b0's sampled bundles (others empty => ComputePowers skipped there)
+    local = {}
+    for (b, c) in sample_pairs:
+        assert b == b0
+        local[(b, c)] = db.add_bundle_synthetic(b, degrees[b][c] + 1, SEEDS["db"] * 1000 + b * 64 + c)
+    ses = db.run_query(p.query_powers, cts, relin, None, threads=threads, powers_only=True)
+    powers_ms_one = ses.powers_ms
+    # masks for the local cache indices
+    alpha = max(local.values()) + 1
+    m = np.zeros((alpha * bic, p.N), dtype=np.uint64)
+    for (b, c), lc in local.items():
+        m[b + lc * bic] = masks[b + c * bic]
+    pairs_local = [(b, local[(b, c)]) for (b, c) in sample_pairs]
+    eval_ms = ses.eval_subset(pairs_local, relin, m, threads=threads)
+    res = {}
+    for (bb, lc, ct) in ses.results():
+        for (b, c), l2 in local.items():
+            if (bb, lc) == (b, l2):
+                res[(b, c)] = ct
+    sample_coeffs = sum(degrees[b][c] + 1 for b, c in sample_pairs)
+    total_coeffs = sum(d + 1 for row in degrees for d in row)
+    n_active = sum(1 for row in degrees if row)
+    est_ms = powers_ms_one * n_active + eval_ms * total_coeffs / sample_coeffs
+    n_bundles = sum(len(r) for r in degrees)
+    info = {
+        "value": n_bundles / (est_ms / 1e3), "unit": "BinBundles/s", "cores": threads, "kind": "port",
+        "sample": f"oracle (SEAL-algorithm restatement, not SEAL), -t {threads}: ComputePowers for 1 of {n_active} bundle indices "
+                  f"({powers_ms_one:.0f} ms) + eval_patstock of {len(sample_pairs)} BinBundles / {sample_coeffs} of {total_coeffs} plaintexts "
+                  f"({eval_ms:.0f} ms); extrapolated linearly to the whole query = {est_ms:.0f} ms",
+        "query_eval_ms_est": est_ms, "host_cores": os.cpu_count(),
+    }
+    return info, res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="apsu_b200", choices=["apsu_b200", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--db-log2", type=int, default=DB_LOG2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=None, help="BinBundles per evaluation chunk (APSU_B200_CHUNK)")
+    args = ap.parse_args()
+    if args.chunk:
+        os.environ["APSU_B200_CHUNK"] = str(args.chunk)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    name = args.workload
+    pj = load_params_json(name)
+    degrees = simulate_bundle_degrees(pj, args.db_log2, SEEDS["db"])
+    n_bundles = sum(len(r) for r in degrees)
+    config = {
+        "workload": f"parameters/{name}.json, receiver set 2^{args.db_log2} (synthetic), {n_bundles} BinBundles "
+                    f"{[len(r) for r in degrees]} per bundle index, degrees {degrees}",
+        "l2": "DB plaintext stream per query is larger than L2 (no flush needed)",
+        "seeds": SEEDS, "parallelism": f"BinBundles sharded over {world} GPU(s); query powers recomputed per owning GPU",
+    }
+
+    # ---------------- reference arm: the CPU restatement, all host threads ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import oracle as O
+        p = O.Params(pj, name + ".json")
+        threads = os.cpu_count() or 1
+        cts, relin, masks = synth_query(p.primes, p.t, p.N, p.first_L, p.K, len(p.query_powers), p.bundle_idx_count,
+                                        max(len(r) for r in degrees) * p.bundle_idx_count, SEEDS["query"])
+        b0 = 0
+        full = [(b0, c) for c, d in enumerate(degrees[b0]) if d + 1 == p.max_items_per_bin][:1]
+        small = [(b0, len(degrees[b0]) - 1)]
+        sample = full + [s for s in small if s not in full]
+        vals = []
+        for _ in range(args.warmup + args.steps):
+            info, _ = cpu_baseline(pj, name, degrees, cts, relin, masks, sample, threads)
+            vals.append(info)
+        vals = vals[args.warmup:] or vals
+        ms = float(np.mean([v["query_eval_ms_est"] for v in vals]))
+        info = vals[-1]
+        info["value"] = n_bundles / (ms / 1e3)
+        print(json.dumps({
+            "impl": "reference", "metric": "receiver_query_eval_binbundles_per_s", "value": info["value"], "unit": "BinBundles/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+            "cpu_baseline": info,
+            "e2e": {"value": info["value"], "unit": "BinBundles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ---------------- this framework ----------------
+    import torch
+    import ctypes as C
+    import apsu_b200
+    from apsu_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: apsu_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    params = apsu_b200.PSUParams.Load(json.dumps(pj))
+    N, t, primes = params.poly_modulus_degree(), params.plain_modulus(), params.coeff_modulus()
+    K = len(primes)
+    bic = params.bundle_idx_count()
+    db = apsu_b200.ReceiverDB(params, local_rank)
+    rx = apsu_b200.Receiver(db)
+    first_L, low_L = db.level(0), db.level(1)
+    stream = torch.cuda.Stream()
+    capi.check(capi.lib().apsu_b200_ctx_set_stream(db._h, C.c_void_p(stream.cuda_stream)))
+
+    # this rank's shard; local cache indices are dense per bundle index
+    mine = shard(degrees, world)[rank]
+    local_of = {}
+    for (b, c, d) in mine:
+        local_of[(b, c)] = db.add_bin_bundle_synthetic(b, d + 1, SEEDS["db"] * 1000 + b * 64 + c)
+    my_bytes = db.stream_bytes()
+    total_bytes = sum(bundle_bytes(pj, d + 1, low_L) for row in degrees for d in row)
+
+    nsrc = len(params.query_powers())
+    src_powers = np.array(params.query_powers(), dtype=np.uint32)
+    npack_global = max(len(r) for r in degrees) * bic
+    cts, relin, masks = synth_query(primes, t, N, first_L, K, nsrc, bic, npack_global, SEEDS["query"])
+    alpha_local = (max(local_of.values()) + 1) if local_of else 1
+    masks_local = np.zeros((alpha_local * bic, N), dtype=np.uint64)
+    for (b, c), lc in local_of.items():
+        masks_local[b + lc * bic] = masks[b + c * bic]
+
+    # pinned host staging for the e2e path
+    def pinned(a):
+        tns = torch.from_numpy(a.view(np.int64)).pin_memory()
+        return tns, tns.numpy().view(np.uint64)
+    cts_t, cts_p = pinned(cts)
+    relin_t, relin_p = pinned(relin)
+    masks_t, masks_p = pinned(masks_local)
+    n_local = len(mine)
+    out_t = torch.empty((max(n_local, 1), 2, N), dtype=torch.int64).pin_memory()
+    out_p = out_t.numpy().view(np.uint64)
+
+    lib = capi.lib()
+    h = db._h
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident path: inputs in HBM before the timed region ----
+    with torch.cuda.stream(stream):
+        capi.check(lib.apsu_b200_query_begin(h, src_powers, nsrc, cts_p.reshape(-1)))
+        capi.check(lib.apsu_b200_set_relin_keys(h, capi.ptr(relin_p)))
+        capi.check(lib.apsu_b200_set_masks(h, masks_p.reshape(-1), masks_p.shape[0]))
+        rx.set_profiling(True)
+
+        def step_resident():
+            capi.check(lib.apsu_b200_compute_powers(h))
+            capi.check(lib.apsu_b200_eval_all(h))
+
+        for _ in range(args.warmup):
+            step_resident()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per_step = []
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_resident()
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms_total = e0.elapsed_time(e1)
+        tm = rx.timings()  # last step: scopes + DB-stream kernel launches timed live with CUDA events
+        ms_step_local = ms_total / args.steps
+
+        # ---- e2e path: host buffers through the C ABI (+ NCCL broadcast / gather for N>1) ----
+        bidx = np.zeros(max(n_local, 1), dtype=np.uint32)
+        cidx = np.zeros(max(n_local, 1), dtype=np.uint32)
+        if dist is not None:
+            d_cts = torch.empty(cts_t.shape, dtype=torch.int64, device="cuda")
+            d_relin = torch.empty(relin_t.shape, dtype=torch.int64, device="cuda")
+            counts = [len(x) for x in shard(degrees, world)]
+            gather_list = [torch.empty((max(cn, 1), 2, N), dtype=torch.int64, device="cuda") for cn in counts] if rank == 0 else None
+
+        def step_e2e():
+            if dist is None:
+                capi.check(lib.apsu_b200_run_query(h, src_powers, nsrc, capi.ptr(cts_p), capi.ptr(relin_p), capi.ptr(masks_p),
+                                                   masks_p.shape[0], capi.ptr(out_p), capi.ptr(bidx), capi.ptr(cidx)))
+            else:
+                # rank 0 holds the query on the host: H2D once, NCCL broadcast over NVLink, evaluate, gather
+                if rank == 0:
+                    d_cts.copy_(cts_t, non_blocking=True)
+                    d_relin.copy_(relin_t, non_blocking=True)
+                dist.broadcast(d_cts, 0)
+                dist.broadcast(d_relin, 0)
+                capi.check(lib.apsu_b200_query_begin_device(h, src_powers, nsrc, C.c_void_p(d_cts.data_ptr())))
+                capi.check(lib.apsu_b200_set_relin_keys_device(h, C.c_void_p(d_relin.data_ptr())))
+                capi.check(lib.apsu_b200_set_masks(h, masks_p.reshape(-1), masks_p.shape[0]))
+                capi.check(lib.apsu_b200_compute_powers(h))
+                capi.check(lib.apsu_b200_eval_all(h))
+                res = torch.empty((max(n_local, 1), 2, N), dtype=torch.int64, device="cuda")
+                if n_local:
+                    capi.check(lib.apsu_b200_copy_results_device(h, C.c_void_p(res.data_ptr())))
+                dist.gather(res, gather_list, dst=0)
+                if rank == 0:
+                    for g in gather_list:
+                        g.cpu()
+
+        for _ in range(args.warmup):
+            step_e2e()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        f1.record(stream)
+        barrier()
+        e2e_ms_local = max(f0.elapsed_time(f1), (time.perf_counter() - w0) * 1e3) / args.steps
+
+    # max over ranks
+    if dist is not None:
+        v = torch.tensor([ms_step_local, e2e_ms_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms = float(v[0]), float(v[1])
+    else:
+        ms_step, e2e_ms = ms_step_local, e2e_ms_local
+
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        mac_gbs = (tm["db_stream_bytes"] / 1e9) / (tm["db_stream_ms"] / 1e3) if tm["db_stream_ms"] else 0.0
+        launches = max(tm["db_stream_launches"], 1)
+        out = {
+            "metric": "receiver_query_eval_binbundles_per_s", "value": n_bundles / (ms_step / 1e3), "unit": "BinBundles/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+            "query_eval_ms": ms_step,
+            "scopes_ms_rank0_last_step": {"Receiver::ComputePowers": tm["compute_powers_ms"], "Receiver::ProcessBinBundleCache(all)": tm["eval_ms"]},
+            "db_stream": {"bytes_per_query": total_bytes, "bytes_rank0": my_bytes, "effective_gbs_whole_eval": (my_bytes / 1e9) / (tm["eval_ms"] / 1e3) if tm["eval_ms"] else None},
+            "roofline": {
+                "kernel": "k_db_mac (DB-stream multiply-accumulate, K1)", "bound": "hbm", "achieved": mac_gbs, "peak": hbm_peak,
+                "unit": "GB/s", "frac": mac_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "launches_timed": tm["db_stream_launches"], "avg_launch_ms": tm["db_stream_ms"] / launches,
+                "algorithmic_bytes_per_launch": tm["db_stream_bytes"] / launches,
+                "share_of_step": tm["db_stream_ms"] / (tm["compute_powers_ms"] + tm["eval_ms"]) if tm["eval_ms"] else None,
+            },
+            "clocks": clocks,
+            "e2e": {"value": n_bundles / (e2e_ms / 1e3), "unit": "BinBundles/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(cts.nbytes + relin.nbytes + masks_local.nbytes),
+                    "d2h_bytes_per_step": int(n_bundles * 2 * N * 8)},
+            "gpu_launches": int(tm["kernel_launches"]) * args.steps,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            # bounded CPU sample of the same workload + bit-exact spot check of those BinBundles
+            b0 = mine[0][0]
+            full = [(b, c) for (b, c, d) in mine if b == b0 and d + 1 == pj["table_params"]["max_items_per_bin"]][:1]
+            small = [(b, c) for (b, c, d) in mine if b == b0][-1:]
+            sample = full + [s for s in small if s not in full]
+            info, ref = cpu_baseline(pj, name, degrees, cts, relin, masks, sample, os.cpu_count() or 1)
+            out["cpu_baseline"] = info
+            got = {(r.bundle_idx, r.cache_idx): r.psu_result.reshape(2, -1) for r in rx.results()}
+            ok = all(np.array_equal(got[(b, local_of[(b, c)])], ref[(b, c)]) for (b, c) in sample)
+            out["parity_sample"] = {"bundles": sample, "bit_exact_vs_oracle": bool(ok)}
+            if not ok:
+                out["INVALID"] = "GPU results differ from the oracle on the sampled BinBundles"
+        print(json.dumps(out))
+    db.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -169,6 +169,9 @@ int apsu_b200_set_relin_keys_device(apsu_b200_ctx *ctx, const void *keys_device)
 int apsu_b200_set_masks_device(apsu_b200_ctx *ctx, const void *masks_device, uint32_t npack);
 /* device pointer + byte size of the result buffer filled by eval_all (valid until the next eval_all) */
 int apsu_b200_results_device(apsu_b200_ctx *ctx, void **ptr, uint64_t *bytes);
+/* asynchronous device-to-device copy of the results into a caller-owned device buffer (e.g. a torch tensor
+ * that is then gathered with NCCL); ordered on the context stream. */
+int apsu_b200_copy_results_device(apsu_b200_ctx *ctx, void *dst_device);
 
 /* ---- SEAL Evaluator calls on the path, as stand-alone batched device operations (K2–K8) ----- */
 /* modulus selector for apsu_b200_op_ntt: index into [coeff_modulus[0..K-1], m_sk, B_0.., plain_modulus] */
