@@ -1,4 +1,5 @@
 #include "engine.hpp"
+#include "db_stream.cuh"
 #include "eval_kernels.cuh"
 #include "hostmath.hpp"
 #include "kernels.cuh"
@@ -556,7 +557,7 @@ void Engine::build_plan()
                 all.push_back(BRef{ s.get(), (uint32_t)result_order_.size() });
                 result_order_.emplace_back(b, s->cache_idx);
             }
-        results_.ensure((size_t)all.size() * 2 * N);
+        results_.ensure((size_t)std::max<size_t>(all.size(), 1) * 2 * N);
         uint32_t alpha_max = 0;
         for (auto &v : db) alpha_max = std::max<uint32_t>(alpha_max, (uint32_t)v.size());
         npack_needed_ = alpha_max * bic;
@@ -564,197 +565,204 @@ void Engine::build_plan()
         uint32_t chunk = 2;
         if (const char *ev = std::getenv("APSU_B200_CHUNK")) chunk = (uint32_t)std::max(1, atoi(ev));
         const uint32_t drops = Ll - Lh;
-        uint32_t lazy_bound = 0xFFFFFFFFu;
-        {
-            int maxbits = 0;
-            for (uint32_t j = 0; j < Ll; j++) maxbits = std::max(maxbits, hm::bit_length(p.coeff_modulus[j]));
-            int room = 128 - 2 * maxbits;
-            if (room < 31) lazy_bound = 1u << room;
-        }
+        if (drops > 1) throw std::logic_error("unexpected level gap between low and high powers");
 
-        for (size_t c0 = 0; c0 < all.size(); c0 += chunk) {
-            arena_.top = eval_base;
-            size_t c1 = std::min(all.size(), c0 + chunk);
-            std::vector<FinalizeJob> fin_direct, fin_ps;
-            std::vector<MacGroup> groups;     // stage A (low level)
-            std::vector<MacGroup> k8groups;   // K8 (high level)
-            std::vector<MulTermsJob> mulj;
-            uint64_t mac_bytes = 0;
-
-            struct Job {
-                BinBundleStore *s;
-                uint32_t bslot; // PS bundle slot within the chunk
-                uint32_t i, nterms;
-            };
-            std::vector<Job> jobs;                 // PS inner polynomials i >= 1
-            std::vector<BRef> psb, direct;         // PS bundles / direct-evaluation bundles
-            for (size_t k = c0; k < c1; k++) {
-                uint32_t degree = all[k].s->ncoeffs - 1;
-                bool using_ps = ps > 1 && ps < degree; // receiver_ddh.cpp:515-517
-                (using_ps ? psb : direct).push_back(all[k]);
+        auto add_job = [&](std::vector<MacGroup> &gs, uint32_t pow_idx, uint32_t tstride, uint32_t cstride, const u64 *coeff, uint32_t nterms, uint32_t out) {
+            if (gs.empty() || gs.back().njobs == kMacJobs || gs.back().pow_idx != pow_idx) {
+                MacGroup g;
+                std::memset(&g, 0, sizeof(g));
+                g.pow_idx = pow_idx;
+                g.pow_term_stride = tstride;
+                g.pow_comp_stride = cstride;
+                gs.push_back(g);
             }
-            // -------- direct evaluation (bin_bundle.cpp:106-174) --------
-            // MAC over degrees 1..D, iNTT, finalize
-            const uint32_t acc0 = arena_.take((size_t)direct.size() * 2 * Ll);
-            auto add_job = [&](std::vector<MacGroup> &gs, uint32_t pow_idx, uint32_t tstride, uint32_t cstride, const u64 *coeff, uint32_t nterms, uint32_t out) {
-                if (gs.empty() || gs.back().njobs == kMacJobs || gs.back().pow_idx != pow_idx) {
-                    MacGroup g;
-                    std::memset(&g, 0, sizeof(g));
-                    g.pow_idx = pow_idx;
-                    g.pow_term_stride = tstride;
-                    g.pow_comp_stride = cstride;
-                    gs.push_back(g);
-                }
-                MacGroup &g = gs.back();
-                g.coeff[g.njobs] = coeff;
-                g.nterms[g.njobs] = nterms;
-                g.out_idx[g.njobs] = out;
-                g.njobs++;
-                g.max_terms = std::max(g.max_terms, nterms);
-            };
-            for (size_t k = 0; k < direct.size(); k++) {
-                BinBundleStore *s = direct[k].s;
-                uint32_t degree = s->ncoeffs - 1;
+            MacGroup &g = gs.back();
+            g.coeff[g.njobs] = coeff;
+            g.nterms[g.njobs] = nterms;
+            g.out_idx[g.njobs] = out;
+            g.njobs++;
+            g.max_terms = std::max(g.max_terms, nterms);
+        };
+
+        // ===== stage A (whole DB, one launch): every NTT-domain accumulation job of every BinBundle =====
+        struct Job {
+            BinBundleStore *s;
+            uint32_t bslot; // index into psb
+            uint32_t i, nterms;
+        };
+        struct PSB {
+            BRef ref;
+            uint32_t job_lo = 0, job_hi = 0;
+        };
+        std::vector<BRef> direct;
+        std::vector<PSB> psb;
+        std::vector<Job> jobs; // PS inner polynomials i >= 1, ordered by bundle
+        for (auto &r : all) {
+            uint32_t degree = r.s->ncoeffs - 1;
+            bool using_ps = ps > 1 && ps < degree; // receiver_ddh.cpp:515-517
+            if (!using_ps) {
                 if (degree > nlow) throw std::logic_error("not enough ciphertext powers available");
-                uint32_t out = acc0 + (uint32_t)k * 2 * Ll;
-                // degree 0: the accumulator is the zero ciphertext (a job with no terms writes zeros)
-                add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, s->ntt_coeffs.p, degree, out);
-                mac_bytes += (uint64_t)degree * Ll * N * 8;
-                FinalizeJob f;
-                std::memset(&f, 0, sizeof(f));
-                f.src[0] = out;
-                f.src[1] = f.src[2] = kNoSrc;
-                f.coeff0 = s->plain_coeffs.p;
-                f.pack = s->bundle_idx + s->cache_idx * bic;
-                f.slot = direct[k].k;
-                fin_direct.push_back(f);
+                direct.push_back(r);
+                continue;
             }
-            // -------- Paterson-Stockmeyer (bin_bundle.cpp:192-360) --------
-            for (size_t k = 0; k < psb.size(); k++) {
-                uint32_t degree = psb[k].s->ncoeffs - 1, H = degree / h, rem = degree % h;
-                for (uint32_t i = 1; i < H; i++) jobs.push_back(Job{ psb[k].s, (uint32_t)k, i, h - 1 });
-                if (rem) jobs.push_back(Job{ psb[k].s, (uint32_t)k, H, rem });
-            }
-            const uint32_t nj = (uint32_t)jobs.size(), nb = (uint32_t)psb.size();
-            // contiguous low-level region: TIN[job][2][Ll], then R0[bundle][2][Ll] (drops==0) or T0[bundle][ps][2][Ll]
-            const uint32_t tin0 = arena_.take((size_t)nj * 2 * Ll);
-            const uint32_t r00 = arena_.take(drops ? (size_t)nb * ps * 2 * Ll : (size_t)nb * 2 * Ll);
-            const uint32_t low_run_first = acc0, low_run_count = (uint32_t)(arena_.top - acc0);
-            for (uint32_t j = 0; j < nj; j++) {
-                BinBundleStore *s = jobs[j].s;
+            PSB e;
+            e.ref = r;
+            e.job_lo = (uint32_t)jobs.size();
+            uint32_t H = degree / h, rem = degree % h;
+            for (uint32_t i = 1; i < H; i++) jobs.push_back(Job{ r.s, (uint32_t)psb.size(), i, h - 1 });
+            if (rem) jobs.push_back(Job{ r.s, (uint32_t)psb.size(), H, rem });
+            e.job_hi = (uint32_t)jobs.size();
+            psb.push_back(e);
+        }
+        arena_.top = eval_base;
+        const uint32_t nj_all = (uint32_t)jobs.size(), nb_all = (uint32_t)psb.size();
+        const uint32_t acc0 = arena_.take((size_t)direct.size() * 2 * Ll); // direct evaluation accumulators
+        const uint32_t tin0 = arena_.take((size_t)nj_all * 2 * Ll);        // inner polynomials i >= 1
+        const uint32_t r00 = drops ? 0 : arena_.take((size_t)nb_all * 2 * Ll); // i = 0 polynomial (no level gap)
+        const uint32_t stageA_count = (uint32_t)arena_.top - acc0;
+        std::vector<MacGroup> groups;
+        std::vector<FinalizeJob> fin_direct;
+        uint64_t mac_bytes = 0;
+        for (size_t k = 0; k < direct.size(); k++) {
+            BinBundleStore *s = direct[k].s;
+            uint32_t degree = s->ncoeffs - 1, out = acc0 + (uint32_t)k * 2 * Ll;
+            // bin_bundle.cpp:106-174; a degree-0 polynomial leaves the zero accumulator
+            add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, s->ntt_coeffs.p, degree, out);
+            mac_bytes += (uint64_t)degree * Ll * N * 8;
+            FinalizeJob f;
+            std::memset(&f, 0, sizeof(f));
+            f.src[0] = out;
+            f.src[1] = f.src[2] = kNoSrc;
+            f.coeff0 = s->plain_coeffs.p;
+            f.pack = s->bundle_idx + s->cache_idx * bic;
+            f.slot = direct[k].k;
+            fin_direct.push_back(f);
+        }
+        for (uint32_t k = 0; k < nb_all; k++) {
+            BinBundleStore *s = psb[k].ref.s;
+            for (uint32_t j = psb[k].job_lo; j < psb[k].job_hi; j++) {
                 // NTT-form rank of degree i*h + 1 is i*(h-1)
                 const u64 *coeff = s->ntt_coeffs.p + (size_t)jobs[j].i * (h - 1) * Ll * N;
                 add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, coeff, jobs[j].nterms, tin0 + j * 2 * Ll);
                 mac_bytes += (uint64_t)jobs[j].nterms * Ll * N * 8;
             }
-            for (uint32_t k = 0; k < nb; k++) {
-                BinBundleStore *s = psb[k].s;
-                if (!drops) {
-                    add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, s->ntt_coeffs.p, ps, r00 + k * 2 * Ll);
-                } else {
+            if (!drops) { // i = 0 terms can be summed in NTT form when no mod-switch separates them from the result
+                add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, s->ntt_coeffs.p, ps, r00 + k * 2 * Ll);
+                mac_bytes += (uint64_t)ps * Ll * N * 8;
+            }
+        }
+        emit_mac(pb, Ll, groups, mac_bytes);
+        // ===== stage B (whole DB): back to coefficient form =====
+        pb.ntt_run(acc0, stageA_count, ctx.pattern_q(Ll), true);
+        emit_finalize(pb, Ll, fin_direct);
+        const uint32_t stage_top = (uint32_t)arena_.top;
+
+        // ===== Paterson-Stockmeyer remainder (bin_bundle.cpp:192-360), `chunk` BinBundles at a time =====
+        for (uint32_t c0 = 0; c0 < nb_all; c0 += chunk) {
+            arena_.top = stage_top;
+            const uint32_t c1 = std::min(nb_all, c0 + chunk), nb = c1 - c0;
+            const uint32_t j0 = psb[c0].job_lo, j1 = psb[c1 - 1].job_hi, nj = j1 - j0;
+            std::vector<FinalizeJob> fin_ps;
+            std::vector<MacGroup> k8groups;
+            std::vector<MulTermsJob> mulj;
+            std::vector<uint32_t> tinh(nj), r0h(nb);
+            if (drops) {
+                // i = 0 polynomial: every term is taken to coefficient form and mod-switched on its own (:314-324)
+                const uint32_t t00 = arena_.take((size_t)nb * ps * 2 * Ll);
+                for (uint32_t k = 0; k < nb; k++) {
+                    BinBundleStore *s = psb[c0 + k].ref.s;
                     MulTermsJob mj;
                     std::memset(&mj, 0, sizeof(mj));
                     mj.coeff = s->ntt_coeffs.p;
-                    mj.out_idx = r00 + k * ps * 2 * Ll;
+                    mj.out_idx = t00 + k * ps * 2 * Ll;
                     mj.pow_idx = low_base[s->bundle_idx];
                     mj.pow_term_stride = 2 * Ll;
                     mj.pow_comp_stride = Ll;
                     mj.nterms = ps;
                     mulj.push_back(mj);
                 }
-                mac_bytes += (uint64_t)ps * Ll * N * 8;
-            }
-            // stage A launch
-            emit_mac(pb, Ll, groups, lazy_bound, mac_bytes);
-            emit_mul_terms(pb, Ll, mulj, ps);
-            // stage B: back to coefficient form
-            pb.ntt_run(low_run_first, low_run_count, ctx.pattern_q(Ll), true);
-
-            if (nb) {
-                // stage C: to the high level
-                uint32_t tinh0 = tin0, r0h0 = r00;
-                std::vector<uint32_t> tinh(nj), r0h(nb);
-                if (drops) {
-                    if (drops != 1) throw std::logic_error("unexpected level gap between low and high powers");
-                    tinh0 = arena_.take((size_t)nj * 2 * Lh);
-                    uint32_t t0h0 = arena_.take((size_t)nb * ps * 2 * Lh);
-                    r0h0 = arena_.take((size_t)nb * 2 * Lh);
-                    std::vector<uint32_t> ms_src, ms_dst;
-                    for (uint32_t j = 0; j < nj; j++)
-                        for (uint32_t c = 0; c < 2; c++) {
-                            ms_src.push_back(tin0 + (j * 2 + c) * Ll);
-                            ms_dst.push_back(tinh0 + (j * 2 + c) * Lh);
-                        }
-                    for (uint32_t k = 0; k < nb * ps; k++)
-                        for (uint32_t c = 0; c < 2; c++) {
-                            ms_src.push_back(r00 + (k * 2 + c) * Ll);
-                            ms_dst.push_back(t0h0 + (k * 2 + c) * Lh);
-                        }
-                    pb.mod_switch_next(Ll, ms_src, ms_dst);
-                    std::vector<std::vector<uint32_t>> terms;
-                    std::vector<uint32_t> sdst;
-                    for (uint32_t k = 0; k < nb; k++)
-                        for (uint32_t c = 0; c < 2; c++) {
-                            std::vector<uint32_t> tl;
-                            for (uint32_t j = 0; j < ps; j++) tl.push_back(t0h0 + ((k * ps + j) * 2 + c) * Lh);
-                            terms.push_back(tl);
-                            sdst.push_back(r0h0 + (k * 2 + c) * Lh);
-                        }
-                    pb.sum_polys(Lh, terms, sdst);
-                }
+                emit_mul_terms(pb, Ll, mulj, ps);
+                pb.ntt_run(t00, nb * ps * 2 * Ll, ctx.pattern_q(Ll), true);
+                const uint32_t tinh0 = arena_.take((size_t)nj * 2 * Lh);
+                const uint32_t t0h0 = arena_.take((size_t)nb * ps * 2 * Lh);
+                const uint32_t r0h0 = arena_.take((size_t)nb * 2 * Lh);
+                std::vector<uint32_t> ms_src, ms_dst;
+                for (uint32_t j = 0; j < nj; j++)
+                    for (uint32_t c = 0; c < 2; c++) {
+                        ms_src.push_back(tin0 + ((j0 + j) * 2 + c) * Ll);
+                        ms_dst.push_back(tinh0 + (j * 2 + c) * Lh);
+                    }
+                for (uint32_t k = 0; k < nb * ps; k++)
+                    for (uint32_t c = 0; c < 2; c++) {
+                        ms_src.push_back(t00 + (k * 2 + c) * Ll);
+                        ms_dst.push_back(t0h0 + (k * 2 + c) * Lh);
+                    }
+                pb.mod_switch_next(Ll, ms_src, ms_dst);
+                std::vector<std::vector<uint32_t>> terms;
+                std::vector<uint32_t> sdst;
+                for (uint32_t k = 0; k < nb; k++)
+                    for (uint32_t c = 0; c < 2; c++) {
+                        std::vector<uint32_t> tl;
+                        for (uint32_t j = 0; j < ps; j++) tl.push_back(t0h0 + ((k * ps + j) * 2 + c) * Lh);
+                        terms.push_back(tl);
+                        sdst.push_back(r0h0 + (k * 2 + c) * Lh);
+                    }
+                pb.sum_polys(Lh, terms, sdst);
                 for (uint32_t j = 0; j < nj; j++) tinh[j] = tinh0 + j * 2 * Lh;
                 for (uint32_t k = 0; k < nb; k++) r0h[k] = r0h0 + k * 2 * Lh;
-                // stage D/E: inner polynomial x high power
-                const uint32_t ext0 = arena_.take((size_t)nj * 2 * LSh);
-                const uint32_t prod0 = arena_.take((size_t)nj * 3 * Lh);
-                const uint32_t mscr = arena_.take(ProgramBuilder::multiply_scratch(ctx, Lh, nj));
-                std::vector<uint32_t> exts(nj), hp(nj), prods(nj);
-                for (uint32_t j = 0; j < nj; j++) {
-                    exts[j] = ext0 + j * 2 * LSh;
-                    prods[j] = prod0 + j * 3 * Lh;
-                    hp[j] = highext_base[jobs[j].s->bundle_idx] + (jobs[j].i - 1) * 2 * LSh;
-                }
-                pb.extend(Lh, tinh, exts);
-                pb.multiply(Lh, exts, hp, prods, mscr);
-                // stage F: sum of the products per bundle (size 3)
-                const uint32_t res30 = arena_.take((size_t)nb * 3 * Lh), res20 = arena_.take((size_t)nb * 2 * Lh);
-                {
-                    std::vector<std::vector<uint32_t>> terms(nb * 3);
-                    std::vector<uint32_t> sdst(nb * 3);
-                    for (uint32_t k = 0; k < nb; k++)
-                        for (uint32_t c = 0; c < 3; c++) sdst[k * 3 + c] = res30 + (k * 3 + c) * Lh;
-                    for (uint32_t j = 0; j < nj; j++)
-                        for (uint32_t c = 0; c < 3; c++) terms[jobs[j].bslot * 3 + c].push_back(prods[j] + c * Lh);
-                    pb.sum_polys(Lh, terms, sdst);
-                }
-                // stage G: one relinearisation per bundle
-                std::vector<uint32_t> res3(nb), res2(nb);
-                for (uint32_t k = 0; k < nb; k++) res3[k] = res30 + k * 3 * Lh, res2[k] = res20 + k * 2 * Lh;
-                const uint32_t rscr = arena_.take(ProgramBuilder::relin_scratch(Lh, nb));
-                pb.relinearize(Lh, res3, res2, rscr);
-                // stage H: constant coefficients of the inner polynomials x high powers (coefficient-form
-                // operands): accumulate in NTT form at the high level, one inverse transform per bundle
-                const uint32_t k80 = arena_.take((size_t)nb * 2 * Lh);
-                for (uint32_t k = 0; k < nb; k++) {
-                    BinBundleStore *s = psb[k].s;
-                    uint32_t H = (s->ncoeffs - 1) / h;
-                    add_job(k8groups, highext_base[s->bundle_idx], 2 * LSh, LSh, s->plain_high_ntt.p, H, k80 + k * 2 * Lh);
-                }
-                emit_mac(pb, Lh, k8groups, lazy_bound, 0);
-                pb.ntt_run(k80, nb * 2 * Lh, ctx.pattern_q(Lh), true);
-                for (uint32_t k = 0; k < nb; k++) {
-                    FinalizeJob f;
-                    std::memset(&f, 0, sizeof(f));
-                    f.src[0] = res2[k];
-                    f.src[1] = r0h[k];
-                    f.src[2] = k80 + k * 2 * Lh;
-                    f.coeff0 = psb[k].s->plain_coeffs.p;
-                    f.pack = psb[k].s->bundle_idx + psb[k].s->cache_idx * bic;
-                    f.slot = psb[k].k;
-                    fin_ps.push_back(f);
-                }
+            } else {
+                for (uint32_t j = 0; j < nj; j++) tinh[j] = tin0 + (j0 + j) * 2 * Ll;
+                for (uint32_t k = 0; k < nb; k++) r0h[k] = r00 + (c0 + k) * 2 * Ll;
             }
-            emit_finalize(pb, Ll, fin_direct);
+            // inner polynomial x high power (:248-304)
+            const uint32_t ext0 = arena_.take((size_t)nj * 2 * LSh);
+            const uint32_t prod0 = arena_.take((size_t)nj * 3 * Lh);
+            const uint32_t mscr = arena_.take(ProgramBuilder::multiply_scratch(ctx, Lh, nj));
+            std::vector<uint32_t> exts(nj), hp(nj), prods(nj);
+            for (uint32_t j = 0; j < nj; j++) {
+                exts[j] = ext0 + j * 2 * LSh;
+                prods[j] = prod0 + j * 3 * Lh;
+                hp[j] = highext_base[jobs[j0 + j].s->bundle_idx] + (jobs[j0 + j].i - 1) * 2 * LSh;
+            }
+            pb.extend(Lh, tinh, exts);
+            pb.multiply(Lh, exts, hp, prods, mscr);
+            // sum of the products per bundle (size 3), one relinearisation per bundle (:308-310)
+            const uint32_t res30 = arena_.take((size_t)nb * 3 * Lh), res20 = arena_.take((size_t)nb * 2 * Lh);
+            {
+                std::vector<std::vector<uint32_t>> terms(nb * 3);
+                std::vector<uint32_t> sdst(nb * 3);
+                for (uint32_t k = 0; k < nb; k++)
+                    for (uint32_t c = 0; c < 3; c++) sdst[k * 3 + c] = res30 + (k * 3 + c) * Lh;
+                for (uint32_t j = 0; j < nj; j++)
+                    for (uint32_t c = 0; c < 3; c++) terms[(jobs[j0 + j].bslot - c0) * 3 + c].push_back(prods[j] + c * Lh);
+                pb.sum_polys(Lh, terms, sdst);
+            }
+            std::vector<uint32_t> res3(nb), res2(nb);
+            for (uint32_t k = 0; k < nb; k++) res3[k] = res30 + k * 3 * Lh, res2[k] = res20 + k * 2 * Lh;
+            const uint32_t rscr = arena_.take(ProgramBuilder::relin_scratch(Lh, nb));
+            pb.relinearize(Lh, res3, res2, rscr);
+            // constant coefficients of the inner polynomials x high powers (:328-337): coefficient-form
+            // operands; accumulated in NTT form at the high level, one inverse transform per bundle
+            const uint32_t k80 = arena_.take((size_t)nb * 2 * Lh);
+            for (uint32_t k = 0; k < nb; k++) {
+                BinBundleStore *s = psb[c0 + k].ref.s;
+                uint32_t H = (s->ncoeffs - 1) / h;
+                add_job(k8groups, highext_base[s->bundle_idx], 2 * LSh, LSh, s->plain_high_ntt.p, H, k80 + k * 2 * Lh);
+            }
+            emit_mac(pb, Lh, k8groups, 0);
+            pb.ntt_run(k80, nb * 2 * Lh, ctx.pattern_q(Lh), true);
+            for (uint32_t k = 0; k < nb; k++) {
+                BinBundleStore *s = psb[c0 + k].ref.s;
+                FinalizeJob f;
+                std::memset(&f, 0, sizeof(f));
+                f.src[0] = res2[k];
+                f.src[1] = r0h[k];
+                f.src[2] = k80 + k * 2 * Lh;
+                f.coeff0 = s->plain_coeffs.p;
+                f.pack = s->bundle_idx + s->cache_idx * bic;
+                f.slot = psb[c0 + k].ref.k;
+                fin_ps.push_back(f);
+            }
             emit_finalize(pb, Lh, fin_ps);
         }
     }
@@ -775,7 +783,7 @@ size_t Engine::add_desc(const void *data, size_t bytes)
     return off;
 }
 
-void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &groups, uint32_t lazy_bound, uint64_t bytes)
+void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &groups, uint64_t bytes)
 {
     if (groups.empty()) return;
     size_t off = add_desc(groups.data(), groups.size() * sizeof(MacGroup));
@@ -783,9 +791,19 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &gro
     groups.clear();
     size_t slot = mac_step_bytes_.size();
     mac_step_bytes_.push_back(bytes);
+    // lazy-accumulation budgets from the largest prime of the level (see db_stream.cuh)
+    int b = 0;
+    for (uint32_t j = 0; j < L; j++) b = std::max(b, hm::bit_length(ctx.params.coeff_modulus[j]));
+    if (b > 61) throw std::invalid_argument("coeff_modulus primes must have at most 61 bits");
+    const uint32_t norm_period = (uint32_t)std::min<uint64_t>(15, (1ull << (63 - b)) - 1);
+    const uint64_t hh_terms = 124 - 2 * b >= 31 ? 0x7FFFFFFFull : ((1ull << (124 - 2 * b)) - 1);
+    const uint32_t reduce_period = (uint32_t)std::max<uint64_t>(1, (hh_terms / norm_period > 1 ? hh_terms / norm_period - 1 : 1));
+    const uint32_t lazy_bound = 128 - 2 * b >= 31 ? 0x7FFFFFFFu : (1u << (128 - 2 * b));
+    const char *sel = std::getenv("APSU_B200_MAC");
+    const bool use_tma = !(sel && std::string(sel) == "v1");
     pb.step([=] {
         const bool timed = profiling && mac_step_bytes_[slot] > 0;
-        cudaEvent_t a = nullptr, b = nullptr;
+        cudaEvent_t a = nullptr, b2 = nullptr;
         if (timed) {
             if (mac_events_used_ == mac_events_.size()) {
                 cudaEvent_t x, y;
@@ -794,16 +812,26 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &gro
                 mac_events_.emplace_back(x, y);
             }
             a = mac_events_[mac_events_used_].first;
-            b = mac_events_[mac_events_used_].second;
+            b2 = mac_events_[mac_events_used_].second;
             mac_events_used_++;
             APSU_CUDA_CHECK(cudaEventRecord(a, ctx.stream));
         }
-        k_db_mac<<<dim3(L * ctx.N / kMacThreads, n), kMacThreads, 0, ctx.stream>>>(
-            arena_.buf.p, reinterpret_cast<const MacGroup *>(desc_dev_.p + off), ctx.level[L], (int)ctx.N, lazy_bound);
+        const MacGroup *gd = reinterpret_cast<const MacGroup *>(desc_dev_.p + off);
+        if (use_tma) {
+            static bool configured = false;
+            if (!configured) {
+                APSU_CUDA_CHECK(cudaFuncSetAttribute(k_db_mac_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmemBytes));
+                configured = true;
+            }
+            k_db_mac_tma<<<dim3(L * ctx.N / kStreamCols, n), kStreamThreads, kStreamSmemBytes, ctx.stream>>>(
+                arena_.buf.p, gd, ctx.level[L], (int)ctx.N, norm_period, reduce_period);
+        } else {
+            k_db_mac<<<dim3(L * ctx.N / kMacThreads, n), kMacThreads, 0, ctx.stream>>>(arena_.buf.p, gd, ctx.level[L], (int)ctx.N, lazy_bound);
+        }
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;
         if (timed) {
-            APSU_CUDA_CHECK(cudaEventRecord(b, ctx.stream));
+            APSU_CUDA_CHECK(cudaEventRecord(b2, ctx.stream));
             timed_mac_bytes_ += mac_step_bytes_[slot];
         }
     });

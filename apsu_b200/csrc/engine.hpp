@@ -142,7 +142,7 @@ private:
     void build_plan();
     void prepare_plain_high(BinBundleStore &s);
     size_t add_desc(const void *data, size_t bytes);
-    void emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &groups, uint32_t lazy_bound, uint64_t bytes);
+    void emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &groups, uint64_t bytes);
     void emit_mul_terms(ProgramBuilder &pb, uint32_t L, std::vector<MulTermsJob> &jobs, uint32_t nterms);
     void emit_finalize(ProgramBuilder &pb, uint32_t Ls, std::vector<FinalizeJob> &jobs);
     template <typename Build>
