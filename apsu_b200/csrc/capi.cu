@@ -207,7 +207,11 @@ int apsu_b200_db_binbundle_coeff(const apsu_b200_ctx *ctx, uint32_t bundle_idx, 
         for (uint32_t i = 0; i < k; i++) rank += (e.is_ntt_degree(i) == e.is_ntt_degree(k));
         if (e.is_ntt_degree(k)) {
             if (num_primes) *num_primes = Ll;
-            if (out) APSU_CUDA_CHECK(cudaMemcpy(out, s.ntt_coeffs.p + (size_t)rank * Ll * N, (size_t)Ll * N * 8, cudaMemcpyDeviceToHost));
+            if (out) {
+                APSU_CUDA_CHECK(cudaMemcpy(out, s.ntt_coeffs.p + (size_t)rank * Ll * N, (size_t)Ll * N * 8, cudaMemcpyDeviceToHost));
+                // device words are stored split at bit 30 (db_stream.cuh); hand back plain residues
+                for (size_t i = 0; i < (size_t)Ll * N; i++) out[i] = (out[i] & 0xFFFFFFFFull) | ((out[i] >> 32) << 30);
+            }
         } else {
             if (num_primes) *num_primes = 0;
             if (out) APSU_CUDA_CHECK(cudaMemcpy(out, s.plain_coeffs.p + (size_t)rank * N, (size_t)N * 8, cudaMemcpyDeviceToHost));

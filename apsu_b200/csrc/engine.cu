@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <map>
 
 namespace apsu_b200 {
@@ -252,6 +253,7 @@ void Engine::prepare_plain_high(BinBundleStore &s)
     k_plain_lift<<<dim3(N / kEwThreads, Lh, cnt), kEwThreads, 0, ctx.stream>>>(s.plain_coeffs.p + N, s.plain_high_ntt.p, ctx.level[Lh], ctx.t, (int)N);
     APSU_LAUNCH_CHECK();
     ctx.ntt(s.plain_high_ntt.p, s.plain_high_ntt.p, cnt * Lh, ctx.pattern_q(Lh), false);
+    pack_words(s.plain_high_ntt.p, s.plain_high_ntt.n);
 }
 
 uint32_t Engine::add_binbundle(uint32_t bundle_idx, const uint64_t *const *coeffs, uint32_t ncoeffs)
@@ -275,12 +277,21 @@ uint32_t Engine::add_binbundle(uint32_t bundle_idx, const uint64_t *const *coeff
         else
             APSU_CUDA_CHECK(cudaMemcpyAsync(s->plain_coeffs.p + (size_t)(ip++) * N, coeffs[k], (size_t)N * 8, cudaMemcpyHostToDevice, ctx.stream));
     }
+    pack_words(s->ntt_coeffs.p, s->ntt_coeffs.n);
     prepare_plain_high(*s);
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
     uint32_t ci = s->cache_idx;
     db[bundle_idx].push_back(std::move(s));
     invalidate_plan();
     return ci;
+}
+
+// NTT-form DB words live in the split ("packed") form the DB-stream kernel consumes (db_stream.cuh)
+void Engine::pack_words(u64 *data, size_t count)
+{
+    if (!count) return;
+    k_pack30<<<(unsigned)((count + 255) / 256), 256, 0, ctx.stream>>>(data, count, 0);
+    APSU_LAUNCH_CHECK();
 }
 
 uint32_t Engine::add_binbundle_synthetic(uint32_t bundle_idx, uint32_t ncoeffs, uint64_t seed)
@@ -786,6 +797,45 @@ size_t Engine::add_desc(const void *data, size_t bytes)
 void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &groups, uint64_t bytes)
 {
     if (groups.empty()) return;
+    // regroup: jobs over the same powers, longest first, eight to a group; full equal-length groups go
+    // first (they run the branch-free kernel variant), ragged ones after
+    uint32_t n_uniform = 0;
+    {
+        struct J {
+            const u64 *coeff;
+            uint32_t nterms, out;
+        };
+        std::map<std::array<uint32_t, 3>, std::vector<J>> by_pow;
+        for (auto &g : groups)
+            for (uint32_t k = 0; k < g.njobs; k++) by_pow[{ g.pow_idx, g.pow_term_stride, g.pow_comp_stride }].push_back(J{ g.coeff[k], g.nterms[k], g.out_idx[k] });
+        std::vector<MacGroup> uni, rag;
+        for (auto &kv : by_pow) {
+            auto &js = kv.second;
+            std::stable_sort(js.begin(), js.end(), [](const J &a, const J &b) { return a.nterms > b.nterms; });
+            for (size_t i = 0; i < js.size(); i += kMacJobs) {
+                MacGroup g;
+                std::memset(&g, 0, sizeof(g));
+                g.pow_idx = kv.first[0];
+                g.pow_term_stride = kv.first[1];
+                g.pow_comp_stride = kv.first[2];
+                bool same = true;
+                for (size_t k = i; k < std::min(js.size(), i + kMacJobs); k++) {
+                    g.coeff[g.njobs] = js[k].coeff;
+                    g.nterms[g.njobs] = js[k].nterms;
+                    g.out_idx[g.njobs] = js[k].out;
+                    g.max_terms = std::max(g.max_terms, js[k].nterms);
+                    same &= js[k].nterms == js[i].nterms;
+                    g.njobs++;
+                }
+                ((same && g.njobs == kMacJobs && g.max_terms > 0) ? uni : rag).push_back(g);
+            }
+        }
+        n_uniform = (uint32_t)uni.size();
+        groups = uni;
+        groups.insert(groups.end(), rag.begin(), rag.end());
+    }
+    int mac_g = 4;
+    if (const char *ev = std::getenv("APSU_B200_MAC_G")) mac_g = atoi(ev) == 4 ? 4 : 8;
     size_t off = add_desc(groups.data(), groups.size() * sizeof(MacGroup));
     uint32_t n = (uint32_t)groups.size();
     groups.clear();
@@ -818,13 +868,23 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &gro
         }
         const MacGroup *gd = reinterpret_cast<const MacGroup *>(desc_dev_.p + off);
         if (use_tma) {
-            static bool configured = false;
-            if (!configured) {
-                APSU_CUDA_CHECK(cudaFuncSetAttribute(k_db_mac_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmemBytes));
-                configured = true;
+            // groups [0, n_uniform) are full and equal-length (branch-free kernel), the rest ragged
+            auto launch = [&](auto kern, size_t smem, int G, const MacGroup *first, uint32_t count) {
+                if (!count) return;
+                APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<dim3(L * ctx.N / kStreamCols, count, kMacJobs / G), kStreamThreads, smem, ctx.stream>>>(
+                    arena_.buf.p, first, ctx.level[L], (int)ctx.N, norm_period, reduce_period);
+                APSU_CUDA_CHECK(cudaGetLastError());
+                ctx.launches++;
+            };
+            if (mac_g == 4) {
+                launch(k_db_mac_tma<4, false>, StreamCfg<4>::smem_bytes, 4, gd, n_uniform);
+                launch(k_db_mac_tma<4, true>, StreamCfg<4>::smem_bytes, 4, gd + n_uniform, n - n_uniform);
+            } else {
+                launch(k_db_mac_tma<8, false>, StreamCfg<8>::smem_bytes, 8, gd, n_uniform);
+                launch(k_db_mac_tma<8, true>, StreamCfg<8>::smem_bytes, 8, gd + n_uniform, n - n_uniform);
             }
-            k_db_mac_tma<<<dim3(L * ctx.N / kStreamCols, n), kStreamThreads, kStreamSmemBytes, ctx.stream>>>(
-                arena_.buf.p, gd, ctx.level[L], (int)ctx.N, norm_period, reduce_period);
+            ctx.launches--; // the common epilogue below counts one
         } else {
             k_db_mac<<<dim3(L * ctx.N / kMacThreads, n), kMacThreads, 0, ctx.stream>>>(arena_.buf.p, gd, ctx.level[L], (int)ctx.N, lazy_bound);
         }

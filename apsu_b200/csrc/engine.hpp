@@ -141,6 +141,7 @@ private:
     void invalidate_plan() { plan_valid_ = false; }
     void build_plan();
     void prepare_plain_high(BinBundleStore &s);
+    void pack_words(u64 *data, size_t count);
     size_t add_desc(const void *data, size_t bytes);
     void emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &groups, uint64_t bytes);
     void emit_mul_terms(ProgramBuilder &pb, uint32_t L, std::vector<MulTermsJob> &jobs, uint32_t nterms);

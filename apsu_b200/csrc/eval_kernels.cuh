@@ -12,6 +12,11 @@ namespace apsu_b200 {
 constexpr int kMacJobs = 8;      // jobs per group: share every ciphertext-power load
 constexpr int kMacThreads = 256;
 
+// NTT-form DB plaintext words are stored split at bit 30 ("packed"): low 30 bits in the low half of the
+// 64-bit word, the remaining bits in the high half — the DB-stream kernel multiplies the halves directly.
+__host__ __device__ __forceinline__ u64 pack30_word(u64 w) { return (w & 0x3FFFFFFFull) | ((w >> 30) << 32); }
+__host__ __device__ __forceinline__ u64 unpack30_word(u64 p) { return (p & 0xFFFFFFFFull) | ((p >> 32) << 30); }
+
 // One group = up to kMacJobs accumulation jobs over the same ciphertext powers.
 // job g: out_g[c][l][n] = sum_{j < nterms_g} power_j[c][l][n] * coeff_g[j][l][n]   (mod q_l)
 struct MacGroup {
@@ -50,7 +55,7 @@ k_db_mac(u64 *A, const MacGroup *__restrict__ groups, LevelConsts c, int N, u32 
         const u64 p0 = pw[j * tstride], p1 = pw[j * tstride + cstride];
         u64 w[kMacJobs];
 #pragma unroll
-        for (int k = 0; k < kMacJobs; k++) w[k] = (j < g.nterms[k]) ? __ldcs(g.coeff[k] + j * LN + col) : 0ull;
+        for (int k = 0; k < kMacJobs; k++) w[k] = (j < g.nterms[k]) ? unpack30_word(__ldcs(g.coeff[k] + j * LN + col)) : 0ull;
 #pragma unroll
         for (int k = 0; k < kMacJobs; k++) {
             mac128(acc[k][0], w[k], p0);
@@ -93,7 +98,7 @@ k_db_mul(u64 *A, const MulTermsJob *__restrict__ jobs, LevelConsts c, int N)
     const u32 col = blockIdx.x * blockDim.x + threadIdx.x;
     const DMod m = c.q[col / N];
     const size_t LN = (size_t)c.L * N;
-    const u64 w = __ldcs(jb.coeff + j * LN + col);
+    const u64 w = unpack30_word(__ldcs(jb.coeff + j * LN + col));
     const u64 *pw = A + ((size_t)jb.pow_idx + (size_t)j * jb.pow_term_stride) * N + col;
     u64 *o = A + ((size_t)jb.out_idx) * N + (size_t)j * 2 * LN + col;
     o[0] = mul_mod(pw[0], w, m);
@@ -236,7 +241,8 @@ __global__ void k_fill_db(u64 *__restrict__ out, size_t count, u64 seed, int mod
         q = mods.t;
         pos = (h ? r * (N + (size_t)(h - 1) * LN) : 0) + within;
     }
-    out[w] = mulhi(splitmix64_at(seed, pos), q);
+    const u64 v = mulhi(splitmix64_at(seed, pos), q);
+    out[w] = mode == 0 ? pack30_word(v) : v; // NTT-form plaintexts are stored packed (db_stream.cuh)
 }
 
 // BatchEncoder::encode scatter: out[p][map[i]] = values[p][i]
