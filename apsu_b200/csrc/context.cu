@@ -237,7 +237,7 @@ template <int LOGN>
 static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, bool inverse, cudaStream_t st)
 {
     constexpr int threads = (1 << LOGN) / 16;
-    constexpr size_t smem = sizeof(u64) << LOGN;
+    constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4)); // + one pad word per 16
     static bool configured = false;
     if (!configured) {
         APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
