@@ -1,0 +1,319 @@
+// C++ host facade over the C ABI (include/apsu_b200.h): the reference's receiver-side surface for the
+// query-evaluation path, same names / argument meaning / exception types, so that the call sites in
+// receiver/apsu/receiver_ddh.cpp and receiver/apsu/zmq/receiver_dispatcher_ddh.cpp read unchanged.
+//
+//   apsu::PSUParams                      common/apsu/psu_params.h:31-222
+//   apsu::PowersDag                      common/apsu/powers.h:41-293
+//   apsu::receiver::BatchedPlaintextPolyn / BinBundleCache   receiver/apsu/bin_bundle.h:52-171
+//   apsu::receiver::ReceiverDB           receiver/apsu/receiver_db.h:60-390 (query-time surface)
+//   apsu::receiver::Query                receiver/apsu/query.h:26-89
+//   apsu::network::ResultPackage         common/apsu/network/result_package.h:44-62
+//   apsu::receiver::Receiver             receiver/apsu/receiver_ddh.h:184-243 (HE part of RunQuery)
+//
+// Header-only; link with libapsu_b200.so.  Ciphertexts/plaintexts are plain std::vector<uint64_t> in SEAL's
+// in-memory layouts (see the C header) — (de)serialisation of SEAL objects stays with the caller.
+#pragma once
+#include "../../include/apsu_b200.h"
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <shared_mutex>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+namespace apsu {
+
+namespace detail {
+// status -> the exception type the reference throws at the same place
+inline void check(int rc)
+{
+    if (rc == APSU_B200_OK) return;
+    std::string msg = apsu_b200_last_error();
+    switch (rc) {
+    case APSU_B200_ERR_INVALID_ARGUMENT: throw std::invalid_argument(msg);
+    case APSU_B200_ERR_LOGIC: throw std::logic_error(msg);
+    default: throw std::runtime_error(msg);
+    }
+}
+} // namespace detail
+
+class PSUParams {
+public:
+    struct TableParams {
+        std::uint32_t hash_func_count, table_size, max_items_per_bin;
+    };
+    struct ItemParams {
+        std::uint32_t felts_per_item;
+    };
+    struct QueryParams {
+        std::uint32_t ps_low_degree;
+        std::set<std::uint32_t> query_powers;
+    };
+    struct SEALParams {
+        std::size_t poly_modulus_degree;
+        std::uint64_t plain_modulus;
+        std::vector<std::uint64_t> coeff_modulus;
+    };
+
+    // PSUParams::Load(const std::string&) — JSON text in the reference's schema
+    static PSUParams Load(const std::string &json)
+    {
+        PSUParams p;
+        detail::check(apsu_b200_params_load_json(json.c_str(), &p.c_));
+        return p;
+    }
+    PSUParams(const ItemParams &ip, const TableParams &tp, const QueryParams &qp, const SEALParams &sp)
+    {
+        c_ = apsu_b200_params{};
+        c_.poly_modulus_degree = static_cast<std::uint32_t>(sp.poly_modulus_degree);
+        c_.plain_modulus = sp.plain_modulus;
+        if (sp.coeff_modulus.size() > APSU_B200_MAX_COEFF_MODULUS) throw std::invalid_argument("coeff_modulus is too long");
+        c_.coeff_modulus_count = static_cast<std::uint32_t>(sp.coeff_modulus.size());
+        for (std::size_t i = 0; i < sp.coeff_modulus.size(); i++) c_.coeff_modulus[i] = sp.coeff_modulus[i];
+        c_.hash_func_count = tp.hash_func_count;
+        c_.table_size = tp.table_size;
+        c_.max_items_per_bin = tp.max_items_per_bin;
+        c_.felts_per_item = ip.felts_per_item;
+        c_.ps_low_degree = qp.ps_low_degree;
+        if (qp.query_powers.size() > APSU_B200_MAX_QUERY_POWERS) throw std::invalid_argument("too many query_powers");
+        for (auto q : qp.query_powers) c_.query_powers[c_.query_power_count++] = q;
+        detail::check(apsu_b200_params_validate(&c_)); // == PSUParams::initialize
+    }
+
+    TableParams table_params() const { return { c_.hash_func_count, c_.table_size, c_.max_items_per_bin }; }
+    ItemParams item_params() const { return { c_.felts_per_item }; }
+    QueryParams query_params() const
+    {
+        return { c_.ps_low_degree, std::set<std::uint32_t>(c_.query_powers, c_.query_powers + c_.query_power_count) };
+    }
+    SEALParams seal_params() const
+    {
+        return { c_.poly_modulus_degree, c_.plain_modulus,
+                 std::vector<std::uint64_t>(c_.coeff_modulus, c_.coeff_modulus + c_.coeff_modulus_count) };
+    }
+    std::uint32_t items_per_bundle() const { return c_.items_per_bundle; }
+    std::uint32_t bins_per_bundle() const { return c_.bins_per_bundle; }
+    std::uint32_t bundle_idx_count() const { return c_.bundle_idx_count; }
+    std::uint32_t item_bit_count() const { return c_.item_bit_count; }
+    std::uint32_t item_bit_count_per_felt() const { return c_.item_bit_count_per_felt; }
+    const apsu_b200_params &c_params() const { return c_; }
+
+private:
+    PSUParams() = default;
+    apsu_b200_params c_{};
+};
+
+class PowersDag {
+public:
+    struct PowersNode {
+        std::uint32_t power = 0, depth = 0;
+        std::pair<std::uint32_t, std::uint32_t> parents{ 0, 0 };
+        bool is_source() const { return !parents.first && !parents.second; }
+    };
+    // configure(params.query_powers, create_powers_set(ps_low_degree, max_items_per_bin)) as in query.cpp:78
+    bool configure(const PSUParams &params)
+    {
+        const apsu_b200_params &c = params.c_params();
+        std::uint32_t cap = c.max_items_per_bin + 1, n = 0;
+        std::vector<std::uint32_t> pw(cap), dp(cap), p1(cap), p2(cap);
+        if (apsu_b200_powers_dag(&c, cap, pw.data(), dp.data(), p1.data(), p2.data(), &n, &depth_) != APSU_B200_OK) return false;
+        nodes_.clear();
+        target_powers_.clear();
+        for (std::uint32_t i = 0; i < n; i++) {
+            nodes_[pw[i]] = PowersNode{ pw[i], dp[i], { p1[i], p2[i] } };
+            target_powers_.insert(pw[i]);
+        }
+        configured_ = true;
+        return true;
+    }
+    bool is_configured() const { return configured_; }
+    std::uint32_t depth() const { need(); return depth_; }
+    std::set<std::uint32_t> target_powers() const { need(); return target_powers_; }
+    std::uint32_t source_count() const { return static_cast<std::uint32_t>(source_nodes().size()); }
+    std::vector<PowersNode> source_nodes() const
+    {
+        need();
+        std::vector<PowersNode> r;
+        for (auto &kv : nodes_)
+            if (kv.second.is_source()) r.push_back(kv.second);
+        return r;
+    }
+    template <typename Func>
+    void apply(Func &&func) const
+    {
+        need();
+        for (auto p : target_powers_) func(nodes_.at(p));
+    }
+
+private:
+    void need() const
+    {
+        if (!configured_) throw std::logic_error("PowersDag has not been configured");
+    }
+    std::unordered_map<std::uint32_t, PowersNode> nodes_;
+    std::set<std::uint32_t> target_powers_;
+    std::uint32_t depth_ = 0;
+    bool configured_ = false;
+};
+
+namespace network {
+// one per BinBundle; psu_result = size-2 ciphertext at the last level, uint64_t[2][1][N]
+struct ResultPackage {
+    std::uint32_t bundle_idx = 0, cache_idx = 0;
+    std::uint32_t label_byte_count = 0, nonce_byte_count = 0;
+    std::vector<std::uint64_t> psu_result;
+};
+} // namespace network
+
+namespace receiver {
+
+// batched_coeffs[k]: NTT form uint64_t[Lp][N] unless k==0 (no PS) / k % (ps_low_degree+1)==0 (PS): uint64_t[N]
+struct BatchedPlaintextPolyn {
+    std::vector<std::vector<std::uint64_t>> batched_coeffs;
+    explicit operator bool() const { return !batched_coeffs.empty(); }
+};
+struct BinBundleCache {
+    BatchedPlaintextPolyn batched_matching_polyn;
+};
+
+class ReceiverDB {
+public:
+    explicit ReceiverDB(PSUParams params, int device = 0) : params_(std::move(params))
+    {
+        detail::check(apsu_b200_ctx_create(&params_.c_params(), device, &ctx_));
+    }
+    ~ReceiverDB() { apsu_b200_ctx_destroy(ctx_); }
+    ReceiverDB(const ReceiverDB &) = delete;
+    ReceiverDB &operator=(const ReceiverDB &) = delete;
+
+    const PSUParams &get_params() const { return params_; }
+    // uploads one BinBundle cache; it stays device-resident (bin_bundles_[bundle_idx].push_back)
+    std::uint32_t add_bin_bundle(std::uint32_t bundle_idx, const BinBundleCache &cache)
+    {
+        std::unique_lock<std::shared_mutex> lock(db_lock_);
+        std::vector<const std::uint64_t *> ptrs;
+        for (auto &v : cache.batched_matching_polyn.batched_coeffs) ptrs.push_back(v.data());
+        std::uint32_t ci = 0;
+        detail::check(apsu_b200_db_add_binbundle(ctx_, bundle_idx, ptrs.data(), static_cast<std::uint32_t>(ptrs.size()), &ci));
+        return ci;
+    }
+    std::uint32_t add_bin_bundle_synthetic(std::uint32_t bundle_idx, std::uint32_t ncoeffs, std::uint64_t seed)
+    {
+        std::unique_lock<std::shared_mutex> lock(db_lock_);
+        std::uint32_t ci = 0;
+        detail::check(apsu_b200_db_add_binbundle_synthetic(ctx_, bundle_idx, ncoeffs, seed, &ci));
+        return ci;
+    }
+    std::size_t get_bin_bundle_count(std::uint32_t bundle_idx) const
+    {
+        std::uint32_t n = 0;
+        detail::check(apsu_b200_db_bin_bundle_count(ctx_, bundle_idx, &n));
+        return n;
+    }
+    std::size_t get_bin_bundle_count() const
+    {
+        std::uint32_t n = 0;
+        detail::check(apsu_b200_db_total_bin_bundle_count(ctx_, &n));
+        return n;
+    }
+    void clear()
+    {
+        std::unique_lock<std::shared_mutex> lock(db_lock_);
+        detail::check(apsu_b200_db_clear(ctx_));
+    }
+    std::shared_lock<std::shared_mutex> get_reader_lock() const { return std::shared_lock<std::shared_mutex>(db_lock_); }
+    apsu_b200_ctx *handle() const { return ctx_; }
+
+private:
+    PSUParams params_;
+    apsu_b200_ctx *ctx_ = nullptr;
+    mutable std::shared_mutex db_lock_;
+};
+
+// the already-extracted query: source power -> one ciphertext per bundle index (uint64_t[2][L][N]), relin keys
+class Query {
+public:
+    Query(std::shared_ptr<ReceiverDB> db, std::unordered_map<std::uint32_t, std::vector<std::vector<std::uint64_t>>> data,
+          std::vector<std::uint64_t> relin_keys)
+        : receiver_db_(std::move(db)), data_(std::move(data)), relin_keys_(std::move(relin_keys))
+    {
+        if (!receiver_db_) throw std::invalid_argument("receiver_db cannot be null");
+        const PSUParams &p = receiver_db_->get_params();
+        std::set<std::uint32_t> given;
+        for (auto &kv : data_) {
+            given.insert(kv.first);
+            if (kv.second.size() != p.bundle_idx_count()) return; // invalid: valid_ stays false (query.cpp:93-99)
+        }
+        if (given != p.query_params().query_powers) return; // query.cpp:68-111
+        if (!pd_.configure(p)) return;
+        valid_ = true;
+    }
+    explicit operator bool() const { return valid_; }
+    std::shared_ptr<ReceiverDB> receiver_db() const { return receiver_db_; }
+    const PowersDag &pd() const { return pd_; }
+    const std::unordered_map<std::uint32_t, std::vector<std::vector<std::uint64_t>>> &data() const { return data_; }
+    const std::vector<std::uint64_t> &relin_keys() const { return relin_keys_; }
+
+private:
+    std::shared_ptr<ReceiverDB> receiver_db_;
+    std::unordered_map<std::uint32_t, std::vector<std::vector<std::uint64_t>>> data_;
+    std::vector<std::uint64_t> relin_keys_;
+    PowersDag pd_;
+    bool valid_ = false;
+};
+
+using ResultPart = std::unique_ptr<network::ResultPackage>;
+
+class Receiver {
+public:
+    // The HE part of Receiver::RunQuery (receiver_ddh.cpp:139-369): `masks` is the dense
+    // [alpha_max_cache_count][bundle_idx_count][N] table of coefficient-form random plaintexts
+    // (random_plain_list, indexed by pack_idx); send_rp_fun receives one ResultPackage per BinBundle.
+    static void RunQuery(const Query &query, const std::vector<std::uint64_t> &masks,
+                         const std::function<void(ResultPart)> &send_rp_fun)
+    {
+        if (!query) throw std::invalid_argument("query is invalid");
+        auto db = query.receiver_db();
+        auto lock = db->get_reader_lock();
+        static std::mutex ctx_mutex; // a context is thread-compatible; serialise
+        std::lock_guard<std::mutex> guard(ctx_mutex);
+        const PSUParams &p = db->get_params();
+        const std::size_t N = p.seal_params().poly_modulus_degree;
+        std::uint32_t L = 0;
+        detail::check(apsu_b200_ctx_level(db->handle(), 0, &L));
+        const std::size_t ct_words = 2 * static_cast<std::size_t>(L) * N, bic = p.bundle_idx_count();
+        std::vector<std::uint32_t> src;
+        std::vector<std::uint64_t> cts;
+        for (auto &kv : query.data()) {
+            src.push_back(kv.first);
+            for (auto &ct : kv.second) {
+                if (ct.size() != ct_words) throw std::invalid_argument("query ciphertext has the wrong size");
+                cts.insert(cts.end(), ct.begin(), ct.end());
+            }
+        }
+        const std::size_t n = db->get_bin_bundle_count();
+        if (masks.size() % N) throw std::invalid_argument("mask table is not a multiple of poly_modulus_degree");
+        std::vector<std::uint64_t> out(n * 2 * N);
+        std::vector<std::uint32_t> bidx(n), cidx(n);
+        detail::check(apsu_b200_run_query(
+            db->handle(), src.data(), static_cast<std::uint32_t>(src.size()), cts.data(),
+            query.relin_keys().empty() ? nullptr : query.relin_keys().data(), masks.data(), static_cast<std::uint32_t>(masks.size() / N),
+            out.data(), bidx.data(), cidx.data()));
+        (void)bic;
+        for (std::size_t k = 0; k < n; k++) {
+            auto rp = std::make_unique<network::ResultPackage>();
+            rp->bundle_idx = bidx[k];
+            rp->cache_idx = cidx[k];
+            rp->psu_result.assign(out.begin() + k * 2 * N, out.begin() + (k + 1) * 2 * N);
+            send_rp_fun(std::move(rp));
+        }
+    }
+};
+
+} // namespace receiver
+} // namespace apsu

@@ -70,17 +70,8 @@ def bundle_bytes(pj: dict, ncoeffs: int, low_L: int) -> int:
 
 
 def shard(degrees, world: int):
-    """contiguous partition of the (bundle_idx, cache_idx) list by cumulative plaintext count, so that a rank
-    touches as few bundle indices as possible (it recomputes the query powers of each index it owns)."""
-    flat = [(b, c, d + 1) for b, row in enumerate(degrees) for c, d in enumerate(row)]
-    total = sum(w for _, _, w in flat)
-    parts = [[] for _ in range(world)]
-    acc = 0
-    for b, c, w in flat:
-        r = min(world - 1, int((acc + w / 2) * world / total))
-        parts[r].append((b, c, w - 1))
-        acc += w
-    return parts
+    from apsu_b200.sharding import shard_bundles
+    return shard_bundles(degrees, world)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -144,44 +135,53 @@ def synth_query(primes, t, N, first_L, K, nsrc, bic, npack, seed):
 
 
 def cpu_baseline(pj, name, degrees, cts, relin, masks, sample_pairs, threads):
-    """Times the oracle (CPU restatement of the reference's SEAL path) on a bounded sample: ComputePowers
-    for ONE bundle index + evaluation of `sample_pairs` BinBundles; extrapolates linearly in the number of
-    bundle indices and in plaintext count.  Returns (dict, {pair: result ndarray})."""
+    """Times the oracle (CPU restatement of the reference's SEAL path, oracle/) with all host threads busy on a
+    bounded sample of the workload: ComputePowers for ONE bundle index (the reference runs bundle indices
+    serially with -t workers over the DAG, receiver_ddh.cpp:325-333) + the evaluation of `threads` full
+    BinBundles in parallel, one per worker as in receiver_ddh.cpp:340-364.  The whole query is extrapolated
+    linearly in bundle indices and plaintext count.  `sample_pairs` (same seeds as the GPU DB) are also
+    evaluated so their result ciphertexts can be compared bit for bit.  Returns (dict, {pair: ndarray})."""
     from oracle import oracle as O
     p = O.Params(pj, name + ".json")
     ctx = O.Context.from_params(p)
     bic = p.bundle_idx_count
     db = O.ReceiverDB(ctx, p)
     b0 = sample_pairs[0][0]
-    # oracle DB holds only bundle index b0's sampled bundles (others empty => ComputePowers skipped there)
+    # the oracle DB holds bundles at index b0 only (other indices empty => ComputePowers skipped there)
     local = {}
     for (b, c) in sample_pairs:
         assert b == b0
         local[(b, c)] = db.add_bundle_synthetic(b, degrees[b][c] + 1, SEEDS["db"] * 1000 + b * 64 + c)
+    full = p.max_items_per_bin
+    timed = [lc for (b, c), lc in local.items() if degrees[b][c] + 1 == full][:threads]
+    while len(timed) < max(threads, 1):  # timing-only full-size bundles so that every worker has one
+        timed.append(db.add_bundle_synthetic(b0, full, 999000 + len(timed)))
     ses = db.run_query(p.query_powers, cts, relin, None, threads=threads, powers_only=True)
     powers_ms_one = ses.powers_ms
-    # masks for the local cache indices
-    alpha = max(local.values()) + 1
+    alpha = db.bundle_count(b0)
     m = np.zeros((alpha * bic, p.N), dtype=np.uint64)
+    m[:] = masks[b0]
     for (b, c), lc in local.items():
         m[b + lc * bic] = masks[b + c * bic]
-    pairs_local = [(b, local[(b, c)]) for (b, c) in sample_pairs]
-    eval_ms = ses.eval_subset(pairs_local, relin, m, threads=threads)
+    eval_ms = ses.eval_subset([(b0, lc) for lc in timed], relin, m, threads=threads)
+    rest = [(b0, lc) for lc in local.values() if lc not in timed]
+    if rest:
+        ses.eval_subset(rest, relin, m, threads=threads)
     res = {}
     for (bb, lc, ct) in ses.results():
         for (b, c), l2 in local.items():
             if (bb, lc) == (b, l2):
                 res[(b, c)] = ct
-    sample_coeffs = sum(degrees[b][c] + 1 for b, c in sample_pairs)
+    timed_coeffs = len(timed) * full
     total_coeffs = sum(d + 1 for row in degrees for d in row)
     n_active = sum(1 for row in degrees if row)
-    est_ms = powers_ms_one * n_active + eval_ms * total_coeffs / sample_coeffs
+    est_ms = powers_ms_one * n_active + eval_ms * total_coeffs / timed_coeffs
     n_bundles = sum(len(r) for r in degrees)
     info = {
         "value": n_bundles / (est_ms / 1e3), "unit": "BinBundles/s", "cores": threads, "kind": "port",
         "sample": f"oracle (SEAL-algorithm restatement, not SEAL), -t {threads}: ComputePowers for 1 of {n_active} bundle indices "
-                  f"({powers_ms_one:.0f} ms) + eval_patstock of {len(sample_pairs)} BinBundles / {sample_coeffs} of {total_coeffs} plaintexts "
-                  f"({eval_ms:.0f} ms); extrapolated linearly to the whole query = {est_ms:.0f} ms",
+                  f"({powers_ms_one:.0f} ms) + eval_patstock of {len(timed)} full BinBundles in parallel = {timed_coeffs} of {total_coeffs} "
+                  f"plaintexts ({eval_ms:.0f} ms); extrapolated linearly to the whole query = {est_ms:.0f} ms",
         "query_eval_ms_est": est_ms, "host_cores": os.cpu_count(),
     }
     return info, res
@@ -340,7 +340,7 @@ def main():
             d_cts = torch.empty(cts_t.shape, dtype=torch.int64, device="cuda")
             d_relin = torch.empty(relin_t.shape, dtype=torch.int64, device="cuda")
             counts = [len(x) for x in shard(degrees, world)]
-            gather_list = [torch.empty((max(cn, 1), 2, N), dtype=torch.int64, device="cuda") for cn in counts] if rank == 0 else None
+            from apsu_b200 import sharding
 
         def step_e2e():
             if dist is None:
@@ -351,8 +351,7 @@ def main():
                 if rank == 0:
                     d_cts.copy_(cts_t, non_blocking=True)
                     d_relin.copy_(relin_t, non_blocking=True)
-                dist.broadcast(d_cts, 0)
-                dist.broadcast(d_relin, 0)
+                sharding.broadcast_query([d_cts, d_relin], src=0)
                 capi.check(lib.apsu_b200_query_begin_device(h, src_powers, nsrc, C.c_void_p(d_cts.data_ptr())))
                 capi.check(lib.apsu_b200_set_relin_keys_device(h, C.c_void_p(d_relin.data_ptr())))
                 capi.check(lib.apsu_b200_set_masks(h, masks_p.reshape(-1), masks_p.shape[0]))
@@ -361,10 +360,9 @@ def main():
                 res = torch.empty((max(n_local, 1), 2, N), dtype=torch.int64, device="cuda")
                 if n_local:
                     capi.check(lib.apsu_b200_copy_results_device(h, C.c_void_p(res.data_ptr())))
-                dist.gather(res, gather_list, dst=0)
+                allres = sharding.gather_results(res[:n_local], counts, N, dst=0)
                 if rank == 0:
-                    for g in gather_list:
-                        g.cpu()
+                    allres.cpu()
 
         for _ in range(args.warmup):
             step_e2e()

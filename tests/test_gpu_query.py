@@ -71,3 +71,130 @@ def rx_targets(p):
         h = p.ps_low_degree + 1
         return list(range(1, p.ps_low_degree + 1)) + list(range(h, p.max_items_per_bin + 1, h))
     return list(range(1, p.max_items_per_bin + 1))
+
+
+def test_results_match_committed_golden_digests():
+    """the CUDA path against tests/golden/oracle_vectors.json (no oracle evaluation involved)."""
+    import hashlib
+    import json
+    import pathlib
+    import apsu_b200
+    gold = json.loads((pathlib.Path(__file__).resolve().parent / "golden" / "oracle_vectors.json").read_text())
+    for name in ("256K-512", "16M-4096", "1M-1024-com"):
+        g = gold["queries"][name]
+        sc = Scenario(name, g["degrees"], planted=8)
+        db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0)
+        try:
+            _upload(sc, db)
+            rx = apsu_b200.Receiver(db)
+            res = rx.RunQuery(apsu_b200.Query(sc.src_powers, sc.cts, sc.relin), sc.masks)
+            assert len(res) == len(g["results"])
+            for r in res:
+                d = hashlib.sha256(np.ascontiguousarray(r.psu_result).tobytes()).hexdigest()
+                assert d == g["results"][f"{r.bundle_idx},{r.cache_idx}"], (name, r.bundle_idx, r.cache_idx)
+        finally:
+            db.close()
+
+
+def test_db_roundtrip_synthetic_fill_and_mask_encode():
+    """device-resident plaintexts read back equal what was uploaded; the synthetic fill equals the oracle's
+    stream; BatchEncoder::encode on the device equals the oracle's."""
+    import apsu_b200
+    from oracle import oracle as O
+    p = O.Params.load("1M-4096-com")
+    ctx = O.Context.from_params(p)
+    odb = O.ReceiverDB(ctx, p)
+    odb.add_bundle_synthetic(0, 30, 1234)
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(p.to_json()), 0)
+    try:
+        assert db.add_bin_bundle_synthetic(0, 30, 1234) == 0
+        coeffs = odb.bundle_coeffs(0, 0)
+        for k, (L, arr) in enumerate(coeffs):
+            assert np.array_equal(db.bin_bundle_coeff(0, 0, k), arr), k
+        assert db.add_bin_bundle(0, [a for _, a in coeffs]) == 1
+        for k, (L, arr) in enumerate(coeffs):
+            assert np.array_equal(db.bin_bundle_coeff(0, 1, k), arr), k
+        assert db.get_bin_bundle_count(0) == 2 and db.get_bin_bundle_count() == 2
+        rx = apsu_b200.Receiver(db)
+        vals = np.random.default_rng(5).integers(0, p.t, size=(3, p.N), dtype=np.uint64)
+        enc = rx.encode_masks(vals)
+        for i in range(3):
+            assert np.array_equal(enc[i], ctx.encode(vals[i]))
+    finally:
+        db.close()
+
+
+def test_error_behaviour_on_device():
+    import apsu_b200
+    sc = Scenario("256K-512", [[5]], planted=2)
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0)
+    try:
+        rx = apsu_b200.Receiver(db)
+        with pytest.raises(AssertionError):  # logic_error: powers before a query
+            rx.ComputePowers()
+        _upload(sc, db)
+        with pytest.raises(ValueError):  # invalid_argument: wrong source powers (query.cpp:68-111)
+            rx.load_query(apsu_b200.Query(sc.src_powers[:-1], sc.cts[:-1], sc.relin))
+        with pytest.raises(ValueError):  # more coefficients than max_items_per_bin
+            db.add_bin_bundle(0, [np.zeros(sc.p.N, dtype=np.uint64)] + [np.zeros((2, sc.p.N), dtype=np.uint64)] * sc.p.max_items_per_bin)
+        rx.load_query(apsu_b200.Query(sc.src_powers, sc.cts, sc.relin))
+        rx.ComputePowers()
+        with pytest.raises(ValueError):  # no masks
+            rx.ProcessBinBundleCaches()
+    finally:
+        db.close()
+
+
+def test_cpp_facade_on_gpu(tmp_path):
+    """Receiver::RunQuery of the C++ facade == the C-ABI path driven from Python, on the same synthetic inputs."""
+    import json
+    import pathlib
+    import subprocess
+    import apsu_b200
+    root = pathlib.Path(__file__).resolve().parent.parent
+    exe = tmp_path / "test_facade"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", str(exe), str(root / "tests" / "cpp" / "test_facade.cpp"),
+                           f"-L{root / 'apsu_b200'}", "-lapsu_b200", f"-Wl,-rpath,{root / 'apsu_b200'}"])
+    table = json.loads((root / "tests" / "golden" / "parameters.json").read_text())
+    pj = tmp_path / "p.json"
+    pj.write_text(json.dumps(table["1M-4096-com.json"]))
+    out = subprocess.check_output([str(exe), "gpu", str(pj), "40", "99"], text=True)
+    lines = [l for l in out.splitlines() if l.startswith("bundle_idx=")]
+    assert len(lines) == 5
+    # same inputs from Python: splitmix64 stream of the C++ test
+    params = apsu_b200.PSUParams.Load(pj.read_text())
+    N, t, primes = params.poly_modulus_degree(), params.plain_modulus(), params.coeff_modulus()
+    K, L, bic = len(primes), len(primes) - 1, params.bundle_idx_count()
+    state = [99]
+
+    def sm():
+        state[0] = (state[0] + 0x9E3779B97F4A7C15) & (2**64 - 1)
+        z = state[0]
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+        return z ^ (z >> 31)
+    qp = params.query_powers()
+    # the C++ test iterates an unordered_map for upload but draws values in std::set order of the powers
+    cts = np.zeros((len(qp), bic, 2, L, N), dtype=np.uint64)
+    for k in range(len(qp)):
+        for b in range(bic):
+            for c in range(2):
+                for j in range(L):
+                    cts[k, b, c, j] = [sm() % primes[j] for _ in range(N)]
+    relin = np.array([sm() % primes[(i // N) % K] for i in range((K - 1) * 2 * K * N)], dtype=np.uint64).reshape(K - 1, 2, K, N)
+    masks = np.array([sm() % t for _ in range(bic * N)], dtype=np.uint64).reshape(bic, N)
+    db = apsu_b200.ReceiverDB(params, 0)
+    try:
+        for b in range(bic):
+            db.add_bin_bundle_synthetic(b, 40, 99 + b)
+        res = apsu_b200.Receiver(db).RunQuery(apsu_b200.Query(qp, cts, relin), masks)
+
+        def fnv(a):
+            h = 1469598103934665603
+            for x in a.reshape(-1):
+                h = ((h ^ int(x)) * 1099511628211) & (2**64 - 1)
+            return h
+        exp = {f"bundle_idx={r.bundle_idx} cache_idx={r.cache_idx} fnv={fnv(r.psu_result):016x}" for r in res}
+        assert set(lines) == exp
+    finally:
+        db.close()

@@ -1,0 +1,142 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared symbol, the
+parameter loader / PowersDag agree with the oracle for all 36 parameter sets, error classes map to the
+reference's exception types, the path fails loudly without a GPU, and BinBundle sharding + the
+torch.distributed exchange work on world_size-2 gloo."""
+import ctypes as C
+import json
+import os
+import pathlib
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+TABLE = json.loads((ROOT / "tests" / "golden" / "parameters.json").read_text())
+
+
+def test_library_exports_every_declared_symbol():
+    from apsu_b200 import capi
+    header = (ROOT / "include" / "apsu_b200.h").read_text()
+    declared = set(re.findall(r"\b(apsu_b200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 40
+    lib = C.CDLL(str(capi.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/apsu_b200.h but not exported"
+    assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
+    assert b"sm_100a" in capi.lib().apsu_b200_version()
+
+
+def test_params_and_powers_dag_match_oracle_for_all_parameter_sets():
+    import apsu_b200
+    for name, obj in TABLE.items():
+        ref = O.Params(obj, name)
+        p = apsu_b200.PSUParams.Load(json.dumps(obj))
+        assert p.coeff_modulus() == ref.primes and p.plain_modulus() == ref.t, name
+        assert (p.bundle_idx_count(), p.items_per_bundle(), p.bins_per_bundle(), p.item_bit_count()) == (
+            ref.bundle_idx_count, ref.items_per_bundle, ref.bins_per_bundle, ref.item_bit_count), name
+        assert p.query_powers() == ref.query_powers
+        dag = apsu_b200.PowersDag(p)
+        exp = {n["power"]: (n["depth"], n["p1"], n["p2"]) for n in O.powers_dag(ref.ps_low_degree, ref.max_items_per_bin, ref.query_powers)}
+        got = {n.power: (n.depth, n.parents[0], n.parents[1]) for n in dag.nodes.values()}
+        assert got == exp, name
+
+
+def test_error_mapping_and_validation():
+    import apsu_b200
+    good = TABLE["16M-4096.json"]
+    with pytest.raises(RuntimeError):  # JSON / loader problems are runtime_error in the reference
+        apsu_b200.PSUParams.Load('{"table_params": {}}')
+    both = json.loads(json.dumps(good))
+    both["seal_params"]["plain_modulus"] = 65537
+    with pytest.raises(RuntimeError):
+        apsu_b200.PSUParams.Load(json.dumps(both))
+    for path, value in [(("table_params", "table_size"), 6553), (("item_params", "felts_per_item"), 1),
+                        (("table_params", "hash_func_count"), 9), (("query_params", "query_powers"), [1, 46]),
+                        (("table_params", "max_items_per_bin"), 0)]:
+        bad = json.loads(json.dumps(good))
+        bad[path[0]][path[1]] = value
+        with pytest.raises(ValueError):  # invalid_argument
+            apsu_b200.PSUParams.Load(json.dumps(bad))
+
+
+def test_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import apsu_b200
+    p = apsu_b200.PSUParams.Load(json.dumps(TABLE["256K-512.json"]))
+    with pytest.raises(apsu_b200.CudaUnavailable):
+        apsu_b200.ReceiverDB(p, 0)
+
+
+def test_product_never_imports_the_oracle():
+    for path in list((ROOT / "apsu_b200").rglob("*.py")) + list((ROOT / "apsu_b200" / "csrc").glob("*")) + list((ROOT / "apsu_b200" / "host").glob("*")):
+        if path.suffix in (".py", ".cu", ".cuh", ".hpp", ".cpp", ".h"):
+            text = path.read_text()
+            assert "oracle" not in text.lower() or path.name in ("capi.py", "eval_kernels.cuh", "capi.cu", "apsu_b200.h", "__init__.py"), path
+            assert "import oracle" not in text and "from oracle" not in text and "liborc" not in text, path
+
+
+def test_cpp_facade_host_side(tmp_path):
+    exe = tmp_path / "test_facade"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", str(exe), str(ROOT / "tests" / "cpp" / "test_facade.cpp"),
+                           f"-L{ROOT / 'apsu_b200'}", "-lapsu_b200", f"-Wl,-rpath,{ROOT / 'apsu_b200'}"])
+    pj = tmp_path / "p.json"
+    pj.write_text(json.dumps(TABLE["16M-4096.json"]))
+    out = subprocess.check_output([str(exe), "host", str(pj)], text=True)
+    assert "N=8192 t=4079617 K=4 bundle_idx_count=4 items_per_bundle=1638 depth=3 sources=6 targets=72" in out
+    assert "exceptions=7" in out
+
+
+def test_shard_partitions_binbundles():
+    from apsu_b200 import sharding
+    degrees = [[1303] * 6 + [153], [1303] * 6 + [196], [1303] * 6 + [156], [1303] * 6 + [116]]
+    for world in (1, 2, 3, 4, 8):
+        parts = sharding.shard_bundles(degrees, world)
+        flat = sorted((b, c) for part in parts for (b, c, _) in part)
+        assert flat == sorted((b, c) for b, row in enumerate(degrees) for c in range(len(row)))
+        loads = [sum(d + 1 for _, _, d in part) for part in parts]
+        assert max(loads) <= 1.35 * (sum(loads) / world) + 1304
+        # a rank touches as few bundle indices as possible
+        assert max(len({b for b, _, _ in part}) for part in parts) <= max(1, -(-4 // world)) + (1 if world == 3 else 0)
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from apsu_b200 import sharding
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+degrees = [[5, 3, 1], [4], [2, 2]]
+parts = sharding.shard_bundles(degrees, world)
+N = 16
+q = torch.arange(24, dtype=torch.int64) * 7 if rank == 0 else torch.zeros(24, dtype=torch.int64)
+sharding.broadcast_query([q], src=0)
+assert torch.equal(q, torch.arange(24, dtype=torch.int64) * 7)
+mine = parts[rank]
+local = torch.tensor([[b * 100 + c] * (2 * N) for (b, c, _) in mine], dtype=torch.int64).reshape(len(mine), 2, N)
+gathered = sharding.gather_results(local, [len(p) for p in parts], N, dst=0)
+if rank == 0:
+    order = [(b, c) for p in parts for (b, c, _) in p]
+    assert gathered.shape[0] == len(order)
+    for k, (b, c) in enumerate(order):
+        assert int(gathered[k, 0, 0]) == b * 100 + c
+    print("OK")
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_exchange_on_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517")
+    out = subprocess.check_output([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                                   "--master-addr", "127.0.0.1", "--master-port", "29517", str(script), str(ROOT)],
+                                  env=env, text=True, stderr=subprocess.STDOUT, timeout=300)
+    assert "OK" in out
