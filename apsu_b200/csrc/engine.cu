@@ -629,7 +629,7 @@ void Engine::build_plan()
         const uint32_t nj_all = (uint32_t)jobs.size(), nb_all = (uint32_t)psb.size();
         const uint32_t acc0 = arena_.take((size_t)direct.size() * 2 * Ll); // direct evaluation accumulators
         const uint32_t tin0 = arena_.take((size_t)nj_all * 2 * Ll);        // inner polynomials i >= 1
-        const uint32_t r00 = drops ? 0 : arena_.take((size_t)nb_all * 2 * Ll); // i = 0 polynomial (no level gap)
+        const uint32_t r00 = arena_.take((size_t)nb_all * 2 * Ll);        // sum of the i = 0 terms
         const uint32_t stageA_count = (uint32_t)arena_.top - acc0;
         std::vector<MacGroup> groups;
         std::vector<FinalizeJob> fin_direct;
@@ -657,10 +657,11 @@ void Engine::build_plan()
                 add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, coeff, jobs[j].nterms, tin0 + j * 2 * Ll);
                 mac_bytes += (uint64_t)jobs[j].nterms * Ll * N * 8;
             }
-            if (!drops) { // i = 0 terms can be summed in NTT form when no mod-switch separates them from the result
-                add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, s->ntt_coeffs.p, ps, r00 + k * 2 * Ll);
-                mac_bytes += (uint64_t)ps * Ll * N * 8;
-            }
+            // i = 0 terms summed in NTT form.  Without a level gap this IS the i = 0 polynomial; with one
+            // (per-term mod-switch, bin_bundle.cpp:314-324) it supplies the linear part and only the terms'
+            // last-prime residues are handled one by one (k_ms_sum_last).
+            add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, s->ntt_coeffs.p, ps, r00 + k * 2 * Ll);
+            mac_bytes += (uint64_t)ps * Ll * N * 8;
         }
         emit_mac(pb, Ll, groups, mac_bytes);
         // ===== stage B (whole DB): back to coefficient form =====
@@ -678,14 +679,16 @@ void Engine::build_plan()
             std::vector<MulTermsJob> mulj;
             std::vector<uint32_t> tinh(nj), r0h(nb);
             if (drops) {
-                // i = 0 polynomial: every term is taken to coefficient form and mod-switched on its own (:314-324)
-                const uint32_t t00 = arena_.take((size_t)nb * ps * 2 * Ll);
+                // i = 0 polynomial: every term is mod-switched on its own (:314-324).  Exact shortcut: the
+                // rounding of a term depends only on its last-prime residue, so only those ps*2 polynomials
+                // are inverse-transformed per term; the other primes use the already inverted sum r00.
+                const uint32_t t00 = arena_.take((size_t)nb * ps * 2);
                 for (uint32_t k = 0; k < nb; k++) {
                     BinBundleStore *s = psb[c0 + k].ref.s;
                     MulTermsJob mj;
                     std::memset(&mj, 0, sizeof(mj));
                     mj.coeff = s->ntt_coeffs.p;
-                    mj.out_idx = t00 + k * ps * 2 * Ll;
+                    mj.out_idx = t00 + k * ps * 2;
                     mj.pow_idx = low_base[s->bundle_idx];
                     mj.pow_term_stride = 2 * Ll;
                     mj.pow_comp_stride = Ll;
@@ -693,9 +696,8 @@ void Engine::build_plan()
                     mulj.push_back(mj);
                 }
                 emit_mul_terms(pb, Ll, mulj, ps);
-                pb.ntt_run(t00, nb * ps * 2 * Ll, ctx.pattern_q(Ll), true);
+                pb.ntt_run(t00, nb * ps * 2, { Ll - 1 }, true);
                 const uint32_t tinh0 = arena_.take((size_t)nj * 2 * Lh);
-                const uint32_t t0h0 = arena_.take((size_t)nb * ps * 2 * Lh);
                 const uint32_t r0h0 = arena_.take((size_t)nb * 2 * Lh);
                 std::vector<uint32_t> ms_src, ms_dst;
                 for (uint32_t j = 0; j < nj; j++)
@@ -703,22 +705,22 @@ void Engine::build_plan()
                         ms_src.push_back(tin0 + ((j0 + j) * 2 + c) * Ll);
                         ms_dst.push_back(tinh0 + (j * 2 + c) * Lh);
                     }
-                for (uint32_t k = 0; k < nb * ps; k++)
-                    for (uint32_t c = 0; c < 2; c++) {
-                        ms_src.push_back(t00 + (k * 2 + c) * Ll);
-                        ms_dst.push_back(t0h0 + (k * 2 + c) * Lh);
-                    }
                 pb.mod_switch_next(Ll, ms_src, ms_dst);
-                std::vector<std::vector<uint32_t>> terms;
-                std::vector<uint32_t> sdst;
-                for (uint32_t k = 0; k < nb; k++)
-                    for (uint32_t c = 0; c < 2; c++) {
-                        std::vector<uint32_t> tl;
-                        for (uint32_t j = 0; j < ps; j++) tl.push_back(t0h0 + ((k * ps + j) * 2 + c) * Lh);
-                        terms.push_back(tl);
-                        sdst.push_back(r0h0 + (k * 2 + c) * Lh);
+                {
+                    std::vector<uint32_t> sum_idx(nb), last_idx(nb), dst_idx(nb);
+                    for (uint32_t k = 0; k < nb; k++) {
+                        sum_idx[k] = r00 + (c0 + k) * 2 * Ll;
+                        last_idx[k] = t00 + k * ps * 2;
+                        dst_idx[k] = r0h0 + k * 2 * Lh;
                     }
-                pb.sum_polys(Lh, terms, sdst);
+                    size_t so = idx_.add(sum_idx), lo = idx_.add(last_idx), dn = idx_.add(dst_idx);
+                    pb.step([=] {
+                        k_ms_sum_last<<<dim3(ctx.N / kEwThreads, 2, nb), kEwThreads, 0, ctx.stream>>>(
+                            arena_.buf.p, idx_.at(so), idx_.at(lo), idx_.at(dn), ps, ctx.level[Ll], (int)ctx.N);
+                        APSU_CUDA_CHECK(cudaGetLastError());
+                        ctx.launches++;
+                    });
+                }
                 for (uint32_t j = 0; j < nj; j++) tinh[j] = tinh0 + j * 2 * Lh;
                 for (uint32_t k = 0; k < nb; k++) r0h[k] = r0h0 + k * 2 * Lh;
             } else {
@@ -904,7 +906,7 @@ void Engine::emit_mul_terms(ProgramBuilder &pb, uint32_t L, std::vector<MulTerms
     uint32_t n = (uint32_t)jobs.size();
     jobs.clear();
     pb.step([=] {
-        k_db_mul<<<dim3(L * ctx.N / kMacThreads, nterms, n), kMacThreads, 0, ctx.stream>>>(
+        k_db_mul_last<<<dim3(ctx.N / kMacThreads, nterms, n), kMacThreads, 0, ctx.stream>>>(
             arena_.buf.p, reinterpret_cast<const MulTermsJob *>(desc_dev_.p + off), ctx.level[L], (int)ctx.N);
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;

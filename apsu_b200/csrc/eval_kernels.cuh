@@ -105,6 +105,66 @@ k_db_mul(u64 *A, const MulTermsJob *__restrict__ jobs, LevelConsts c, int N)
     o[LN] = mul_mod(pw[(size_t)jb.pow_comp_stride * N], w, m);
 }
 
+// Last-prime variant: only the residues modulo the LAST prime of the level are produced,
+// out[term][c][n] (one polynomial per (term, component)).  grid (N/256, nterms, n_bundles).
+// Used for the PS i=0 polynomial when a mod-switch separates low and high powers: the per-term rounding of
+// mod_switch_to_next only depends on each term's last-prime residue (see k_ms_sum_last).
+__global__ void __launch_bounds__(kMacThreads)
+k_db_mul_last(u64 *A, const MulTermsJob *__restrict__ jobs, LevelConsts c, int N)
+{
+    const MulTermsJob jb = jobs[blockIdx.z];
+    const u32 j = blockIdx.y;
+    if (j >= jb.nterms) return;
+    const u32 n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = c.L - 1;
+    const DMod m = c.q[l];
+    const size_t LN = (size_t)c.L * N, col = (size_t)l * N + n;
+    const u64 w = unpack30_word(__ldcs(jb.coeff + j * LN + col));
+    const u64 *pw = A + ((size_t)jb.pow_idx + (size_t)j * jb.pow_term_stride) * N + col;
+    u64 *o = A + ((size_t)jb.out_idx + (size_t)j * 2) * N + n;
+    o[0] = mul_mod(pw[0], w, m);
+    o[N] = mul_mod(pw[(size_t)jb.pow_comp_stride * N], w, m);
+}
+
+// sum_j mod_switch_to_next(t_j) for terms t_j given as (a) the coefficient-form SUM of all terms modulo the
+// first L-1 primes and (b) each term's coefficient-form residue modulo the last prime q_k:
+//   mod_switch(t_j)[i] = (t_j[i] - ((t_j[k] + half) mod q_k) mod q_i + half mod q_i) * q_k^-1   (mod q_i)
+// is linear in t_j[i] once a_j = (t_j[k] + half) mod q_k is known, so
+//   sum_j = (sum_j t_j[i] - sum_j (a_j mod q_i) + nterms * (half mod q_i)) * q_k^-1  (mod q_i)   — exact.
+// grid (N/256, 2, n_bundles): sum_idx[b] -> [2][L][N] (component c at +c*L), last_idx[b] -> [nterms][2][N],
+// dst_idx[b] -> [2][L-1][N].
+__global__ void __launch_bounds__(kEwThreads)
+k_ms_sum_last(u64 *A, const u32 *__restrict__ sum_idx, const u32 *__restrict__ last_idx, const u32 *__restrict__ dst_idx, u32 nterms,
+              LevelConsts c, int N)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 comp = blockIdx.y, b = blockIdx.z;
+    const int L = c.L;
+    const u64 qk = c.q[L - 1].q, half = qk >> 1;
+    u64 s[kMaxQ];
+#pragma unroll
+    for (int i = 0; i < kMaxQ; i++) s[i] = 0;
+    const u64 *t = A + ((size_t)last_idx[b] + comp) * N + n;
+    for (u32 j = 0; j < nterms; j++) {
+        const u64 a = add_mod(t[(size_t)j * 2 * N], half, qk);
+#pragma unroll
+        for (int i = 0; i < kMaxQ - 1; i++)
+            if (i + 1 < L) s[i] = add_mod(s[i], barrett64(a, c.q[i]), c.q[i].q);
+    }
+    const u64 *x = A + ((size_t)sum_idx[b] + (size_t)comp * L) * N + n;
+    u64 *o = A + ((size_t)dst_idx[b] + (size_t)comp * (L - 1)) * N + n;
+#pragma unroll
+    for (int i = 0; i < kMaxQ - 1; i++) {
+        if (i + 1 < L) {
+            const DMod m = c.q[i];
+            const u64 corr = mul_mod(barrett64(nterms, m), c.half_mod[i], m); // nterms * (half mod q_i)
+            u64 v = sub_mod(x[(size_t)i * N], s[i], m.q);
+            v = add_mod(v, corr, m.q);
+            o[(size_t)i * N] = mul_shoup(v, c.inv_qlast[i], m.q);
+        }
+    }
+}
+
 // ---- final assembly of one result ciphertext ----
 struct FinalizeJob {
     u32 src[3];          // arena indices of size-2 ciphertexts [2][Ls][N] to add up (0xFFFFFFFF = none)
