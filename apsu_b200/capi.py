@@ -106,6 +106,7 @@ SIGNATURES = {
     "apsu_b200_op_relinearize": (C.c_int, [vp, C.c_uint32, u64p, u64p, C.c_uint32]),
     "apsu_b200_op_mod_switch_next": (C.c_int, [vp, C.c_uint32, u64p, u64p, C.c_uint32]),
     "apsu_b200_last_timings": (C.c_int, [vp, C.POINTER(CTimings)]),
+    "apsu_b200_bench_ntt": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_float)]),
     "apsu_b200_set_profiling": (C.c_int, [vp, C.c_int]),
 }
 

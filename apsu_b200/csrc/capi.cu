@@ -357,6 +357,30 @@ int apsu_b200_last_timings(apsu_b200_ctx *ctx, apsu_b200_timings *out)
         *need(out, "out") = e.timings;
     });
 }
+int apsu_b200_bench_ntt(apsu_b200_ctx *ctx, uint32_t count, uint32_t iters, int inverse, float *ms)
+{
+    return guarded([&] {
+        Engine &e = E(ctx);
+        if (!count || !iters) throw std::invalid_argument("count and iters must be positive");
+        DBuf<u64> buf;
+        buf.alloc((size_t)count * e.ctx.N);
+        APSU_CUDA_CHECK(cudaMemsetAsync(buf.p, 0, buf.n * 8, e.ctx.stream));
+        auto pat = e.ctx.pattern_q(e.ctx.first_L);
+        e.ctx.ntt(buf.p, buf.p, count, pat, inverse != 0); // warm-up
+        cudaEvent_t a, b;
+        APSU_CUDA_CHECK(cudaEventCreate(&a));
+        APSU_CUDA_CHECK(cudaEventCreate(&b));
+        APSU_CUDA_CHECK(cudaEventRecord(a, e.ctx.stream));
+        for (uint32_t i = 0; i < iters; i++) e.ctx.ntt(buf.p, buf.p, count, pat, inverse != 0);
+        APSU_CUDA_CHECK(cudaEventRecord(b, e.ctx.stream));
+        APSU_CUDA_CHECK(cudaEventSynchronize(b));
+        float t = 0;
+        APSU_CUDA_CHECK(cudaEventElapsedTime(&t, a, b));
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        *need(ms, "ms") = t / iters;
+    });
+}
 int apsu_b200_set_profiling(apsu_b200_ctx *ctx, int enabled)
 {
     return guarded([&] { E(ctx).profiling = enabled != 0; });

@@ -85,69 +85,108 @@ __device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict_
     }
 }
 
-template <int LOGN, bool FWD, int S, int REM>
-struct PassRunner {
-    // runs stages [S, LOGN) forward (ascending) — or the same stages descending for the inverse
+// middle passes (shared memory -> shared memory), COUNT passes of three stages starting at stage S;
+// the inverse transform runs the same passes in the opposite order
+template <int LOGN, bool FWD, int S, int COUNT>
+struct MidRunner {
     __device__ static __forceinline__ void run(u64 *sm, const ulonglong2 *tw, u64 q, u64 two_q)
     {
-        constexpr int R = REM >= 3 ? 3 : REM;
         if (FWD) {
-            smem_pass<LOGN, R, true>(sm, tw, S, q, two_q);
+            smem_pass<LOGN, 3, true>(sm, tw, S, q, two_q);
             __syncthreads();
-            PassRunner<LOGN, FWD, S + R, REM - R>::run(sm, tw, q, two_q);
+            MidRunner<LOGN, FWD, S + 3, COUNT - 1>::run(sm, tw, q, two_q);
         } else {
-            PassRunner<LOGN, FWD, S + R, REM - R>::run(sm, tw, q, two_q);
-            smem_pass<LOGN, R, false>(sm, tw, S, q, two_q);
+            MidRunner<LOGN, FWD, S + 3, COUNT - 1>::run(sm, tw, q, two_q);
+            smem_pass<LOGN, 3, false>(sm, tw, S, q, two_q);
             __syncthreads();
         }
     }
 };
 template <int LOGN, bool FWD, int S>
-struct PassRunner<LOGN, FWD, S, 0> {
+struct MidRunner<LOGN, FWD, S, 0> {
     __device__ static __forceinline__ void run(u64 *, const ulonglong2 *, u64, u64) {}
 };
 
+// One CTA per polynomial.  Stages are grouped as [RF | 3 | 3 | ... | 3] with RF = 1..3; the pass that touches
+// global memory on the way in and the one on the way out do their butterflies straight from / to global
+// memory (coalesced), so a transform costs (number of passes - 1) shared-memory round trips.
 template <int LOGN, bool FWD>
 __global__ void __launch_bounds__((1 << LOGN) / 16, (1 << (14 - LOGN))) ntt_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, NttArgs a, NttSrc src)
 {
     constexpr int N = 1 << LOGN;
+    constexpr int RF = (LOGN % 3 == 0) ? 3 : (LOGN % 3);
+    constexpr int MID = (LOGN - RF - 3) / 3;
     extern __shared__ u64 sm[];
     const unsigned p = blockIdx.x;
     const int slot = p % a.pattern_len;
     const DMod m = a.mod[slot];
     const u64 q = m.q, two_q = 2 * m.q;
     const ulonglong2 *tw = a.tw + ((size_t)a.table[slot] * 2 + (FWD ? 0 : 1)) * N;
-
     const u64 *ip = in + (size_t)(src.src_idx ? src.src_idx[p] : p) * N;
+    u64 *op = out + (size_t)(src.dst_idx ? src.dst_idx[p] : p) * N;
     const bool reduce = src.reduce_input != 0;
-    const ulonglong2 *ip2 = reinterpret_cast<const ulonglong2 *>(ip);
-    for (unsigned i = threadIdx.x; i < N / 2; i += blockDim.x) {
-        ulonglong2 v = ip2[i];
-        if (reduce) {
-            v.x = barrett64(v.x, m);
-            v.y = barrett64(v.y, m);
+
+    if (FWD) {
+        // stages [0, RF): global -> registers -> shared
+        {
+            constexpr unsigned stride = N >> RF;
+            for (unsigned g = threadIdx.x; g < stride; g += blockDim.x) {
+                u64 x[1 << RF];
+#pragma unroll
+                for (int k = 0; k < (1 << RF); k++) {
+                    u64 v = ip[g + k * stride];
+                    x[k] = reduce ? barrett64(v, m) : v;
+                }
+                fwd_group<RF>(x, tw, 0, 0, q, two_q);
+#pragma unroll
+                for (int k = 0; k < (1 << RF); k++) sm[pad_idx(g + k * stride)] = x[k];
+            }
         }
-        const unsigned pi = pad_idx(2 * i); // 2i and 2i+1 share a 16-group, so they stay adjacent
-        sm[pi] = v.x;
-        sm[pi + 1] = v.y;
-    }
-    __syncthreads();
-    PassRunner<LOGN, FWD, 0, LOGN>::run(sm, tw, q, two_q);
-    ulonglong2 *op2 = reinterpret_cast<ulonglong2 *>(out + (size_t)(src.dst_idx ? src.dst_idx[p] : p) * N);
-    const DShoup inv_n = a.inv_n[slot];
-    for (unsigned i = threadIdx.x; i < N / 2; i += blockDim.x) {
-        const unsigned pi = pad_idx(2 * i);
-        ulonglong2 v = make_ulonglong2(sm[pi], sm[pi + 1]);
-        if (FWD) {
-            if (v.x >= two_q) v.x -= two_q;
-            if (v.x >= q) v.x -= q;
-            if (v.y >= two_q) v.y -= two_q;
-            if (v.y >= q) v.y -= q;
-        } else {
-            v.x = mul_shoup(v.x, inv_n, q);
-            v.y = mul_shoup(v.y, inv_n, q);
+        __syncthreads();
+        MidRunner<LOGN, true, RF, MID>::run(sm, tw, q, two_q);
+        // stages [LOGN-3, LOGN): shared -> registers -> global, fully reduced
+        for (unsigned g = threadIdx.x; g < (N >> 3); g += blockDim.x) {
+            u64 x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = sm[pad_idx(8 * g + k)];
+            fwd_group<3>(x, tw, g, LOGN - 3, q, two_q);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (x[k] >= two_q) x[k] -= two_q;
+                if (x[k] >= q) x[k] -= q;
+            }
+            ulonglong2 *o2 = reinterpret_cast<ulonglong2 *>(op + 8 * g);
+#pragma unroll
+            for (int k = 0; k < 4; k++) o2[k] = make_ulonglong2(x[2 * k], x[2 * k + 1]);
         }
-        op2[i] = v;
+    } else {
+        // stages [LOGN-3, LOGN) first: global -> registers -> shared
+        for (unsigned g = threadIdx.x; g < (N >> 3); g += blockDim.x) {
+            u64 x[8];
+            const ulonglong2 *i2 = reinterpret_cast<const ulonglong2 *>(ip + 8 * g);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                ulonglong2 v = i2[k];
+                x[2 * k] = reduce ? barrett64(v.x, m) : v.x;
+                x[2 * k + 1] = reduce ? barrett64(v.y, m) : v.y;
+            }
+            inv_group<3>(x, tw, g, LOGN - 3, q, two_q);
+#pragma unroll
+            for (int k = 0; k < 8; k++) sm[pad_idx(8 * g + k)] = x[k];
+        }
+        __syncthreads();
+        MidRunner<LOGN, false, RF, MID>::run(sm, tw, q, two_q);
+        // stages [0, RF) last, then the N^-1 scaling: shared -> registers -> global
+        const DShoup inv_n = a.inv_n[slot];
+        constexpr unsigned stride = N >> RF;
+        for (unsigned g = threadIdx.x; g < stride; g += blockDim.x) {
+            u64 x[1 << RF];
+#pragma unroll
+            for (int k = 0; k < (1 << RF); k++) x[k] = sm[pad_idx(g + k * stride)];
+            inv_group<RF>(x, tw, 0, 0, q, two_q);
+#pragma unroll
+            for (int k = 0; k < (1 << RF); k++) op[g + k * stride] = mul_shoup(x[k], inv_n, q);
+        }
     }
 }
 

@@ -197,6 +197,10 @@ typedef struct apsu_b200_timings {
     uint32_t kernel_launches; /* kernels launched by the last compute_powers + eval_all */
 } apsu_b200_timings;
 int apsu_b200_last_timings(apsu_b200_ctx *ctx, apsu_b200_timings *out);
+/* NTT micro-benchmark on device-resident data: `count` polynomials over the first-level primes, `iters`
+ * back-to-back launches timed with CUDA events; *ms = average per launch.  (BASELINE metric "NTT GB/s":
+ * 16*N bytes per polynomial per transform.) */
+int apsu_b200_bench_ntt(apsu_b200_ctx *ctx, uint32_t count, uint32_t iters, int inverse, float *ms);
 /* when enabled, DB-stream launches are individually timed with CUDA events (adds event overhead only) */
 int apsu_b200_set_profiling(apsu_b200_ctx *ctx, int enabled);
 
