@@ -573,7 +573,7 @@ void Engine::build_plan()
         for (auto &v : db) alpha_max = std::max<uint32_t>(alpha_max, (uint32_t)v.size());
         npack_needed_ = alpha_max * bic;
 
-        uint32_t chunk = 2;
+        uint32_t chunk = 32; // measured on B200: larger batches win over L2 locality (launch tails dominate)
         if (const char *ev = std::getenv("APSU_B200_CHUNK")) chunk = (uint32_t)std::max(1, atoi(ev));
         const uint32_t drops = Ll - Lh;
         if (drops > 1) throw std::logic_error("unexpected level gap between low and high powers");
