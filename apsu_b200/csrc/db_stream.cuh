@@ -107,99 +107,76 @@ __device__ __forceinline__ u64 reduce3(const Acc3 &a, const DMod &m)
     return barrett128(lo, hi, m);
 }
 
+// a stage holds TWO consecutive terms: [term a: p0 | p1 | w_0..w_{G-1}] [term b: same]
 template <int G>
 struct StreamCfg {
-    static constexpr int stage_words = (2 + G) * kStreamCols; // p0 | p1 | w_0..w_{G-1}
-    static constexpr size_t smem_bytes = (size_t)kStreamStages * stage_words * 8 + 2 * kStreamStages * 8 + sizeof(MacGroup) + 16;
+    static constexpr int term_words = (2 + G) * kStreamCols;
+    static constexpr int stage_words = 2 * term_words;
+    static constexpr size_t smem_bytes = (size_t)kStreamStages * stage_words * 8 + 2 * kStreamStages * 8 + 16;
 };
 
-// grid (L*N/128, n_groups, kMacJobs/G), block 160 (4 consumer warps + 1 producer warp).
-// A CTA handles jobs [z*G, z*G+G) of its MacGroup.  RAGGED: jobs of the group have different term counts
-// (a job that ran out of terms multiplies by zero); otherwise every job has max_terms terms.
-// norm_period / reduce_period depend only on the bit size of the largest prime (host computes them).
+// two terms into one accumulator.  The MACs of a lane are adjacent so that ptxas folds each pair of
+// products into one IADD3 / IADD3.X (three-input adds with two carries): 4 add instructions per MAC
+// instead of 6 (the compiler never keeps the 64-bit addend inside IMAD.WIDE on sm_100a).
+__device__ __forceinline__ void mac3x2(Acc3 &a, u32 wla, u32 wha, u32 pla, u32 pha, u32 wlb, u32 whb, u32 plb, u32 phb)
+{
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.ll) : "r"(wla), "r"(pla));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.ll) : "r"(wlb), "r"(plb));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(wla), "r"(pha));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(wha), "r"(pla));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(wlb), "r"(phb));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(whb), "r"(plb));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.hh) : "r"(wha), "r"(pha));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.hh) : "r"(whb), "r"(phb));
+}
+
+// consumer side of one work item: all term pairs of G jobs on one 128-coefficient tile
 template <int G, bool RAGGED>
-__global__ void __launch_bounds__(kStreamThreads)
-k_db_mac_tma(u64 *A, const MacGroup *__restrict__ groups, LevelConsts c, int N, u32 norm_period, u32 reduce_period)
+__device__ __forceinline__ void stream_consume(const MacGroup *__restrict__ g, int job0, u32 max_terms, u32 &it, u64 *ring, u64 *full,
+                                               u64 *empty, Acc3 (&acc)[G][2], const DMod &m, u32 norm_pairs, u32 reduce_period)
 {
     using Cfg = StreamCfg<G>;
-    extern __shared__ __align__(128) u64 smem[];
-    u64 *ring = smem;                                     // [stage][2+G][128]
-    u64 *full = smem + kStreamStages * Cfg::stage_words;  // [stage]
-    u64 *empty = full + kStreamStages;                    // [stage]
-    MacGroup *g = reinterpret_cast<MacGroup *>(empty + kStreamStages);
-
     const int tid = threadIdx.x;
-    if (tid < (int)(sizeof(MacGroup) / 4)) reinterpret_cast<u32 *>(g)[tid] = reinterpret_cast<const u32 *>(&groups[blockIdx.y])[tid];
-    if (tid == 0) {
-        for (int s = 0; s < kStreamStages; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kStreamConsumerWarps);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const int job0 = blockIdx.z * G;
-    if (job0 >= (int)g->njobs) return; // whole CTA: nothing to do for this slice of the group
-    u32 max_terms = 0;
-#pragma unroll
-    for (int k = 0; k < G; k++) max_terms = max(max_terms, g->nterms[job0 + k]);
-
-    const u32 col0 = blockIdx.x * kStreamCols; // l*N + n0 of this tile
-    const size_t LN = (size_t)c.L * N;
-
-    if (tid >= kStreamCols) {
-        // ---------------- producer warp ----------------
-        if (tid == kStreamCols) {
-            const u64 pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-            const u64 *pw = A + (size_t)g->pow_idx * N + col0;
-            const size_t tstride = (size_t)g->pow_term_stride * N, cstride = (size_t)g->pow_comp_stride * N;
-            for (u32 j = 0; j < max_terms; j++) {
-                const int s = j % kStreamStages;
-                const u32 use = j / kStreamStages;
-                if (use) mbar_wait(&empty[s], (use - 1) & 1);
-                u32 active = G;
-                if (RAGGED) {
-                    active = 0;
-                    for (int k = 0; k < G; k++) active += (j < g->nterms[job0 + k]);
-                }
-                mbar_expect_tx(&full[s], (2 + active) * kStreamTileBytes);
-                u64 *st = ring + (size_t)s * Cfg::stage_words;
-                bulk_g2s(st, pw + j * tstride, kStreamTileBytes, &full[s], pol_keep);
-                bulk_g2s(st + kStreamCols, pw + j * tstride + cstride, kStreamTileBytes, &full[s], pol_keep);
-                for (int k = 0; k < G; k++)
-                    if (!RAGGED || j < g->nterms[job0 + k])
-                        bulk_g2s(st + (2 + k) * kStreamCols, g->coeff[job0 + k] + j * LN + col0, kStreamTileBytes, &full[s], pol_stream);
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumer warps: one (prime, coefficient) column per thread ----------------
-    const DMod m = c.q[col0 / N];
-    Acc3 acc[G][2];
-#pragma unroll
-    for (int k = 0; k < G; k++) acc[k][0] = acc[k][1] = Acc3{ 0, 0, 0 };
+    const u32 npairs = (max_terms + 1) / 2;
     u32 since_norm = 0, since_reduce = 0;
-
-    for (u32 j = 0; j < max_terms; j++) {
-        const int s = j % kStreamStages;
-        mbar_wait(&full[s], (j / kStreamStages) & 1);
-        const u64 *st = ring + (size_t)s * Cfg::stage_words + tid;
-        const u64 p0 = st[0], p1 = st[kStreamCols];
-        const u32 p0l = (u32)p0 & 0x3FFFFFFFu, p0h = (u32)(p0 >> 30);
-        const u32 p1l = (u32)p1 & 0x3FFFFFFFu, p1h = (u32)(p1 >> 30);
+    u32 nt[G];
+    if (RAGGED) {
+#pragma unroll
+        for (int k = 0; k < G; k++) nt[k] = __ldg(&g->nterms[job0 + k]);
+    }
+    for (u32 jp = 0; jp < npairs; jp++, it++) {
+        const int s = it % kStreamStages;
+        mbar_wait(&full[s], (it / kStreamStages) & 1);
+        const u64 *sa = ring + (size_t)s * Cfg::stage_words + tid;
+        const u64 *sb = sa + Cfg::term_words;
+        const bool two = 2 * jp + 1 < max_terms; // uniform; an odd tail multiplies the (stale) b operands by zero
+        // copy the stage into registers and hand it back to the producer at once: the ring's job is to keep
+        // HBM requests in flight, so a stage must not stay occupied while the MACs run
+        const u64 p0a = sa[0], p1a = sa[kStreamCols], p0b = sb[0], p1b = sb[kStreamCols];
+        u64 wa[G], wb[G];
 #pragma unroll
         for (int k = 0; k < G; k++) {
-            u64 w = st[(2 + k) * kStreamCols]; // packed: halves are the two limbs
-            if (RAGGED) w = (j < g->nterms[job0 + k]) ? w : 0ull; // stale tile of a finished job
-            const u32 wl = (u32)w, wh = (u32)(w >> 32);
-            mac3(acc[k][0], wl, wh, p0l, p0h);
-            mac3(acc[k][1], wl, wh, p1l, p1h);
+            wa[k] = sa[(2 + k) * kStreamCols]; // packed: halves are the limbs
+            wb[k] = sb[(2 + k) * kStreamCols];
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty[s]);
-        if (++since_norm == norm_period) {
+        const u32 p0al = (u32)p0a & 0x3FFFFFFFu, p0ah = (u32)(p0a >> 30), p1al = (u32)p1a & 0x3FFFFFFFu, p1ah = (u32)(p1a >> 30);
+        const u32 p0bl = (u32)p0b & 0x3FFFFFFFu, p0bh = (u32)(p0b >> 30), p1bl = (u32)p1b & 0x3FFFFFFFu, p1bh = (u32)(p1b >> 30);
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            u64 a = wa[k], b = wb[k];
+            if (RAGGED) {
+                a = (2 * jp < nt[k]) ? a : 0ull; // stale tile of a finished job
+                b = (2 * jp + 1 < nt[k]) ? b : 0ull;
+            } else if (!two) {
+                b = 0ull;
+            }
+            const u32 wal = (u32)a, wah = (u32)(a >> 32), wbl = (u32)b, wbh = (u32)(b >> 32);
+            mac3x2(acc[k][0], wal, wah, p0al, p0ah, wbl, wbh, p0bl, p0bh);
+            mac3x2(acc[k][1], wal, wah, p1al, p1ah, wbl, wbh, p1bl, p1bh);
+        }
+        if (++since_norm == norm_pairs) {
             since_norm = 0;
 #pragma unroll
             for (int k = 0; k < G; k++) {
@@ -217,15 +194,113 @@ k_db_mac_tma(u64 *A, const MacGroup *__restrict__ groups, LevelConsts c, int N, 
             }
         }
     }
-    const u32 col = col0 + tid;
+}
+
+// Persistent kernel: grid = SMs x resident CTAs, block 160 (4 consumer warps + 1 producer warp).  Work item =
+// (group, slice of G jobs, 128-coefficient tile); a CTA walks items blockIdx.x, +gridDim.x, ... with tiles
+// fastest, so the CTAs running at any moment read neighbouring memory and the TMA ring never drains between
+// items (the producer prefetches the next item while the consumers reduce and store the current one).
+// MacGroup::pad_ != 0 marks a ragged group (jobs of different length).
+// norm_pairs = term PAIRS between lane renormalisations, reduce_period = renormalisations between full
+// reductions; both depend only on the bit size of the largest prime (host computes them).
+template <int G>
+__global__ void __launch_bounds__(kStreamThreads, (G == 4 ? 4 : 3))
+k_db_mac_tma(u64 *A, const MacGroup *__restrict__ groups, u32 n_groups, LevelConsts c, int N, u32 norm_pairs, u32 reduce_period)
+{
+    using Cfg = StreamCfg<G>;
+    extern __shared__ __align__(128) u64 smem[];
+    u64 *ring = smem;                                     // [stage][2][2+G][128]
+    u64 *full = smem + kStreamStages * Cfg::stage_words;  // [stage]
+    u64 *empty = full + kStreamStages;                    // [stage]
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < kStreamStages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kStreamConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    constexpr u32 slices = kMacJobs / G;
+    const u32 n_tiles = (u32)c.L * N / kStreamCols;
+    const u32 n_items = n_groups * slices * n_tiles;
+    const size_t LN = (size_t)c.L * N;
+    u32 it = 0; // stage counter, runs across work items identically in the producer and the consumers
+
+    if (tid >= kStreamCols) {
+        // ---------------- producer warp ----------------
+        if (tid != kStreamCols) return;
+        const u64 pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+        for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const u32 tile = item % n_tiles, rest = item / n_tiles;
+            const MacGroup *g = &groups[rest / slices];
+            const int job0 = (int)(rest % slices) * G;
+            if (job0 >= (int)g->njobs) continue;
+            u32 nt[G], max_terms = 0;
+            const u64 *cf[G];
+            for (int k = 0; k < G; k++) {
+                nt[k] = g->nterms[job0 + k];
+                cf[k] = g->coeff[job0 + k];
+                max_terms = max(max_terms, nt[k]);
+            }
+            const bool ragged = g->pad_ != 0;
+            const u32 col0 = tile * kStreamCols;
+            const u64 *pw = A + (size_t)g->pow_idx * N + col0;
+            const size_t tstride = (size_t)g->pow_term_stride * N, cstride = (size_t)g->pow_comp_stride * N;
+            const u32 npairs = (max_terms + 1) / 2;
+            for (u32 jp = 0; jp < npairs; jp++, it++) {
+                const int s = it % kStreamStages;
+                const u32 use = it / kStreamStages;
+                if (use) mbar_wait(&empty[s], (use - 1) & 1);
+                const u32 nt2 = (2 * jp + 1 < max_terms) ? 2u : 1u;
+                u32 tiles = 2 * nt2;
+                for (u32 h = 0; h < nt2; h++)
+                    for (int k = 0; k < G; k++) tiles += (!ragged || 2 * jp + h < nt[k]);
+                mbar_expect_tx(&full[s], tiles * kStreamTileBytes);
+                for (u32 h = 0; h < nt2; h++) {
+                    const u32 j = 2 * jp + h;
+                    u64 *st = ring + (size_t)s * Cfg::stage_words + (size_t)h * Cfg::term_words;
+                    bulk_g2s(st, pw + j * tstride, kStreamTileBytes, &full[s], pol_keep);
+                    bulk_g2s(st + kStreamCols, pw + j * tstride + cstride, kStreamTileBytes, &full[s], pol_keep);
+                    for (int k = 0; k < G; k++)
+                        if (!ragged || j < nt[k]) bulk_g2s(st + (2 + k) * kStreamCols, cf[k] + j * LN + col0, kStreamTileBytes, &full[s], pol_stream);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps: one (prime, coefficient) column per thread ----------------
+    for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const u32 tile = item % n_tiles, rest = item / n_tiles;
+        const MacGroup *g = &groups[rest / slices];
+        const int job0 = (int)(rest % slices) * G;
+        const int njobs = (int)__ldg(&g->njobs);
+        if (job0 >= njobs) continue;
+        u32 max_terms = 0;
 #pragma unroll
-    for (int k = 0; k < G; k++) {
-        if (job0 + k < (int)g->njobs) {
-            normalize3(acc[k][0]);
-            normalize3(acc[k][1]);
-            u64 *o = A + (size_t)g->out_idx[job0 + k] * N + col;
-            o[0] = reduce3(acc[k][0], m);
-            o[LN] = reduce3(acc[k][1], m);
+        for (int k = 0; k < G; k++) max_terms = max(max_terms, __ldg(&g->nterms[job0 + k]));
+        const u32 col0 = tile * kStreamCols;
+        const DMod m = c.q[col0 / N];
+        Acc3 acc[G][2];
+#pragma unroll
+        for (int k = 0; k < G; k++) acc[k][0] = acc[k][1] = Acc3{ 0, 0, 0 };
+        if (__ldg(&g->pad_) != 0)
+            stream_consume<G, true>(g, job0, max_terms, it, ring, full, empty, acc, m, norm_pairs, reduce_period);
+        else
+            stream_consume<G, false>(g, job0, max_terms, it, ring, full, empty, acc, m, norm_pairs, reduce_period);
+        const u32 col = col0 + tid;
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            if (job0 + k < njobs) {
+                normalize3(acc[k][0]);
+                normalize3(acc[k][1]);
+                u64 *o = A + (size_t)__ldg(&g->out_idx[job0 + k]) * N + col;
+                o[0] = reduce3(acc[k][0], m);
+                o[LN] = reduce3(acc[k][1], m);
+            }
         }
     }
 }

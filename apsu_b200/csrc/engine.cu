@@ -829,7 +829,9 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &gro
                     same &= js[k].nterms == js[i].nterms;
                     g.njobs++;
                 }
-                ((same && g.njobs == kMacJobs && g.max_terms > 0) ? uni : rag).push_back(g);
+                const bool uniform = same && g.njobs == kMacJobs && g.max_terms > 0;
+                g.pad_ = uniform ? 0 : 1; // ragged marker read by the kernel
+                (uniform ? uni : rag).push_back(g);
             }
         }
         n_uniform = (uint32_t)uni.size();
@@ -847,9 +849,13 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &gro
     int b = 0;
     for (uint32_t j = 0; j < L; j++) b = std::max(b, hm::bit_length(ctx.params.coeff_modulus[j]));
     if (b > 61) throw std::invalid_argument("coeff_modulus primes must have at most 61 bits");
-    const uint32_t norm_period = (uint32_t)std::min<uint64_t>(15, (1ull << (63 - b)) - 1);
+    // lane capacities in TERMS: ll < 2^30 + T*2^60, mid < 2^35 + 2T*2^b, hh < T*2^(2b-60) (+carries); the
+    // kernel consumes terms in pairs
+    const uint64_t norm_terms = std::min<uint64_t>(15, (1ull << (63 - b)) - 1);
+    const uint32_t norm_period = (uint32_t)std::max<uint64_t>(1, norm_terms / 2); // in term pairs
     const uint64_t hh_terms = 124 - 2 * b >= 31 ? 0x7FFFFFFFull : ((1ull << (124 - 2 * b)) - 1);
-    const uint32_t reduce_period = (uint32_t)std::max<uint64_t>(1, (hh_terms / norm_period > 1 ? hh_terms / norm_period - 1 : 1));
+    const uint64_t per_norm = 2ull * norm_period;
+    const uint32_t reduce_period = (uint32_t)std::max<uint64_t>(1, (hh_terms / per_norm > 1 ? hh_terms / per_norm - 1 : 1));
     const uint32_t lazy_bound = 128 - 2 * b >= 31 ? 0x7FFFFFFFu : (1u << (128 - 2 * b));
     const char *sel = std::getenv("APSU_B200_MAC");
     const bool use_tma = !(sel && std::string(sel) == "v1");
@@ -870,22 +876,24 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &gro
         }
         const MacGroup *gd = reinterpret_cast<const MacGroup *>(desc_dev_.p + off);
         if (use_tma) {
-            // groups [0, n_uniform) are full and equal-length (branch-free kernel), the rest ragged
-            auto launch = [&](auto kern, size_t smem, int G, const MacGroup *first, uint32_t count) {
-                if (!count) return;
+            // one persistent launch over all groups (uniform ones first; ragged groups carry pad_ = 1)
+            auto launch = [&](auto kern, size_t smem, int min_blocks) {
                 APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<dim3(L * ctx.N / kStreamCols, count, kMacJobs / G), kStreamThreads, smem, ctx.stream>>>(
-                    arena_.buf.p, first, ctx.level[L], (int)ctx.N, norm_period, reduce_period);
+                int per_sm = 0;
+                APSU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStreamThreads, smem));
+                per_sm = std::max(1, std::min(per_sm, min_blocks));
+                int sms = 0;
+                APSU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device));
+                uint32_t items = n * (kMacJobs / mac_g) * (L * ctx.N / kStreamCols);
+                uint32_t grid = std::min<uint32_t>(items, (uint32_t)(sms * per_sm));
+                kern<<<grid, kStreamThreads, smem, ctx.stream>>>(arena_.buf.p, gd, n, ctx.level[L], (int)ctx.N, norm_period, reduce_period);
                 APSU_CUDA_CHECK(cudaGetLastError());
                 ctx.launches++;
             };
-            if (mac_g == 4) {
-                launch(k_db_mac_tma<4, false>, StreamCfg<4>::smem_bytes, 4, gd, n_uniform);
-                launch(k_db_mac_tma<4, true>, StreamCfg<4>::smem_bytes, 4, gd + n_uniform, n - n_uniform);
-            } else {
-                launch(k_db_mac_tma<8, false>, StreamCfg<8>::smem_bytes, 8, gd, n_uniform);
-                launch(k_db_mac_tma<8, true>, StreamCfg<8>::smem_bytes, 8, gd + n_uniform, n - n_uniform);
-            }
+            if (mac_g == 4)
+                launch(k_db_mac_tma<4>, StreamCfg<4>::smem_bytes, 4);
+            else
+                launch(k_db_mac_tma<8>, StreamCfg<8>::smem_bytes, 3);
             ctx.launches--; // the common epilogue below counts one
         } else {
             k_db_mac<<<dim3(L * ctx.N / kMacThreads, n), kMacThreads, 0, ctx.stream>>>(arena_.buf.p, gd, ctx.level[L], (int)ctx.N, lazy_bound);
