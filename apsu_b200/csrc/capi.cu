@@ -208,9 +208,13 @@ int apsu_b200_db_binbundle_coeff(const apsu_b200_ctx *ctx, uint32_t bundle_idx, 
         if (e.is_ntt_degree(k)) {
             if (num_primes) *num_primes = Ll;
             if (out) {
-                APSU_CUDA_CHECK(cudaMemcpy(out, s.ntt_coeffs.p + (size_t)rank * Ll * N, (size_t)Ll * N * 8, cudaMemcpyDeviceToHost));
-                // device words are stored split at bit 30 (db_stream.cuh); hand back plain residues
-                for (size_t i = 0; i < (size_t)Ll * N; i++) out[i] = (out[i] & 0xFFFFFFFFull) | ((out[i] >> 32) << 30);
+                // device plaintexts are tile-major ([Ll*N/128][n_ntt][128]) and split (db_stream.cuh); hand back
+                // plain residues in the standard [Ll][N] order
+                const size_t row_bytes = 128 * sizeof(uint64_t);
+                APSU_CUDA_CHECK(cudaMemcpy2D(out, row_bytes, s.ntt_coeffs.p + (size_t)rank * 128, (size_t)s.n_ntt * row_bytes, row_bytes, (size_t)Ll * N / 128,
+                                             cudaMemcpyDeviceToHost));
+                const int sp = e.db_split();
+                for (size_t i = 0; i < (size_t)Ll * N; i++) out[i] = (out[i] & 0xFFFFFFFFull) | ((out[i] >> 32) << sp);
             }
         } else {
             if (num_primes) *num_primes = 0;

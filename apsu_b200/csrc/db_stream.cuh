@@ -1,33 +1,57 @@
 // K1 — the DB stream: out_g = sum_j power_j ⊙ plaintext_{g,j} over NTT-form plaintexts resident in HBM
 // (BatchedPlaintextPolyn::eval / eval_patstock inner loops, receiver/apsu/bin_bundle.cpp:142-149, 251-265,
-// 280-294).  This is the HBM-bound kernel of the path; everything about it is shaped by that:
+// 280-294, 328-337).  This is the HBM-bound kernel of the path.  Measured facts that shape it (tools/lab,
+// profiles/lab_r01_*.log, B200):
 //
-//  * operands reach the SM through TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a 4-stage
-//    shared-memory ring signalled by mbarriers, issued by one producer warp — the amount of HBM traffic
-//    in flight is set by the ring depth, not by registers or occupancy;
+//  * a pure read of the DB reaches 7.2 TB/s, and a bulk-copy ring with the MACs removed 6.9-7.0 TB/s: the
+//    copy pipeline is not the limit, the integer work is;
+//  * IMAD.WIDE.U32 (32x32+64) issues at 32 lanes/clk/SM (quarter rate).  A 64x64 product from four of them
+//    caps the kernel at 9.3 TB/s with a perfectly busy pipe and reached 3.8-4.6 TB/s in practice.  The MAC is
+//    therefore done Karatsuba-style with THREE products per word and component: operands are split at bit
+//    s = ceil(bits/2) into (lo, hi); lanes ll += wl*pl, hh += wh*ph, kk += (wl+wh)*(pl+ph) are plain 64-bit
+//    sums and  sum w*p = ll + (kk - ll - hh)*2^s + hh*2^2s  is rebuilt and Barrett-reduced once per output
+//    (canonical residue => identical to the reference's multiply_plain + add_inplace term by term);
+//  * every product must be ONE instruction: `mad.lo.cc.u32` + `madc.hi.u32` on the two halves of a lane is
+//    what ptxas turns into a single IMAD.WIDE.U32 with the 64-bit addend (`mad.wide.u32` and plain C are
+//    split into IMAD.WIDE + IADD3 + IADD3.X);
+//  * operands reach the SM through TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a shared-memory ring
+//    signalled by mbarriers, issued by one producer warp.  The DB and the powers are stored TILE-MAJOR
+//    ([128-column tile][term][128 words], words already split) so that the four terms of a stage are ONE 4 KB
+//    copy per job and one 8 KB copy for the powers: 5 bulk copies per 24 KB stage instead of 24 (row-major
+//    1 KB copies cost 15 %);
 //  * plaintext tiles carry an L2 evict_first policy (each byte is read exactly once per query), the
 //    ciphertext powers evict_last (re-read by every group of the same bundle index);
-//  * one CTA = G accumulation jobs sharing the two power words of each term;
-//  * B200 has no 64x64 multiplier: a 128-bit multiply-accumulate done with mul.lo/mul.hi costs ~15
-//    instructions and would make the kernel issue-bound at about the HBM rate.  Both operands are split
-//    at bit 30 instead and the four 32x32->64 partial products are summed into three 64-bit lanes
-//    (weights 2^0, 2^30, 2^60) with IMAD.WIDE and no carry chains between lanes; lanes are renormalised
-//    every `norm_period` terms and the residue is produced once per output with one Barrett reduction.
-//    Canonical outputs => identical to multiply_plain + add_inplace term by term;
-//  * the DB stores every NTT-form plaintext word already split ("packed": low 30 bits in the low half,
-//    the rest in the high half of the 64-bit word), so the split costs no instructions in the stream.
+//  * one CTA = four accumulation jobs sharing the power words; 2 CTAs/SM with 4 x 24 KB stages each.
 #pragma once
 #include "device_ctx.hpp"
 #include "eval_kernels.cuh"
 
 namespace apsu_b200 {
 
-constexpr int kStreamCols = 128;                    // coefficients per CTA tile
-constexpr int kStreamStages = 4;
-constexpr int kStreamConsumerWarps = kStreamCols / 32;
-constexpr int kStreamThreads = kStreamCols + 32;    // consumers + one producer warp
-constexpr int kStreamTileBytes = kStreamCols * 8;
+constexpr int kKtCols = 128;   // coefficients per tile
+constexpr int kKtTS = 4;       // terms per ring stage
+constexpr int kKtG = 4;        // jobs per group (share every ciphertext-power load)
+constexpr int kKtThreads = kKtCols + 32; // 4 consumer warps + one producer warp
+constexpr int kKtStageWords = kKtTS * (2 + kKtG) * kKtCols; // [P: TS*2 tiles][W job 0: TS tiles] .. [W job G-1]
+constexpr size_t kt_smem_bytes(int stages) { return (size_t)stages * kKtStageWords * 8 + 2 * stages * 8 + 16; }
+// launch shape used by the engine: 4 stages x 24 KB, 2 CTAs/SM (tools/lab: 6.4 TB/s; 3 stages x 3 CTAs 6.2)
+constexpr int kKtStages = 4;
+constexpr int kKtCtasPerSm = 2;
 
+// One group = up to kKtG accumulation jobs over the same ciphertext powers (power j+1 multiplies term j).
+// job k: out_k[c][l][n] = sum_{j < nterms_k} power_j[c][l][n] * w_k[j][l][n]   (mod q_l)
+struct KtGroup {
+    const u64 *w[kKtG];  // tile-major split plaintexts: word (tile, term, col) at w[k] + ((size_t)tile*wstride[k] + term)*128 + col
+    u32 wstride[kKtG];   // plaintext rows per tile in the buffer job k reads
+    u32 nterms[kKtG];
+    u32 out_idx[kKtG];   // arena index of [2][L][N]
+    u32 p_idx;           // arena index of the tile-major split power table: (tile, term, comp, col) at
+                         // A + p_idx*N + (((size_t)tile*pstride + term)*2 + comp)*128 + col
+    u32 pstride;         // terms per tile in the power table
+    u32 njobs;
+    u32 max_terms;
+    u32 ragged;          // jobs of different length (or fewer than kKtG jobs)
+};
 
 __device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
@@ -76,240 +100,246 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, 
                  : "memory");
 }
 
-// three 64-bit lanes of weight 2^0, 2^30, 2^60
-struct Acc3 {
-    u64 ll, mid, hh;
+// Karatsuba lanes of one accumulator
+struct AccK {
+    u64 ll, kk, hh;
 };
-__device__ __forceinline__ void mac3(Acc3 &a, u32 wl, u32 wh, u32 pl, u32 ph)
+// lane += x*y as ONE IMAD.WIDE.U32 with the 64-bit addend (see the header comment)
+__device__ __forceinline__ void madw(u64 &lane, u32 x, u32 y)
 {
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.ll) : "r"(wl), "r"(pl));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(wl), "r"(ph));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(wh), "r"(pl));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.hh) : "r"(wh), "r"(ph));
+    u32 lo = (u32)lane, hi = (u32)(lane >> 32);
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+        "madc.hi.u32 %1, %2, %3, %1;"
+        : "+r"(lo), "+r"(hi)
+        : "r"(x), "r"(y));
+    lane = ((u64)hi << 32) | lo;
 }
-__device__ __forceinline__ void normalize3(Acc3 &a)
+__device__ __forceinline__ void mac_k(AccK &a, u32 wl, u32 wh, u32 ws, u32 pl, u32 ph, u32 ps)
 {
-    a.mid += a.ll >> 30;
-    a.ll &= 0x3FFFFFFFull;
-    a.hh += a.mid >> 30;
-    a.mid &= 0x3FFFFFFFull;
+    madw(a.ll, wl, pl);
+    madw(a.kk, ws, ps);
+    madw(a.hh, wh, ph);
 }
-// value of the three lanes modulo q (lanes normalised, total < 2^128)
-__device__ __forceinline__ u64 reduce3(const Acc3 &a, const DMod &m)
+// value of the lanes modulo q (canonical)
+__device__ __forceinline__ u64 reduce_k(const AccK &a, const DMod &m, int s)
 {
+    const u64 mid = a.kk - a.ll - a.hh;
     u64 lo = a.ll, hi = 0;
-    u64 t = a.mid << 30;
+    u64 t = mid << s;
     lo += t;
-    hi += (a.mid >> 34) + (lo < t);
-    t = a.hh << 60;
+    hi += (mid >> (64 - s)) + (lo < t);
+    t = a.hh << (2 * s);
     lo += t;
-    hi += (a.hh >> 4) + (lo < t);
+    hi += (a.hh >> (64 - 2 * s)) + (lo < t);
     return barrett128(lo, hi, m);
 }
+// replaces the lanes by the ones of the reduced value (keeps the 64-bit lanes from overflowing on long sums)
+__device__ __forceinline__ void fold_k(AccK &a, const DMod &m, int s)
+{
+    const u64 r = reduce_k(a, m, s);
+    const u64 lo = r & ((1ull << s) - 1), hi = r >> s;
+    a.ll = lo;
+    a.hh = 0;
+    a.kk = lo + hi; // mid = kk - ll - hh = hi
+}
 
-// a stage holds TWO consecutive terms: [term a: p0 | p1 | w_0..w_{G-1}] [term b: same]
-template <int G>
-struct StreamCfg {
-    static constexpr int term_words = (2 + G) * kStreamCols;
-    static constexpr int stage_words = 2 * term_words;
-    static constexpr size_t smem_bytes = (size_t)kStreamStages * stage_words * 8 + 2 * kStreamStages * 8 + 16;
+// one ring stage in registers
+struct KtRegs {
+    u64 p[kKtTS][2], w[kKtG][kKtTS];
 };
-
-// two terms into one accumulator.  The MACs of a lane are adjacent so that ptxas folds each pair of
-// products into one IADD3 / IADD3.X (three-input adds with two carries): 4 add instructions per MAC
-// instead of 6 (the compiler never keeps the 64-bit addend inside IMAD.WIDE on sm_100a).
-__device__ __forceinline__ void mac3x2(Acc3 &a, u32 wla, u32 wha, u32 pla, u32 pha, u32 wlb, u32 whb, u32 plb, u32 phb)
+__device__ __forceinline__ void kt_load(KtRegs &r, const u64 *sb)
 {
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.ll) : "r"(wla), "r"(pla));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.ll) : "r"(wlb), "r"(plb));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(wla), "r"(pha));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(wha), "r"(pla));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(wlb), "r"(phb));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(whb), "r"(plb));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.hh) : "r"(wha), "r"(pha));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.hh) : "r"(whb), "r"(phb));
-}
-
-// consumer side of one work item: all term pairs of G jobs on one 128-coefficient tile
-template <int G, bool RAGGED>
-__device__ __forceinline__ void stream_consume(const MacGroup *__restrict__ g, int job0, u32 max_terms, u32 &it, u64 *ring, u64 *full,
-                                               u64 *empty, Acc3 (&acc)[G][2], const DMod &m, u32 norm_pairs, u32 reduce_period)
-{
-    using Cfg = StreamCfg<G>;
-    const int tid = threadIdx.x;
-    const u32 npairs = (max_terms + 1) / 2;
-    u32 since_norm = 0, since_reduce = 0;
-    u32 nt[G];
-    if (RAGGED) {
 #pragma unroll
-        for (int k = 0; k < G; k++) nt[k] = __ldg(&g->nterms[job0 + k]);
+    for (int h = 0; h < kKtTS; h++) {
+        r.p[h][0] = sb[(h * 2) * kKtCols];
+        r.p[h][1] = sb[(h * 2 + 1) * kKtCols];
+#pragma unroll
+        for (int k = 0; k < kKtG; k++) r.w[k][h] = sb[(kKtTS * 2 + k * kKtTS + h) * kKtCols];
     }
-    for (u32 jp = 0; jp < npairs; jp++, it++) {
-        const int s = it % kStreamStages;
-        mbar_wait(&full[s], (it / kStreamStages) & 1);
-        const u64 *sa = ring + (size_t)s * Cfg::stage_words + tid;
-        const u64 *sb = sa + Cfg::term_words;
-        const bool two = 2 * jp + 1 < max_terms; // uniform; an odd tail multiplies the (stale) b operands by zero
-        // copy the stage into registers and hand it back to the producer at once: the ring's job is to keep
-        // HBM requests in flight, so a stage must not stay occupied while the MACs run
-        const u64 p0a = sa[0], p1a = sa[kStreamCols], p0b = sb[0], p1b = sb[kStreamCols];
-        u64 wa[G], wb[G];
+}
+// MASKED: term t0+h of job k only counts while t0+h < nt[k] (ragged groups and the last, partial stage); the
+// shared-memory words of absent terms are stale and are multiplied by zero
+template <bool MASKED>
+__device__ __forceinline__ void kt_mac(const KtRegs &r, AccK (&acc)[kKtG][2], const u32 (&nt)[kKtG], u32 t0)
+{
 #pragma unroll
-        for (int k = 0; k < G; k++) {
-            wa[k] = sa[(2 + k) * kStreamCols]; // packed: halves are the limbs
-            wb[k] = sb[(2 + k) * kStreamCols];
-        }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty[s]);
-        const u32 p0al = (u32)p0a & 0x3FFFFFFFu, p0ah = (u32)(p0a >> 30), p1al = (u32)p1a & 0x3FFFFFFFu, p1ah = (u32)(p1a >> 30);
-        const u32 p0bl = (u32)p0b & 0x3FFFFFFFu, p0bh = (u32)(p0b >> 30), p1bl = (u32)p1b & 0x3FFFFFFFu, p1bh = (u32)(p1b >> 30);
+    for (int h = 0; h < kKtTS; h++) {
+        const u32 p0l = (u32)r.p[h][0], p0h = (u32)(r.p[h][0] >> 32), p1l = (u32)r.p[h][1], p1h = (u32)(r.p[h][1] >> 32);
+        const u32 p0s = p0l + p0h, p1s = p1l + p1h;
 #pragma unroll
-        for (int k = 0; k < G; k++) {
-            u64 a = wa[k], b = wb[k];
-            if (RAGGED) {
-                a = (2 * jp < nt[k]) ? a : 0ull; // stale tile of a finished job
-                b = (2 * jp + 1 < nt[k]) ? b : 0ull;
-            } else if (!two) {
-                b = 0ull;
-            }
-            const u32 wal = (u32)a, wah = (u32)(a >> 32), wbl = (u32)b, wbh = (u32)(b >> 32);
-            mac3x2(acc[k][0], wal, wah, p0al, p0ah, wbl, wbh, p0bl, p0bh);
-            mac3x2(acc[k][1], wal, wah, p1al, p1ah, wbl, wbh, p1bl, p1bh);
-        }
-        if (++since_norm == norm_pairs) {
-            since_norm = 0;
-#pragma unroll
-            for (int k = 0; k < G; k++) {
-                normalize3(acc[k][0]);
-                normalize3(acc[k][1]);
-            }
-            if (++since_reduce == reduce_period) { // only for primes above 57 bits
-                since_reduce = 0;
-#pragma unroll
-                for (int k = 0; k < G; k++)
-                    for (int cc = 0; cc < 2; cc++) {
-                        u64 r = reduce3(acc[k][cc], m);
-                        acc[k][cc] = Acc3{ r & 0x3FFFFFFFull, r >> 30, 0 };
-                    }
-            }
+        for (int k = 0; k < kKtG; k++) {
+            u64 w = r.w[k][h];
+            if (MASKED) w = (t0 + h < nt[k]) ? w : 0ull;
+            const u32 wl = (u32)w, wh = (u32)(w >> 32), ws = wl + wh;
+            mac_k(acc[k][0], wl, wh, ws, p0l, p0h, p0s);
+            mac_k(acc[k][1], wl, wh, ws, p1l, p1h, p1s);
         }
     }
 }
 
-// Persistent kernel: grid = SMs x resident CTAs, block 160 (4 consumer warps + 1 producer warp).  Work item =
-// (group, slice of G jobs, 128-coefficient tile); a CTA walks items blockIdx.x, +gridDim.x, ... with tiles
-// fastest, so the CTAs running at any moment read neighbouring memory and the TMA ring never drains between
-// items (the producer prefetches the next item while the consumers reduce and store the current one).
-// MacGroup::pad_ != 0 marks a ragged group (jobs of different length).
-// norm_pairs = term PAIRS between lane renormalisations, reduce_period = renormalisations between full
-// reductions; both depend only on the bit size of the largest prime (host computes them).
-template <int G>
-__global__ void __launch_bounds__(kStreamThreads, (G == 4 ? 4 : 3))
-k_db_mac_tma(u64 *A, const MacGroup *__restrict__ groups, u32 n_groups, LevelConsts c, int N, u32 norm_pairs, u32 reduce_period)
+// Persistent kernel: grid = SMs x CTAs/SM, block 160 (4 consumer warps + 1 producer warp).  Work item =
+// (group, 128-coefficient tile); a CTA walks items blockIdx.x, +gridDim.x, ... with tiles fastest and the
+// ring never drains between items (the producer prefetches the next item while the consumers reduce and
+// store the current one).
+// split = bit position the operands were split at; fold_stages = ring stages between lane folds (host:
+// largest count for which the kk lane cannot overflow, from the bit size of the largest prime).
+template <int STAGES, int MINB>
+__global__ void __launch_bounds__(kKtThreads, MINB)
+k_db_mac_kt(u64 *A, const KtGroup *__restrict__ groups, u32 n_groups, LevelConsts c, int N, int split, u32 fold_stages)
 {
-    using Cfg = StreamCfg<G>;
     extern __shared__ __align__(128) u64 smem[];
-    u64 *ring = smem;                                     // [stage][2][2+G][128]
-    u64 *full = smem + kStreamStages * Cfg::stage_words;  // [stage]
-    u64 *empty = full + kStreamStages;                    // [stage]
+    u64 *ring = smem;                              // [stage][kKtStageWords]
+    u64 *full = smem + STAGES * kKtStageWords;     // [stage]
+    u64 *empty = full + STAGES;                    // [stage]
 
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int s = 0; s < kStreamStages; s++) {
+        for (int s = 0; s < STAGES; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kStreamConsumerWarps);
+            mbar_init(&empty[s], kKtCols / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    constexpr u32 slices = kMacJobs / G;
-    const u32 n_tiles = (u32)c.L * N / kStreamCols;
-    const u32 n_items = n_groups * slices * n_tiles;
+    const u32 n_tiles = (u32)c.L * N / kKtCols;
+    const u32 n_items = n_groups * n_tiles;
     const size_t LN = (size_t)c.L * N;
     u32 it = 0; // stage counter, runs across work items identically in the producer and the consumers
 
-    if (tid >= kStreamCols) {
+    if (tid >= kKtCols) {
         // ---------------- producer warp ----------------
-        if (tid != kStreamCols) return;
+        if (tid != kKtCols) return;
         const u64 pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
         for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const u32 tile = item % n_tiles, rest = item / n_tiles;
-            const MacGroup *g = &groups[rest / slices];
-            const int job0 = (int)(rest % slices) * G;
-            if (job0 >= (int)g->njobs) continue;
-            u32 nt[G], max_terms = 0;
-            const u64 *cf[G];
-            for (int k = 0; k < G; k++) {
-                nt[k] = g->nterms[job0 + k];
-                cf[k] = g->coeff[job0 + k];
-                max_terms = max(max_terms, nt[k]);
+            const u32 tile = item % n_tiles;
+            const KtGroup *g = &groups[item / n_tiles];
+            const u32 max_terms = g->max_terms;
+            u32 nt[kKtG];
+            const u64 *wk[kKtG];
+#pragma unroll
+            for (int k = 0; k < kKtG; k++) {
+                nt[k] = g->nterms[k];
+                wk[k] = g->w[k] + (size_t)tile * g->wstride[k] * kKtCols;
             }
-            const bool ragged = g->pad_ != 0;
-            const u32 col0 = tile * kStreamCols;
-            const u64 *pw = A + (size_t)g->pow_idx * N + col0;
-            const size_t tstride = (size_t)g->pow_term_stride * N, cstride = (size_t)g->pow_comp_stride * N;
-            const u32 npairs = (max_terms + 1) / 2;
-            for (u32 jp = 0; jp < npairs; jp++, it++) {
-                const int s = it % kStreamStages;
-                const u32 use = it / kStreamStages;
+            const u64 *pk = A + (size_t)g->p_idx * N + (size_t)tile * g->pstride * 2 * kKtCols;
+            const u32 nst = (max_terms + kKtTS - 1) / kKtTS;
+            for (u32 st = 0; st < nst; st++, it++) {
+                const int s = it % STAGES;
+                const u32 use = it / STAGES;
                 if (use) mbar_wait(&empty[s], (use - 1) & 1);
-                const u32 nt2 = (2 * jp + 1 < max_terms) ? 2u : 1u;
-                u32 tiles = 2 * nt2;
-                for (u32 h = 0; h < nt2; h++)
-                    for (int k = 0; k < G; k++) tiles += (!ragged || 2 * jp + h < nt[k]);
-                mbar_expect_tx(&full[s], tiles * kStreamTileBytes);
-                for (u32 h = 0; h < nt2; h++) {
-                    const u32 j = 2 * jp + h;
-                    u64 *st = ring + (size_t)s * Cfg::stage_words + (size_t)h * Cfg::term_words;
-                    bulk_g2s(st, pw + j * tstride, kStreamTileBytes, &full[s], pol_keep);
-                    bulk_g2s(st + kStreamCols, pw + j * tstride + cstride, kStreamTileBytes, &full[s], pol_keep);
-                    for (int k = 0; k < G; k++)
-                        if (!ragged || j < nt[k]) bulk_g2s(st + (2 + k) * kStreamCols, cf[k] + j * LN + col0, kStreamTileBytes, &full[s], pol_stream);
+                const u32 t0 = st * kKtTS;
+                const u32 ntp = min((u32)kKtTS, max_terms - t0);
+                u32 nk[kKtG], rows = 2 * ntp;
+#pragma unroll
+                for (int k = 0; k < kKtG; k++) {
+                    nk[k] = nt[k] > t0 ? min((u32)kKtTS, nt[k] - t0) : 0u;
+                    rows += nk[k];
                 }
+                mbar_expect_tx(&full[s], rows * kKtCols * 8);
+                u64 *sb = ring + (size_t)s * kKtStageWords;
+                bulk_g2s(sb, pk + (size_t)t0 * 2 * kKtCols, ntp * 2 * kKtCols * 8, &full[s], pol_keep);
+#pragma unroll
+                for (int k = 0; k < kKtG; k++)
+                    if (nk[k]) bulk_g2s(sb + (kKtTS * 2 + k * kKtTS) * kKtCols, wk[k] + (size_t)t0 * kKtCols, nk[k] * kKtCols * 8, &full[s], pol_stream);
             }
         }
         return;
     }
 
     // ---------------- consumer warps: one (prime, coefficient) column per thread ----------------
+    const bool lane0 = (tid & 31) == 0;
     for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const u32 tile = item % n_tiles, rest = item / n_tiles;
-        const MacGroup *g = &groups[rest / slices];
-        const int job0 = (int)(rest % slices) * G;
-        const int njobs = (int)__ldg(&g->njobs);
-        if (job0 >= njobs) continue;
-        u32 max_terms = 0;
+        const u32 tile = item % n_tiles;
+        const KtGroup *g = &groups[item / n_tiles];
+        const u32 max_terms = __ldg(&g->max_terms);
+        const bool ragged = __ldg(&g->ragged) != 0;
+        u32 nt[kKtG];
 #pragma unroll
-        for (int k = 0; k < G; k++) max_terms = max(max_terms, __ldg(&g->nterms[job0 + k]));
-        const u32 col0 = tile * kStreamCols;
+        for (int k = 0; k < kKtG; k++) nt[k] = __ldg(&g->nterms[k]);
+        const u32 col0 = tile * kKtCols;
         const DMod m = c.q[col0 / N];
-        Acc3 acc[G][2];
+        AccK acc[kKtG][2];
 #pragma unroll
-        for (int k = 0; k < G; k++) acc[k][0] = acc[k][1] = Acc3{ 0, 0, 0 };
-        if (__ldg(&g->pad_) != 0)
-            stream_consume<G, true>(g, job0, max_terms, it, ring, full, empty, acc, m, norm_pairs, reduce_period);
-        else
-            stream_consume<G, false>(g, job0, max_terms, it, ring, full, empty, acc, m, norm_pairs, reduce_period);
+        for (int k = 0; k < kKtG; k++) acc[k][0] = acc[k][1] = AccK{ 0, 0, 0 };
+        const u32 nst = (max_terms + kKtTS - 1) / kKtTS;
+        const u32 nst_plain = ragged ? 0u : max_terms / kKtTS; // stages whose terms all exist for all jobs
+        // stages run in blocks of at most fold_stages; the lanes are folded between blocks (never inside the
+        // hot loop: for the reference's parameter sets a whole inner polynomial fits one block)
+        for (u32 b0 = 0; b0 < nst; b0 += fold_stages) {
+            const u32 b1 = min(nst, b0 + fold_stages), p1 = min(b1, max(nst_plain, b0));
+            // unrolled by two: ptxas leaves the accumulators of the fused IMAD.WIDE chain in different
+            // registers than they started in, and the moves that repair that are per loop trip, not per stage
+#pragma unroll 2
+            for (u32 st = b0; st < p1; st++, it++) {
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (it / STAGES) & 1);
+                KtRegs r;
+                kt_load(r, ring + (size_t)s * kKtStageWords + tid);
+                __syncwarp();
+                if (lane0) mbar_arrive(&empty[s]); // the stage is in registers: hand it back before the MACs
+                kt_mac<false>(r, acc, nt, 0);
+            }
+#pragma unroll 1
+            for (u32 st = p1; st < b1; st++, it++) {
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (it / STAGES) & 1);
+                KtRegs r;
+                kt_load(r, ring + (size_t)s * kKtStageWords + tid);
+                __syncwarp();
+                if (lane0) mbar_arrive(&empty[s]);
+                kt_mac<true>(r, acc, nt, st * kKtTS);
+            }
+            if (b1 < nst) {
+#pragma unroll
+                for (int k = 0; k < kKtG; k++) {
+                    fold_k(acc[k][0], m, split);
+                    fold_k(acc[k][1], m, split);
+                }
+            }
+        }
+        const u32 njobs = __ldg(&g->njobs);
         const u32 col = col0 + tid;
 #pragma unroll
-        for (int k = 0; k < G; k++) {
-            if (job0 + k < njobs) {
-                normalize3(acc[k][0]);
-                normalize3(acc[k][1]);
-                u64 *o = A + (size_t)__ldg(&g->out_idx[job0 + k]) * N + col;
-                o[0] = reduce3(acc[k][0], m);
-                o[LN] = reduce3(acc[k][1], m);
+        for (int k = 0; k < kKtG; k++) {
+            if ((u32)k < njobs) {
+                u64 *o = A + (size_t)__ldg(&g->out_idx[k]) * N + col;
+                o[0] = reduce_k(acc[k][0], m, split);
+                o[LN] = reduce_k(acc[k][1], m, split);
             }
         }
     }
 }
 
-// in-place conversion of DB plaintext words to / from the packed form
-__global__ void k_pack30(u64 *__restrict__ data, size_t count, int unpack)
+// ---- layout kernels ----
+// standard [rows][L*N] -> tile-major split [L*N/128][rows][128].  grid (L*N/128, ceil(rows/8)), block 128 x 8 rows
+__global__ void __launch_bounds__(128) k_pack_tile(const u64 *__restrict__ src, u64 *__restrict__ dst, u32 rows, u32 LN, int split)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) data[i] = unpack ? unpack30_word(data[i]) : pack30_word(data[i]);
+    const u32 tile = blockIdx.x, c = threadIdx.x;
+    const u32 r0 = blockIdx.y * 8;
+#pragma unroll
+    for (u32 r = r0; r < r0 + 8; r++)
+        if (r < rows) dst[((size_t)tile * rows + r) * kKtCols + c] = split_word(src[(size_t)r * LN + (size_t)tile * kKtCols + c], split);
+}
+// inverse of k_pack_tile (DB read-back)
+__global__ void __launch_bounds__(128) k_unpack_tile(const u64 *__restrict__ src, u64 *__restrict__ dst, u32 rows, u32 LN, int split)
+{
+    const u32 tile = blockIdx.x, c = threadIdx.x;
+    const u32 r0 = blockIdx.y * 8;
+#pragma unroll
+    for (u32 r = r0; r < r0 + 8; r++)
+        if (r < rows) dst[(size_t)r * LN + (size_t)tile * kKtCols + c] = unsplit_word(src[((size_t)tile * rows + r) * kKtCols + c], split);
+}
+// ciphertext powers from the arena into the tile-major split table one bundle index streams against:
+// dst[((tile*T + t)*2 + comp)*128 + c] = split(A[(src[t*2+comp] + l)*N + n]),  l*N + n = tile*128 + c.
+// src[t*2+comp] = arena index of prime 0 of component comp of term t (its L primes are consecutive polynomials).
+// grid (L*N/128, T*2, tables), block 128; table z: sources src[z*T*2 ..], destination arena index dst_idx[z]
+__global__ void __launch_bounds__(128) k_pack_powers(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst_idx, u32 T, int N, int split)
+{
+    const u32 tile = blockIdx.x, tc = blockIdx.y, z = blockIdx.z, c = threadIdx.x;
+    const size_t col = (size_t)tile * kKtCols + c; // l*N + n: consecutive primes are consecutive polynomials
+    u64 *dst = A + (size_t)dst_idx[z] * N;
+    dst[((size_t)tile * T * 2 + tc) * kKtCols + c] = split_word(A[(size_t)src[(size_t)z * T * 2 + tc] * N + col], split);
 }
 
 } // namespace apsu_b200

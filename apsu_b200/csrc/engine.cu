@@ -172,6 +172,21 @@ struct ProgramBuilder {
         step([=] { en->run_mod_switch_next(L, n, en->idx_.at(so), en->idx_.at(dn)); });
     }
 
+    // tile-major split power tables (k_pack_powers): table z gathers T*2 (term, component) sources
+    void pack_powers(uint32_t L, uint32_t T, const std::vector<uint32_t> &src, const std::vector<uint32_t> &dst)
+    {
+        if (dst.empty() || !T) return;
+        size_t so = idx.add(src), dn = idx.add(dst);
+        uint32_t nz = (uint32_t)dst.size();
+        Engine *en = &e;
+        step([=] {
+            k_pack_powers<<<dim3(L * en->ctx.N / kKtCols, T * 2, nz), kKtCols, 0, en->ctx.stream>>>(en->arena_.buf.p, en->idx_.at(so), en->idx_.at(dn), T,
+                                                                                                  (int)en->ctx.N, en->split_);
+            APSU_CUDA_CHECK(cudaGetLastError());
+            en->ctx.launches++;
+        });
+    }
+
     // dst[k] = sum of the RNS polynomials ([L][N]) listed in terms[k]
     void sum_polys(uint32_t L, const std::vector<std::vector<uint32_t>> &terms, const std::vector<uint32_t> &dst)
     {
@@ -206,6 +221,21 @@ Engine::Engine(const apsu_b200_params &p, int device) : ctx(p, device)
     if (dag.depth() > 0 && !ctx.using_keyswitching())
         throw std::invalid_argument("parameters need ciphertext multiplications but provide no key-switching prime");
     db.resize(p.bundle_idx_count);
+    {
+        // DB-stream operand split and lane-fold period (db_stream.cuh) from the largest data prime
+        int b = 0;
+        const uint32_t ndata = ctx.K > 1 ? ctx.K - 1 : 1;
+        for (uint32_t j = 0; j < ndata; j++) b = std::max(b, hm::bit_length(p.coeff_modulus[j]));
+        if (b > 60) throw std::invalid_argument("coeff_modulus primes must have at most 60 bits");
+        split_ = std::max(1, (b + 1) / 2);
+        const unsigned __int128 one = 1;
+        const unsigned __int128 sum_max = ((one << split_) - 1) + ((one << std::max(0, b - split_)) - 1);
+        const unsigned __int128 prod_max = sum_max * sum_max;
+        const unsigned __int128 room = ((one << 64) - 1) - (one << (split_ + 1));
+        const unsigned __int128 cap = prod_max ? room / prod_max : room; // terms the kk lane can take after a fold
+        if (cap < (unsigned)kKtTS) throw std::logic_error("DB-stream lanes cannot hold one ring stage");
+        fold_stages_ = (uint32_t)std::min<unsigned __int128>(cap / kKtTS, 0x7FFFFFFFu);
+    }
     levels_dev_.upload(ctx.level, ctx.stream);
     for (auto &ev : ev_) APSU_CUDA_CHECK(cudaEventCreate(&ev));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
@@ -250,10 +280,12 @@ void Engine::prepare_plain_high(BinBundleStore &s)
     if (!ctx.params.ps_low_degree || s.n_plain <= 1) return;
     uint32_t cnt = s.n_plain - 1;
     s.plain_high_ntt.alloc((size_t)cnt * Lh * N);
-    k_plain_lift<<<dim3(N / kEwThreads, Lh, cnt), kEwThreads, 0, ctx.stream>>>(s.plain_coeffs.p + N, s.plain_high_ntt.p, ctx.level[Lh], ctx.t, (int)N);
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream)); // the staging buffer may still feed an earlier pack
+    stage_.ensure((size_t)cnt * Lh * N);
+    k_plain_lift<<<dim3(N / kEwThreads, Lh, cnt), kEwThreads, 0, ctx.stream>>>(s.plain_coeffs.p + N, stage_.p, ctx.level[Lh], ctx.t, (int)N);
     APSU_LAUNCH_CHECK();
-    ctx.ntt(s.plain_high_ntt.p, s.plain_high_ntt.p, cnt * Lh, ctx.pattern_q(Lh), false);
-    pack_words(s.plain_high_ntt.p, s.plain_high_ntt.n);
+    ctx.ntt(stage_.p, stage_.p, cnt * Lh, ctx.pattern_q(Lh), false);
+    pack_tile(stage_.p, s.plain_high_ntt.p, cnt, Lh);
 }
 
 uint32_t Engine::add_binbundle(uint32_t bundle_idx, const uint64_t *const *coeffs, uint32_t ncoeffs)
@@ -270,14 +302,17 @@ uint32_t Engine::add_binbundle(uint32_t bundle_idx, const uint64_t *const *coeff
     s->ntt_coeffs.alloc((size_t)s->n_ntt * Ll * N);
     s->plain_coeffs.alloc((size_t)s->n_plain * N);
     uint32_t in = 0, ip = 0;
-    for (uint32_t k = 0; k < ncoeffs; k++) {
+    for (uint32_t k = 0; k < ncoeffs; k++)
         if (!coeffs[k]) throw std::invalid_argument("null plaintext pointer");
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    stage_.ensure((size_t)s->n_ntt * Ll * N);
+    for (uint32_t k = 0; k < ncoeffs; k++) {
         if (is_ntt_degree(k))
-            APSU_CUDA_CHECK(cudaMemcpyAsync(s->ntt_coeffs.p + (size_t)(in++) * Ll * N, coeffs[k], (size_t)Ll * N * 8, cudaMemcpyHostToDevice, ctx.stream));
+            APSU_CUDA_CHECK(cudaMemcpyAsync(stage_.p + (size_t)(in++) * Ll * N, coeffs[k], (size_t)Ll * N * 8, cudaMemcpyHostToDevice, ctx.stream));
         else
             APSU_CUDA_CHECK(cudaMemcpyAsync(s->plain_coeffs.p + (size_t)(ip++) * N, coeffs[k], (size_t)N * 8, cudaMemcpyHostToDevice, ctx.stream));
     }
-    pack_words(s->ntt_coeffs.p, s->ntt_coeffs.n);
+    pack_tile(stage_.p, s->ntt_coeffs.p, s->n_ntt, Ll);
     prepare_plain_high(*s);
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
     uint32_t ci = s->cache_idx;
@@ -286,11 +321,12 @@ uint32_t Engine::add_binbundle(uint32_t bundle_idx, const uint64_t *const *coeff
     return ci;
 }
 
-// NTT-form DB words live in the split ("packed") form the DB-stream kernel consumes (db_stream.cuh)
-void Engine::pack_words(u64 *data, size_t count)
+// NTT-form DB words live tile-major and split, the form the DB-stream kernel consumes (db_stream.cuh):
+// standard [rows][L][N] -> [L*N/128][rows][128]
+void Engine::pack_tile(const u64 *src, u64 *dst, uint32_t rows, uint32_t L)
 {
-    if (!count) return;
-    k_pack30<<<(unsigned)((count + 255) / 256), 256, 0, ctx.stream>>>(data, count, 0);
+    if (!rows) return;
+    k_pack_tile<<<dim3(L * ctx.N / kKtCols, (rows + 7) / 8), kKtCols, 0, ctx.stream>>>(src, dst, rows, L * ctx.N, split_);
     APSU_LAUNCH_CHECK();
 }
 
@@ -313,10 +349,10 @@ uint32_t Engine::add_binbundle_synthetic(uint32_t bundle_idx, uint32_t ncoeffs, 
     fm.L = (int)Ll;
     size_t cn = s->ntt_coeffs.n, cp = s->plain_coeffs.n;
     if (cn) {
-        k_fill_db<<<(unsigned)((cn + 255) / 256), 256, 0, ctx.stream>>>(s->ntt_coeffs.p, cn, seed, 0, ps ? ps + 1 : 0, fm, (int)N);
+        k_fill_db<<<(unsigned)((cn + 255) / 256), 256, 0, ctx.stream>>>(s->ntt_coeffs.p, cn, seed, 0, ps ? ps + 1 : 0, fm, (int)N, s->n_ntt, split_);
         APSU_LAUNCH_CHECK();
     }
-    k_fill_db<<<(unsigned)((cp + 255) / 256), 256, 0, ctx.stream>>>(s->plain_coeffs.p, cp, seed, 1, ps ? ps + 1 : 0, fm, (int)N);
+    k_fill_db<<<(unsigned)((cp + 255) / 256), 256, 0, ctx.stream>>>(s->plain_coeffs.p, cp, seed, 1, ps ? ps + 1 : 0, fm, (int)N, 0, split_);
     APSU_LAUNCH_CHECK();
     prepare_plain_high(*s);
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
@@ -439,12 +475,17 @@ void Engine::build_plan()
     // final powers as the evaluation reads them
     const uint32_t nlow = ps ? ps : maxp;          // powers 1..nlow in NTT form at the low level
     const uint32_t nhigh = ps ? maxp / h : 0;      // powers h, 2h, .. in coefficient form at the high level
-    std::vector<uint32_t> low_base(bic, kNoSrc), highext_base(bic, kNoSrc);
+    // LOWT / HIGHT: the same powers tile-major and split, the tables the DB-stream kernel reads (db_stream.cuh)
+    std::vector<uint32_t> low_base(bic, kNoSrc), highext_base(bic, kNoSrc), lowt_base(bic, kNoSrc), hight_base(bic, kNoSrc);
     std::vector<std::vector<uint32_t>> highc_loc(bic, std::vector<uint32_t>(nhigh + 1, kNoSrc));
     for (uint32_t b = 0; b < bic; b++) {
         if (!active[b]) continue;
         low_base[b] = arena_.take((size_t)nlow * 2 * Ll);
-        if (nhigh) highext_base[b] = arena_.take((size_t)nhigh * 2 * LSh);
+        lowt_base[b] = arena_.take((size_t)nlow * 2 * Ll);
+        if (nhigh) {
+            highext_base[b] = arena_.take((size_t)nhigh * 2 * LSh);
+            hight_base[b] = arena_.take((size_t)nhigh * 2 * Lh);
+        }
     }
     final_power_.assign(bic, std::vector<PowerLoc>(maxp + 1));
 
@@ -548,6 +589,21 @@ void Engine::build_plan()
         }
         pb.ntt(ntt_src, ntt_dst, ctx.pattern_q(Ll), false);
         pb.extend(Lh, hx_cts, hx_dst);
+        // tile-major split copies for the DB stream
+        {
+            std::vector<uint32_t> lsrc, ldst, hsrc, hdst;
+            for (uint32_t b = 0; b < bic; b++) {
+                if (!active[b]) continue;
+                ldst.push_back(lowt_base[b]);
+                for (uint32_t tc = 0; tc < nlow * 2; tc++) lsrc.push_back(low_base[b] + tc * Ll);
+                if (nhigh) {
+                    hdst.push_back(hight_base[b]);
+                    for (uint32_t tc = 0; tc < nhigh * 2; tc++) hsrc.push_back(highext_base[b] + tc * LSh);
+                }
+            }
+            pb.pack_powers(Ll, nlow, lsrc, ldst);
+            pb.pack_powers(Lh, nhigh, hsrc, hdst);
+        }
     }
     const uint32_t powers_top = (uint32_t)arena_.high_water;
     // coefficient-form high powers must survive for get_power(); keep eval scratch above the powers scratch
@@ -578,21 +634,19 @@ void Engine::build_plan()
         const uint32_t drops = Ll - Lh;
         if (drops > 1) throw std::logic_error("unexpected level gap between low and high powers");
 
-        auto add_job = [&](std::vector<MacGroup> &gs, uint32_t pow_idx, uint32_t tstride, uint32_t cstride, const u64 *coeff, uint32_t nterms, uint32_t out) {
-            if (gs.empty() || gs.back().njobs == kMacJobs || gs.back().pow_idx != pow_idx) {
-                MacGroup g;
-                std::memset(&g, 0, sizeof(g));
-                g.pow_idx = pow_idx;
-                g.pow_term_stride = tstride;
-                g.pow_comp_stride = cstride;
-                gs.push_back(g);
-            }
-            MacGroup &g = gs.back();
-            g.coeff[g.njobs] = coeff;
-            g.nterms[g.njobs] = nterms;
-            g.out_idx[g.njobs] = out;
-            g.njobs++;
-            g.max_terms = std::max(g.max_terms, nterms);
+        // one accumulation job; emit_mac regroups them (kKtG to a group, equal lengths together)
+        auto add_job = [&](std::vector<KtGroup> &gs, uint32_t p_idx, uint32_t pstride, const u64 *w, uint32_t wstride, uint32_t nterms, uint32_t out) {
+            KtGroup g;
+            std::memset(&g, 0, sizeof(g));
+            g.p_idx = p_idx;
+            g.pstride = pstride;
+            g.w[0] = w;
+            g.wstride[0] = wstride;
+            g.nterms[0] = nterms;
+            g.out_idx[0] = out;
+            g.njobs = 1;
+            g.max_terms = nterms;
+            gs.push_back(g);
         };
 
         // ===== stage A (whole DB, one launch): every NTT-domain accumulation job of every BinBundle =====
@@ -631,14 +685,14 @@ void Engine::build_plan()
         const uint32_t tin0 = arena_.take((size_t)nj_all * 2 * Ll);        // inner polynomials i >= 1
         const uint32_t r00 = arena_.take((size_t)nb_all * 2 * Ll);        // sum of the i = 0 terms
         const uint32_t stageA_count = (uint32_t)arena_.top - acc0;
-        std::vector<MacGroup> groups;
+        std::vector<KtGroup> groups;
         std::vector<FinalizeJob> fin_direct;
         uint64_t mac_bytes = 0;
         for (size_t k = 0; k < direct.size(); k++) {
             BinBundleStore *s = direct[k].s;
             uint32_t degree = s->ncoeffs - 1, out = acc0 + (uint32_t)k * 2 * Ll;
             // bin_bundle.cpp:106-174; a degree-0 polynomial leaves the zero accumulator
-            add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, s->ntt_coeffs.p, degree, out);
+            add_job(groups, lowt_base[s->bundle_idx], nlow, s->ntt_coeffs.p, s->n_ntt, degree, out);
             mac_bytes += (uint64_t)degree * Ll * N * 8;
             FinalizeJob f;
             std::memset(&f, 0, sizeof(f));
@@ -653,14 +707,14 @@ void Engine::build_plan()
             BinBundleStore *s = psb[k].ref.s;
             for (uint32_t j = psb[k].job_lo; j < psb[k].job_hi; j++) {
                 // NTT-form rank of degree i*h + 1 is i*(h-1)
-                const u64 *coeff = s->ntt_coeffs.p + (size_t)jobs[j].i * (h - 1) * Ll * N;
-                add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, coeff, jobs[j].nterms, tin0 + j * 2 * Ll);
+                const u64 *coeff = s->ntt_coeffs.p + (size_t)jobs[j].i * (h - 1) * kKtCols;
+                add_job(groups, lowt_base[s->bundle_idx], nlow, coeff, s->n_ntt, jobs[j].nterms, tin0 + j * 2 * Ll);
                 mac_bytes += (uint64_t)jobs[j].nterms * Ll * N * 8;
             }
             // i = 0 terms summed in NTT form.  Without a level gap this IS the i = 0 polynomial; with one
             // (per-term mod-switch, bin_bundle.cpp:314-324) it supplies the linear part and only the terms'
             // last-prime residues are handled one by one (k_ms_sum_last).
-            add_job(groups, low_base[s->bundle_idx], 2 * Ll, Ll, s->ntt_coeffs.p, ps, r00 + k * 2 * Ll);
+            add_job(groups, lowt_base[s->bundle_idx], nlow, s->ntt_coeffs.p, s->n_ntt, ps, r00 + k * 2 * Ll);
             mac_bytes += (uint64_t)ps * Ll * N * 8;
         }
         emit_mac(pb, Ll, groups, mac_bytes);
@@ -675,7 +729,7 @@ void Engine::build_plan()
             const uint32_t c1 = std::min(nb_all, c0 + chunk), nb = c1 - c0;
             const uint32_t j0 = psb[c0].job_lo, j1 = psb[c1 - 1].job_hi, nj = j1 - j0;
             std::vector<FinalizeJob> fin_ps;
-            std::vector<MacGroup> k8groups;
+            std::vector<KtGroup> k8groups;
             std::vector<MulTermsJob> mulj;
             std::vector<uint32_t> tinh(nj), r0h(nb);
             if (drops) {
@@ -688,6 +742,7 @@ void Engine::build_plan()
                     MulTermsJob mj;
                     std::memset(&mj, 0, sizeof(mj));
                     mj.coeff = s->ntt_coeffs.p;
+                    mj.rows = s->n_ntt;
                     mj.out_idx = t00 + k * ps * 2;
                     mj.pow_idx = low_base[s->bundle_idx];
                     mj.pow_term_stride = 2 * Ll;
@@ -760,7 +815,7 @@ void Engine::build_plan()
             for (uint32_t k = 0; k < nb; k++) {
                 BinBundleStore *s = psb[c0 + k].ref.s;
                 uint32_t H = (s->ncoeffs - 1) / h;
-                add_job(k8groups, highext_base[s->bundle_idx], 2 * LSh, LSh, s->plain_high_ntt.p, H, k80 + k * 2 * Lh);
+                add_job(k8groups, hight_base[s->bundle_idx], nhigh, s->plain_high_ntt.p, s->n_plain - 1, H, k80 + k * 2 * Lh);
             }
             emit_mac(pb, Lh, k8groups, 0);
             pb.ntt_run(k80, nb * 2 * Lh, ctx.pattern_q(Lh), true);
@@ -796,69 +851,50 @@ size_t Engine::add_desc(const void *data, size_t bytes)
     return off;
 }
 
-void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &groups, uint64_t bytes)
+void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<KtGroup> &groups, uint64_t bytes)
 {
     if (groups.empty()) return;
-    // regroup: jobs over the same powers, longest first, eight to a group; full equal-length groups go
-    // first (they run the branch-free kernel variant), ragged ones after
-    uint32_t n_uniform = 0;
+    // regroup: jobs over the same power table, longest first, kKtG to a group; full equal-length groups run the
+    // branch-free path of the kernel, the others (marked ragged) the masked one
     {
         struct J {
-            const u64 *coeff;
-            uint32_t nterms, out;
+            const u64 *w;
+            uint32_t wstride, nterms, out;
         };
-        std::map<std::array<uint32_t, 3>, std::vector<J>> by_pow;
+        std::map<std::array<uint32_t, 2>, std::vector<J>> by_pow;
         for (auto &g : groups)
-            for (uint32_t k = 0; k < g.njobs; k++) by_pow[{ g.pow_idx, g.pow_term_stride, g.pow_comp_stride }].push_back(J{ g.coeff[k], g.nterms[k], g.out_idx[k] });
-        std::vector<MacGroup> uni, rag;
+            for (uint32_t k = 0; k < g.njobs; k++) by_pow[{ g.p_idx, g.pstride }].push_back(J{ g.w[k], g.wstride[k], g.nterms[k], g.out_idx[k] });
+        std::vector<KtGroup> out;
         for (auto &kv : by_pow) {
             auto &js = kv.second;
             std::stable_sort(js.begin(), js.end(), [](const J &a, const J &b) { return a.nterms > b.nterms; });
-            for (size_t i = 0; i < js.size(); i += kMacJobs) {
-                MacGroup g;
+            for (size_t i = 0; i < js.size(); i += kKtG) {
+                KtGroup g;
                 std::memset(&g, 0, sizeof(g));
-                g.pow_idx = kv.first[0];
-                g.pow_term_stride = kv.first[1];
-                g.pow_comp_stride = kv.first[2];
+                g.p_idx = kv.first[0];
+                g.pstride = kv.first[1];
                 bool same = true;
-                for (size_t k = i; k < std::min(js.size(), i + kMacJobs); k++) {
-                    g.coeff[g.njobs] = js[k].coeff;
+                for (size_t k = i; k < std::min(js.size(), i + kKtG); k++) {
+                    g.w[g.njobs] = js[k].w;
+                    g.wstride[g.njobs] = js[k].wstride;
                     g.nterms[g.njobs] = js[k].nterms;
                     g.out_idx[g.njobs] = js[k].out;
                     g.max_terms = std::max(g.max_terms, js[k].nterms);
                     same &= js[k].nterms == js[i].nterms;
                     g.njobs++;
                 }
-                const bool uniform = same && g.njobs == kMacJobs && g.max_terms > 0;
-                g.pad_ = uniform ? 0 : 1; // ragged marker read by the kernel
-                (uniform ? uni : rag).push_back(g);
+                for (uint32_t k = g.njobs; k < (uint32_t)kKtG; k++) g.w[k] = g.w[0]; // never read: nterms = 0
+                g.ragged = (same && g.njobs == (uint32_t)kKtG) ? 0 : 1;
+                out.push_back(g);
             }
         }
-        n_uniform = (uint32_t)uni.size();
-        groups = uni;
-        groups.insert(groups.end(), rag.begin(), rag.end());
+        groups = out;
     }
-    int mac_g = 4;
-    if (const char *ev = std::getenv("APSU_B200_MAC_G")) mac_g = atoi(ev) == 4 ? 4 : 8;
-    size_t off = add_desc(groups.data(), groups.size() * sizeof(MacGroup));
+    size_t off = add_desc(groups.data(), groups.size() * sizeof(KtGroup));
     uint32_t n = (uint32_t)groups.size();
     groups.clear();
     size_t slot = mac_step_bytes_.size();
     mac_step_bytes_.push_back(bytes);
-    // lazy-accumulation budgets from the largest prime of the level (see db_stream.cuh)
-    int b = 0;
-    for (uint32_t j = 0; j < L; j++) b = std::max(b, hm::bit_length(ctx.params.coeff_modulus[j]));
-    if (b > 61) throw std::invalid_argument("coeff_modulus primes must have at most 61 bits");
-    // lane capacities in TERMS: ll < 2^30 + T*2^60, mid < 2^35 + 2T*2^b, hh < T*2^(2b-60) (+carries); the
-    // kernel consumes terms in pairs
-    const uint64_t norm_terms = std::min<uint64_t>(15, (1ull << (63 - b)) - 1);
-    const uint32_t norm_period = (uint32_t)std::max<uint64_t>(1, norm_terms / 2); // in term pairs
-    const uint64_t hh_terms = 124 - 2 * b >= 31 ? 0x7FFFFFFFull : ((1ull << (124 - 2 * b)) - 1);
-    const uint64_t per_norm = 2ull * norm_period;
-    const uint32_t reduce_period = (uint32_t)std::max<uint64_t>(1, (hh_terms / per_norm > 1 ? hh_terms / per_norm - 1 : 1));
-    const uint32_t lazy_bound = 128 - 2 * b >= 31 ? 0x7FFFFFFFu : (1u << (128 - 2 * b));
-    const char *sel = std::getenv("APSU_B200_MAC");
-    const bool use_tma = !(sel && std::string(sel) == "v1");
     pb.step([=] {
         const bool timed = profiling && mac_step_bytes_[slot] > 0;
         cudaEvent_t a = nullptr, b2 = nullptr;
@@ -874,30 +910,19 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &gro
             mac_events_used_++;
             APSU_CUDA_CHECK(cudaEventRecord(a, ctx.stream));
         }
-        const MacGroup *gd = reinterpret_cast<const MacGroup *>(desc_dev_.p + off);
-        if (use_tma) {
-            // one persistent launch over all groups (uniform ones first; ragged groups carry pad_ = 1)
-            auto launch = [&](auto kern, size_t smem, int min_blocks) {
-                APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int per_sm = 0;
-                APSU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStreamThreads, smem));
-                per_sm = std::max(1, std::min(per_sm, min_blocks));
-                int sms = 0;
-                APSU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device));
-                uint32_t items = n * (kMacJobs / mac_g) * (L * ctx.N / kStreamCols);
-                uint32_t grid = std::min<uint32_t>(items, (uint32_t)(sms * per_sm));
-                kern<<<grid, kStreamThreads, smem, ctx.stream>>>(arena_.buf.p, gd, n, ctx.level[L], (int)ctx.N, norm_period, reduce_period);
-                APSU_CUDA_CHECK(cudaGetLastError());
-                ctx.launches++;
-            };
-            if (mac_g == 4)
-                launch(k_db_mac_tma<4>, StreamCfg<4>::smem_bytes, 4);
-            else
-                launch(k_db_mac_tma<8>, StreamCfg<8>::smem_bytes, 3);
-            ctx.launches--; // the common epilogue below counts one
-        } else {
-            k_db_mac<<<dim3(L * ctx.N / kMacThreads, n), kMacThreads, 0, ctx.stream>>>(arena_.buf.p, gd, ctx.level[L], (int)ctx.N, lazy_bound);
-        }
+        const KtGroup *gd = reinterpret_cast<const KtGroup *>(desc_dev_.p + off);
+        // one persistent launch over all groups
+        auto kern = k_db_mac_kt<kKtStages, kKtCtasPerSm>;
+        constexpr size_t smem = kt_smem_bytes(kKtStages);
+        APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        APSU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kKtThreads, smem));
+        per_sm = std::max(1, std::min(per_sm, kKtCtasPerSm));
+        int sms = 0;
+        APSU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device));
+        const uint32_t items = n * (L * ctx.N / kKtCols);
+        const uint32_t grid = std::min<uint32_t>(items, (uint32_t)(sms * per_sm));
+        kern<<<grid, kKtThreads, smem, ctx.stream>>>(arena_.buf.p, gd, n, ctx.level[L], (int)ctx.N, split_, fold_stages_);
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;
         if (timed) {
@@ -915,7 +940,7 @@ void Engine::emit_mul_terms(ProgramBuilder &pb, uint32_t L, std::vector<MulTerms
     jobs.clear();
     pb.step([=] {
         k_db_mul_last<<<dim3(ctx.N / kMacThreads, nterms, n), kMacThreads, 0, ctx.stream>>>(
-            arena_.buf.p, reinterpret_cast<const MulTermsJob *>(desc_dev_.p + off), ctx.level[L], (int)ctx.N);
+            arena_.buf.p, reinterpret_cast<const MulTermsJob *>(desc_dev_.p + off), ctx.level[L], (int)ctx.N, split_);
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;
     });

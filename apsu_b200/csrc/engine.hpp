@@ -9,7 +9,7 @@
 namespace apsu_b200 {
 
 struct ProgramBuilder;
-struct MacGroup;
+struct KtGroup;
 struct MulTermsJob;
 struct FinalizeJob;
 
@@ -46,12 +46,14 @@ struct Arena {
 struct BinBundleStore {
     uint32_t bundle_idx = 0, cache_idx = 0;
     uint32_t ncoeffs = 0;
-    // NTT-form plaintexts, packed in degree order (coefficient-form degrees skipped): [n_ntt][low_L][N]
+    // NTT-form plaintexts in degree order (coefficient-form degrees skipped), tile-major and split
+    // (db_stream.cuh): [low_L*N/128][n_ntt][128]
     DBuf<u64> ntt_coeffs;
     // coefficient-form plaintexts (degree 0 and, with PS, multiples of ps_low+1): [n_plain][N]
     DBuf<u64> plain_coeffs;
     // PS only: the coefficient-form plaintexts of degree i*(ps_low+1), i>=1, lifted and NTT'd at the high
-    // level once at upload (multiply_plain on coefficient-form operands, bin_bundle.cpp:328-337): [n_plain-1][high_L][N]
+    // level once at upload (multiply_plain on coefficient-form operands, bin_bundle.cpp:328-337), tile-major
+    // and split: [high_L*N/128][n_plain-1][128]
     DBuf<u64> plain_high_ntt;
     uint32_t n_ntt = 0, n_plain = 0;
 };
@@ -72,6 +74,7 @@ public:
     uint32_t total_bundles() const;
     uint64_t stream_bytes() const;
     void clear_db();
+    int db_split() const { return split_; } // bit position the stored NTT-form words are split at
     bool is_ntt_degree(uint32_t k) const
     {
         uint32_t ps = ctx.params.ps_low_degree;
@@ -117,7 +120,7 @@ private:
     // the polynomial arena and the two programs
     Arena arena_;
     IdxPool idx_;
-    std::vector<uint8_t> desc_host_; // kernel descriptor structs (MacGroup, FinalizeJob, ...)
+    std::vector<uint8_t> desc_host_; // kernel descriptor structs (KtGroup, FinalizeJob, ...)
     DBuf<uint8_t> desc_dev_;
     std::vector<Step> powers_prog_, eval_prog_;
     bool plan_valid_ = false;
@@ -141,9 +144,12 @@ private:
     void invalidate_plan() { plan_valid_ = false; }
     void build_plan();
     void prepare_plain_high(BinBundleStore &s);
-    void pack_words(u64 *data, size_t count);
+    void pack_tile(const u64 *src, u64 *dst, uint32_t rows, uint32_t L);
+    DBuf<u64> stage_;         // staging for uploads in the standard layout
+    int split_ = 30;          // bit position the DB-stream operands are split at
+    uint32_t fold_stages_ = 1; // ring stages between lane folds in the DB-stream kernel
     size_t add_desc(const void *data, size_t bytes);
-    void emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<MacGroup> &groups, uint64_t bytes);
+    void emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<KtGroup> &groups, uint64_t bytes);
     void emit_mul_terms(ProgramBuilder &pb, uint32_t L, std::vector<MulTermsJob> &jobs, uint32_t nterms);
     void emit_finalize(ProgramBuilder &pb, uint32_t Ls, std::vector<FinalizeJob> &jobs);
     template <typename Build>

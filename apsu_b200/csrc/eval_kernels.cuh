@@ -1,6 +1,7 @@
 // Kernels of the per-BinBundle polynomial evaluation (K1, K7, K8, K9, K10 of SURVEY.md §2.2):
-//   k_db_mac      — the DB stream: sum_j power_j ⊙ plaintext_j over NTT-form plaintexts (HBM-bound)
-//   k_db_mul      — per-term products (Paterson-Stockmeyer i=0 polynomial, bin_bundle.cpp:314-324)
+//   k_db_mac_kt   — the DB stream: sum_j power_j ⊙ plaintext_j over NTT-form plaintexts (HBM-bound; db_stream.cuh)
+//   k_db_mul_last — per-term last-prime products (Paterson-Stockmeyer i=0 polynomial, bin_bundle.cpp:314-324)
+//   k_ms_sum_last — the per-term mod-switch of those terms, summed
 //   k_finalize    — add_plain(coeff 0) + add_plain(mask) + mod-switch to the last level + clear bits
 //   k_plain_lift  — fast plain lift of a coefficient-form plaintext to RNS (before its NTT)
 //   k_fill_uniform, k_slot_scatter — synthetic DB fill, BatchEncoder slot permutation
@@ -9,108 +10,31 @@
 
 namespace apsu_b200 {
 
-constexpr int kMacJobs = 8;      // jobs per group: share every ciphertext-power load
 constexpr int kMacThreads = 256;
+constexpr int kTileCols = 128; // the DB-stream tile (db_stream.cuh)
 
-// NTT-form DB plaintext words are stored split at bit 30 ("packed"): low 30 bits in the low half of the
-// 64-bit word, the remaining bits in the high half — the DB-stream kernel multiplies the halves directly.
-__host__ __device__ __forceinline__ u64 pack30_word(u64 w) { return (w & 0x3FFFFFFFull) | ((w >> 30) << 32); }
-__host__ __device__ __forceinline__ u64 unpack30_word(u64 p) { return (p & 0xFFFFFFFFull) | ((p >> 32) << 30); }
+// NTT-form DB plaintexts live TILE-MAJOR and SPLIT (db_stream.cuh): a buffer of `rows` plaintexts over L*N
+// columns is [L*N/128][rows][128] words, each word split at bit `split` (low part in the low half of the
+// 64-bit word, the remaining bits in the high half) — the DB-stream kernel multiplies the halves directly.
+__host__ __device__ __forceinline__ u64 split_word(u64 w, int s) { return (w & ((1ull << s) - 1)) | ((w >> s) << 32); }
+__host__ __device__ __forceinline__ u64 unsplit_word(u64 p, int s) { return (p & 0xFFFFFFFFull) | ((p >> 32) << s); }
+__device__ __forceinline__ size_t tile_major_at(u32 rows, u32 row, size_t col) { return ((col / kTileCols) * rows + row) * kTileCols + col % kTileCols; }
 
-// One group = up to kMacJobs accumulation jobs over the same ciphertext powers.
-// job g: out_g[c][l][n] = sum_{j < nterms_g} power_j[c][l][n] * coeff_g[j][l][n]   (mod q_l)
-struct MacGroup {
-    const u64 *coeff[kMacJobs]; // plaintexts of job g, term j at coeff[g] + j*L*N (HBM-resident DB)
-    u32 nterms[kMacJobs];
-    u32 out_idx[kMacJobs];      // arena index of [2][L][N]
-    u32 pow_idx;                // arena index of power term 0, component 0, prime 0
-    u32 pow_term_stride;        // polynomials between consecutive terms
-    u32 pow_comp_stride;        // polynomials between the two ciphertext components
-    u32 njobs;
-    u32 max_terms;
-    u32 pad_;
-};
-
-// grid (L*N/256, n_groups).  Each thread owns one (prime, coefficient) column: streams the G
-// plaintext words of term j with independent 8-byte coalesced loads, multiplies them into 2G 128-bit
-// lazy accumulators against the two power words (L2-resident, shared by the G jobs), reduces once.
-// lazy_bound = number of products that fit 128 bits for the largest prime (>= 256 for <=60-bit primes).
-__global__ void __launch_bounds__(kMacThreads)
-k_db_mac(u64 *A, const MacGroup *__restrict__ groups, LevelConsts c, int N, u32 lazy_bound)
-{
-    __shared__ MacGroup g;
-    if (threadIdx.x < sizeof(MacGroup) / 4) reinterpret_cast<u32 *>(&g)[threadIdx.x] = reinterpret_cast<const u32 *>(&groups[blockIdx.y])[threadIdx.x];
-    __syncthreads();
-    const u32 col = blockIdx.x * blockDim.x + threadIdx.x; // l*N + n
-    const u32 l = col / N;
-    const DMod m = c.q[l];
-    const size_t LN = (size_t)c.L * N;
-    Acc128 acc[kMacJobs][2];
-#pragma unroll
-    for (int k = 0; k < kMacJobs; k++) acc[k][0] = acc[k][1] = Acc128{ 0, 0 };
-    const u64 *pw = A + (size_t)g.pow_idx * N + col;
-    const size_t tstride = (size_t)g.pow_term_stride * N, cstride = (size_t)g.pow_comp_stride * N;
-    u32 since_reduce = 0;
-    for (u32 j = 0; j < g.max_terms; j++) {
-        const u64 p0 = pw[j * tstride], p1 = pw[j * tstride + cstride];
-        u64 w[kMacJobs];
-#pragma unroll
-        for (int k = 0; k < kMacJobs; k++) w[k] = (j < g.nterms[k]) ? unpack30_word(__ldcs(g.coeff[k] + j * LN + col)) : 0ull;
-#pragma unroll
-        for (int k = 0; k < kMacJobs; k++) {
-            mac128(acc[k][0], w[k], p0);
-            mac128(acc[k][1], w[k], p1);
-        }
-        if (++since_reduce == lazy_bound) { // never taken for the reference parameter sets
-            since_reduce = 0;
-#pragma unroll
-            for (int k = 0; k < kMacJobs; k++) {
-                acc[k][0] = Acc128{ barrett128(acc[k][0].lo, acc[k][0].hi, m), 0 };
-                acc[k][1] = Acc128{ barrett128(acc[k][1].lo, acc[k][1].hi, m), 0 };
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kMacJobs; k++) {
-        if (k < (int)g.njobs) {
-            u64 *o = A + (size_t)g.out_idx[k] * N + col;
-            o[0] = barrett128(acc[k][0].lo, acc[k][0].hi, m);
-            o[LN] = barrett128(acc[k][1].lo, acc[k][1].hi, m);
-        }
-    }
-}
-
-// per-term products: out[term][c][l][n] = power_term[c][l][n] * coeff[term][l][n].
-// grid (L*N/256, nterms, n_bundles); bundle b: coeff[b], out_idx[b] (terms contiguous: [term][2][L][N]).
+// per-term products of the Paterson-Stockmeyer i=0 polynomial (bin_bundle.cpp:314-324), one job per BinBundle
 struct MulTermsJob {
-    const u64 *coeff;
+    const u64 *coeff; // tile-major split plaintexts of the BinBundle, `rows` per tile; terms are rows 0..nterms-1
+    u32 rows;
     u32 out_idx;
-    u32 pow_idx, pow_term_stride, pow_comp_stride;
+    u32 pow_idx, pow_term_stride, pow_comp_stride; // powers in the standard layout (arena)
     u32 nterms;
-    u32 pad_;
 };
-__global__ void __launch_bounds__(kMacThreads)
-k_db_mul(u64 *A, const MulTermsJob *__restrict__ jobs, LevelConsts c, int N)
-{
-    const MulTermsJob jb = jobs[blockIdx.z];
-    const u32 j = blockIdx.y;
-    if (j >= jb.nterms) return;
-    const u32 col = blockIdx.x * blockDim.x + threadIdx.x;
-    const DMod m = c.q[col / N];
-    const size_t LN = (size_t)c.L * N;
-    const u64 w = unpack30_word(__ldcs(jb.coeff + j * LN + col));
-    const u64 *pw = A + ((size_t)jb.pow_idx + (size_t)j * jb.pow_term_stride) * N + col;
-    u64 *o = A + ((size_t)jb.out_idx) * N + (size_t)j * 2 * LN + col;
-    o[0] = mul_mod(pw[0], w, m);
-    o[LN] = mul_mod(pw[(size_t)jb.pow_comp_stride * N], w, m);
-}
 
 // Last-prime variant: only the residues modulo the LAST prime of the level are produced,
 // out[term][c][n] (one polynomial per (term, component)).  grid (N/256, nterms, n_bundles).
 // Used for the PS i=0 polynomial when a mod-switch separates low and high powers: the per-term rounding of
 // mod_switch_to_next only depends on each term's last-prime residue (see k_ms_sum_last).
 __global__ void __launch_bounds__(kMacThreads)
-k_db_mul_last(u64 *A, const MulTermsJob *__restrict__ jobs, LevelConsts c, int N)
+k_db_mul_last(u64 *A, const MulTermsJob *__restrict__ jobs, LevelConsts c, int N, int split)
 {
     const MulTermsJob jb = jobs[blockIdx.z];
     const u32 j = blockIdx.y;
@@ -118,8 +42,8 @@ k_db_mul_last(u64 *A, const MulTermsJob *__restrict__ jobs, LevelConsts c, int N
     const u32 n = blockIdx.x * blockDim.x + threadIdx.x;
     const int l = c.L - 1;
     const DMod m = c.q[l];
-    const size_t LN = (size_t)c.L * N, col = (size_t)l * N + n;
-    const u64 w = unpack30_word(__ldcs(jb.coeff + j * LN + col));
+    const size_t col = (size_t)l * N + n;
+    const u64 w = unsplit_word(__ldcs(jb.coeff + tile_major_at(jb.rows, j, col)), split);
     const u64 *pw = A + ((size_t)jb.pow_idx + (size_t)j * jb.pow_term_stride) * N + col;
     u64 *o = A + ((size_t)jb.out_idx + (size_t)j * 2) * N + n;
     o[0] = mul_mod(pw[0], w, m);
@@ -274,14 +198,14 @@ __device__ __forceinline__ u64 splitmix64_at(u64 seed, u64 k)
 // Synthetic BinBundle fill.  The stream visits the plaintexts in degree order (coefficient-form ones are
 // N words mod t, NTT-form ones L*N words mod q_l) and word k of the stream is
 // (splitmix64_at(seed, k) * modulus) >> 64 — the same words the oracle's synthetic fill produces.
-// mode 0: `out` is the packed NTT-form buffer [n_ntt][L][N]; mode 1: the coefficient-form buffer [n_plain][N].
-// h = ps_low_degree + 1 (0 when Paterson-Stockmeyer is off).
+// mode 0: `out` is the tile-major split NTT-form buffer of `rows` plaintexts; mode 1: the coefficient-form
+// buffer [n_plain][N].  h = ps_low_degree + 1 (0 when Paterson-Stockmeyer is off).
 struct FillMods {
     u64 q[kMaxQ];
     u64 t;
     int L;
 };
-__global__ void k_fill_db(u64 *__restrict__ out, size_t count, u64 seed, int mode, u32 h, FillMods mods, int N)
+__global__ void k_fill_db(u64 *__restrict__ out, size_t count, u64 seed, int mode, u32 h, FillMods mods, int N, u32 rows, int split)
 {
     size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= count) return;
@@ -302,7 +226,10 @@ __global__ void k_fill_db(u64 *__restrict__ out, size_t count, u64 seed, int mod
         pos = (h ? r * (N + (size_t)(h - 1) * LN) : 0) + within;
     }
     const u64 v = mulhi(splitmix64_at(seed, pos), q);
-    out[w] = mode == 0 ? pack30_word(v) : v; // NTT-form plaintexts are stored packed (db_stream.cuh)
+    if (mode == 0)
+        out[tile_major_at(rows, (u32)(w / LN), w % LN)] = split_word(v, split);
+    else
+        out[w] = v;
 }
 
 // BatchEncoder::encode scatter: out[p][map[i]] = values[p][i]

@@ -422,7 +422,7 @@ def main():
             "scopes_ms_rank0_last_step": {"Receiver::ComputePowers": tm["compute_powers_ms"], "Receiver::ProcessBinBundleCache(all)": tm["eval_ms"]},
             "db_stream": {"bytes_per_query": total_bytes, "bytes_rank0": my_bytes, "effective_gbs_whole_eval": (my_bytes / 1e9) / (tm["eval_ms"] / 1e3) if tm["eval_ms"] else None},
             "roofline": {
-                "kernel": "k_db_mac (DB-stream multiply-accumulate, K1)", "bound": "hbm", "achieved": mac_gbs, "peak": hbm_peak,
+                "kernel": "k_db_mac_kt (DB-stream multiply-accumulate, K1)", "bound": "hbm", "achieved": mac_gbs, "peak": hbm_peak,
                 "unit": "GB/s", "frac": mac_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "launches_timed": tm["db_stream_launches"], "avg_launch_ms": tm["db_stream_ms"] / launches,
                 "algorithmic_bytes_per_launch": tm["db_stream_bytes"] / launches,
