@@ -66,6 +66,54 @@ def test_query_parity(name):
         db.close()
 
 
+def _all_parameter_files():
+    import json
+    import pathlib
+    table = json.loads((pathlib.Path(__file__).resolve().parent / "golden" / "parameters.json").read_text())
+    return sorted(k[:-5] for k in table)
+
+
+def _sweep_degrees(p):
+    """small BinBundles that still take every branch the parameter file allows: Paterson-Stockmeyer with and
+    without a remainder polynomial plus a bundle below the PS threshold, or direct evaluation at full degree;
+    first and last bundle index populated, the ones between empty (receiver_ddh.cpp:399-402)."""
+    bic, maxdeg, ps = p.bundle_idx_count, p.max_items_per_bin - 1, p.ps_low_degree
+    deg = [[] for _ in range(bic)]
+    if ps:
+        h = ps + 1
+        d0 = min(maxdeg, (2 * h + ps // 2) if ps < 100 else h + ps // 4)
+        d1 = min(maxdeg, 2 * h if ps < 100 else h)
+        small = min(maxdeg, max(1, ps - 1) if ps < 100 else 20)
+    else:
+        d0, d1, small = maxdeg, max(1, maxdeg // 2), min(maxdeg, 3)
+    deg[0] = [d0, small]
+    if bic > 1:
+        deg[bic - 1] = [d1]
+    return deg
+
+
+@pytest.mark.parametrize("name", [n for n in _all_parameter_files() if n not in CASES])
+def test_query_parity_every_parameter_file(name):
+    """north star: bit-exact result ciphertexts and identical decrypted output on EVERY parameters/*.json
+    (the seven files in CASES get the deeper staged test above)."""
+    import apsu_b200
+    from oracle import oracle as O
+    sc = Scenario(name, _sweep_degrees(O.Params.load(name)), planted=4)
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0)
+    try:
+        _upload(sc, db)
+        rx = apsu_b200.Receiver(db)
+        exp = {(b, c): ct for b, c, ct in sc.db.run_query(sc.src_powers, sc.cts, sc.relin, sc.masks, threads=8).results()}
+        got = {(r.bundle_idx, r.cache_idx): r.psu_result for r in rx.RunQuery(apsu_b200.Query(sc.src_powers, sc.cts, sc.relin), sc.masks)}
+        assert set(got) == set(exp)
+        for key in exp:
+            assert np.array_equal(got[key].reshape(2, -1), exp[key]), key
+            ok, budget, _, _ = sc.check_result(key[0], key[1], got[key].reshape(2, -1))
+            assert ok and budget > 0, (key, budget)
+    finally:
+        db.close()
+
+
 def rx_targets(p):
     if p.ps_low_degree:
         h = p.ps_low_degree + 1
