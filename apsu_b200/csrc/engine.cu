@@ -362,9 +362,85 @@ uint32_t Engine::add_binbundle_synthetic(uint32_t bundle_idx, uint32_t ncoeffs, 
     return ci;
 }
 
-uint32_t Engine::add_binbundle_from_bins(uint32_t, const uint32_t *, const uint64_t *)
+// BinBundle::regen_cache on the device (bin_bundle.cpp:934-1041): regen_polyns = polyn_with_roots per bin,
+// regen_plaintexts = BatchedPlaintextPolyn ctor (bin_bundle.cpp:366-430): plaintext i = BatchEncoder::encode of
+// the degree-i coefficients of all bins, NTT form at the plaintext level unless i == 0 / i % (ps_low+1) == 0.
+uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bin_sizes, const uint64_t *roots)
 {
-    throw std::logic_error("device-side BinBundle construction from raw bins is not implemented yet (SURVEY.md §8 row f1)");
+    if (bundle_idx >= db.size()) throw std::invalid_argument("bundle_idx is out of range");
+    const apsu_b200_params &p = ctx.params;
+    const uint32_t N = ctx.N, Ll = ctx.low_L, nbins = p.bins_per_bundle;
+    std::vector<uint32_t> first(nbins);
+    uint32_t max_deg = 0;
+    size_t total = 0;
+    for (uint32_t b = 0; b < nbins; b++) {
+        first[b] = (uint32_t)total;
+        total += bin_sizes[b];
+        max_deg = std::max(max_deg, bin_sizes[b]);
+        // a bin holds fewer than max_items_per_bin items (receiver_db.cpp:388-389)
+        if (bin_sizes[b] >= p.max_items_per_bin) throw std::invalid_argument("a bin holds max_items_per_bin or more items");
+    }
+    if (total >= (1ull << 32)) throw std::invalid_argument("too many items in one BinBundle");
+    for (size_t i = 0; i < total; i++)
+        if (roots[i] >= ctx.t) throw std::invalid_argument("bin item is not a field element (>= plain_modulus)");
+    const uint32_t ncoeffs = max_deg + 1;
+
+    auto s = std::make_unique<BinBundleStore>();
+    s->bundle_idx = bundle_idx;
+    s->cache_idx = (uint32_t)db[bundle_idx].size();
+    s->ncoeffs = ncoeffs;
+    std::vector<uint32_t> ntt_rows, plain_rows;
+    for (uint32_t k = 0; k < ncoeffs; k++) (is_ntt_degree(k) ? ntt_rows : plain_rows).push_back(k);
+    s->n_ntt = (uint32_t)ntt_rows.size();
+    s->n_plain = (uint32_t)plain_rows.size();
+    s->ntt_coeffs.alloc((size_t)s->n_ntt * Ll * N);
+    s->plain_coeffs.alloc((size_t)s->n_plain * N);
+
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    DBuf<uint32_t> d_first, d_size, d_rows;
+    DBuf<u64> d_roots, M, enc;
+    d_first.upload(first, ctx.stream);
+    d_size.alloc(nbins);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(d_size.p, bin_sizes, nbins * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx.stream));
+    d_roots.alloc(std::max<size_t>(total, 1));
+    if (total) APSU_CUDA_CHECK(cudaMemcpyAsync(d_roots.p, roots, total * 8, cudaMemcpyHostToDevice, ctx.stream));
+    M.alloc((size_t)ncoeffs * N);
+    enc.alloc((size_t)ncoeffs * N);
+    APSU_CUDA_CHECK(cudaMemsetAsync(M.p, 0, M.n * 8, ctx.stream));
+    APSU_CUDA_CHECK(cudaMemsetAsync(enc.p, 0, enc.n * 8, ctx.stream));
+    {
+        // one warp per bin; as many warps per block as the polynomials leave shared memory for
+        const size_t per_warp = (size_t)(max_deg + 2) * 8;
+        int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (160 * 1024) / per_warp));
+        const size_t smem = per_warp * warps;
+        const DMod mt = ctx.mod_host[ctx.idx_t];
+        const bool small = ctx.t < (1ull << 32);
+        auto kern = small ? k_polyn_with_roots<true> : k_polyn_with_roots<false>;
+        APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(nbins + warps - 1) / warps, warps * 32, smem, ctx.stream>>>(d_first.p, d_size.p, d_roots.p, M.p, nbins, max_deg, mt, (int)N);
+        APSU_LAUNCH_CHECK();
+    }
+    // BatchEncoder::encode: slot permutation + inverse NTT modulo t
+    k_slot_scatter<<<dim3(N / 256, ncoeffs), 256, 0, ctx.stream>>>(M.p, enc.p, ctx.slot_map.p, (int)N);
+    APSU_LAUNCH_CHECK();
+    ctx.ntt(enc.p, enc.p, ncoeffs, { ctx.idx_t }, true);
+    for (uint32_t i = 0; i < s->n_plain; i++)
+        APSU_CUDA_CHECK(cudaMemcpyAsync(s->plain_coeffs.p + (size_t)i * N, enc.p + (size_t)plain_rows[i] * N, (size_t)N * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+    if (s->n_ntt) {
+        // transform_to_ntt_inplace(pt, plaintext level): lift + NTT, then the tile-major split store
+        d_rows.upload(ntt_rows, ctx.stream);
+        stage_.ensure((size_t)s->n_ntt * Ll * N);
+        k_plain_lift<<<dim3(N / kEwThreads, Ll, s->n_ntt), kEwThreads, 0, ctx.stream>>>(enc.p, stage_.p, ctx.level[Ll], ctx.t, (int)N, d_rows.p);
+        APSU_LAUNCH_CHECK();
+        ctx.ntt(stage_.p, stage_.p, s->n_ntt * Ll, ctx.pattern_q(Ll), false);
+        pack_tile(stage_.p, s->ntt_coeffs.p, s->n_ntt, Ll);
+    }
+    prepare_plain_high(*s);
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    uint32_t ci = s->cache_idx;
+    db[bundle_idx].push_back(std::move(s));
+    invalidate_plan();
+    return ci;
 }
 
 // ------------------------------------------------------------------------------------------------

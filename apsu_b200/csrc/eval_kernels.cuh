@@ -175,14 +175,14 @@ k_finalize(u64 *A, const FinalizeJob *__restrict__ jobs, const LevelConsts *__re
 }
 
 // fast plain lift: coefficient-form plaintext [N] mod t -> RNS [L][N] (then NTT'd by the caller).
-// grid (N/256, L, n_plain): src plaintext p at in + p*N, dst at out + p*L*N
+// grid (N/256, L, n_plain): src plaintext p at in + rows[p]*N (rows == null: p), dst at out + p*L*N
 __global__ void __launch_bounds__(kEwThreads)
-k_plain_lift(const u64 *__restrict__ in, u64 *__restrict__ out, LevelConsts c, u64 t, int N)
+k_plain_lift(const u64 *__restrict__ in, u64 *__restrict__ out, LevelConsts c, u64 t, int N, const u32 *__restrict__ rows = nullptr)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     const size_t p = blockIdx.z;
-    const u64 v = in[p * N + n];
+    const u64 v = in[(rows ? (size_t)rows[p] : p) * N + n];
     const u64 thr = (t + 1) >> 1;
     out[(p * c.L + j) * N + n] = v >= thr ? v + (c.q[j].q - t) : v;
 }
@@ -230,6 +230,48 @@ __global__ void k_fill_db(u64 *__restrict__ out, size_t count, u64 seed, int mod
         out[tile_major_at(rows, (u32)(w / LN), w % LN)] = split_word(v, split);
     else
         out[w] = v;
+}
+
+// polyn_with_roots (common/apsu/util/interpolate.cpp:27-80) for every bin of a BinBundle: P = prod (x - a) over
+// the bin's roots, coefficients in degree-ascending order, written column-wise into the coefficient matrix
+// M[degree][bin] that BatchedPlaintextPolyn's ctor gathers (bin_bundle.cpp:390-407); M is pre-zeroed.
+// One warp per bin, the polynomial in shared memory; a root multiplies in place from the top coefficient
+// down, 32 coefficients at a time (polyn[i] = polyn[i-1] - a*polyn[i] only needs the old values to its left).
+// block = 32*warps, grid = ceil(nbins / warps), dynamic smem = warps * (max_deg + 2) words.
+// SMALL: t < 2^32, products fit one word.
+template <bool SMALL>
+__global__ void k_polyn_with_roots(const u32 *__restrict__ bin_first, const u32 *__restrict__ bin_size, const u64 *__restrict__ roots, u64 *__restrict__ M,
+                                   u32 nbins, u32 max_deg, DMod mt, int N)
+{
+    extern __shared__ u64 poly_smem[];
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const u32 bin = blockIdx.x * warps + warp;
+    if (bin >= nbins) return;
+    u64 *c = poly_smem + (size_t)warp * (max_deg + 2);
+    const u32 d = bin_size[bin];
+    const u64 *r = roots + bin_first[bin];
+    const u64 t = mt.q;
+    if (lane == 0) c[0] = 1;
+    __syncwarp();
+    for (u32 k = 0; k < d; k++) {
+        const u64 a = r[k];
+        const u64 neg_a = a ? t - a : 0; // negate_uint_mod
+        // polynomial currently has k+1 coefficients c[0..k]; after this root k+2: c[0..k+1]
+        // top coefficient first: c[k+1] = c[k] (old c[k+1] = 0)
+        for (int hi = (int)k + 1; hi >= 0; hi -= 32) {
+            const int i = hi - (int)lane;
+            u64 v = 0;
+            if (i >= 0) {
+                const u64 ci = i <= (int)k ? c[i] : 0, cl = i > 0 ? c[i - 1] : 0;
+                const u64 prod = SMALL ? barrett64(ci * neg_a, mt) : mul_mod(ci, neg_a, mt);
+                v = add_mod(prod, cl, t);
+            }
+            __syncwarp();
+            if (i >= 0) c[i] = v;
+            __syncwarp();
+        }
+    }
+    for (u32 i = lane; i <= d; i += 32) M[(size_t)i * N + bin] = c[i];
 }
 
 // BatchEncoder::encode scatter: out[p][map[i]] = values[p][i]

@@ -209,6 +209,22 @@ public:
         detail::check(apsu_b200_db_add_binbundle_synthetic(ctx_, bundle_idx, ncoeffs, seed, &ci));
         return ci;
     }
+    // BinBundle::regen_cache on the device (bin_bundle.cpp:934-1041): item_bins -> matching polynomials ->
+    // batched plaintexts, all built and kept on the GPU
+    std::uint32_t add_bin_bundle_from_bins(std::uint32_t bundle_idx, const std::vector<std::vector<std::uint64_t>> &item_bins)
+    {
+        std::unique_lock<std::shared_mutex> lock(db_lock_);
+        std::vector<std::uint32_t> sizes;
+        std::vector<std::uint64_t> roots;
+        for (auto &b : item_bins) {
+            sizes.push_back(static_cast<std::uint32_t>(b.size()));
+            roots.insert(roots.end(), b.begin(), b.end());
+        }
+        if (roots.empty()) roots.push_back(0);
+        std::uint32_t ci = 0;
+        detail::check(apsu_b200_db_add_binbundle_from_bins(ctx_, bundle_idx, sizes.data(), roots.data(), &ci));
+        return ci;
+    }
     std::size_t get_bin_bundle_count(std::uint32_t bundle_idx) const
     {
         std::uint32_t n = 0;

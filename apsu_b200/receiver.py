@@ -135,6 +135,18 @@ class ReceiverDB:
         capi.check(capi.lib().apsu_b200_db_add_binbundle_synthetic(self._h, bundle_idx, ncoeffs, seed, C.byref(ci)))
         return ci.value
 
+    def add_bin_bundle_from_bins(self, bundle_idx: int, bins) -> int:
+        """BinBundle::regen_cache on the device (receiver/apsu/bin_bundle.cpp:934-1041): `bins` is one list of
+        field elements (the items hashed to that bin) per bin of the bundle; polyn_with_roots, BatchEncoder::encode
+        and the NTTs run on the GPU and the cache stays device-resident."""
+        sizes = np.ascontiguousarray([len(b) for b in bins], dtype=np.uint32)
+        if len(sizes) != self.params.bins_per_bundle():
+            raise ValueError("bins must hold one entry per bin of the bundle")
+        roots = np.ascontiguousarray([x for b in bins for x in b] or [0], dtype=np.uint64)
+        ci = C.c_uint32()
+        capi.check(capi.lib().apsu_b200_db_add_binbundle_from_bins(self._h, bundle_idx, sizes, roots, C.byref(ci)))
+        return ci.value
+
     def get_bin_bundle_count(self, bundle_idx: int | None = None) -> int:
         v = C.c_uint32()
         if bundle_idx is None:

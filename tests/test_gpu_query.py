@@ -172,6 +172,35 @@ def test_db_roundtrip_synthetic_fill_and_mask_encode():
         db.close()
 
 
+@pytest.mark.parametrize("name,degrees", [("256K-512", [[63, 5]]), ("1M-4096-com", [[97, 9], [], [], [20], [0]]), ("100K-1", [[19]]),
+                                          ("16M-4096", [[140], [], [], [44, 45]])])
+def test_db_build_on_device(name, degrees):
+    """row f1: BinBundle::regen_cache on the GPU (polyn_with_roots, encode, NTT) gives the plaintexts the oracle
+    builds from the same bins, and a query against the device-built DB gives the oracle's result ciphertexts."""
+    import apsu_b200
+    sc = Scenario(name, degrees, planted=4)
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0)
+    try:
+        for b in range(sc.p.bundle_idx_count):
+            for c in range(len(sc.degrees[b])):
+                assert db.add_bin_bundle_from_bins(b, sc.bins[(b, c)]) == c
+                coeffs = sc.db.bundle_coeffs(b, c)
+                for k, (L, arr) in enumerate(coeffs):
+                    assert np.array_equal(db.bin_bundle_coeff(b, c, k), arr), (b, c, k)
+        rx = apsu_b200.Receiver(db)
+        exp = {(b, c): ct for b, c, ct in sc.db.run_query(sc.src_powers, sc.cts, sc.relin, sc.masks, threads=8).results()}
+        got = {(r.bundle_idx, r.cache_idx): r.psu_result for r in rx.RunQuery(apsu_b200.Query(sc.src_powers, sc.cts, sc.relin), sc.masks)}
+        assert set(got) == set(exp)
+        for key in exp:
+            assert np.array_equal(got[key].reshape(2, -1), exp[key]), key
+        with pytest.raises(ValueError):  # a bin with max_items_per_bin items (receiver_db.cpp:388-389)
+            bins = [[] for _ in range(sc.p.bins_per_bundle)]
+            bins[3] = list(range(sc.p.max_items_per_bin))
+            db.add_bin_bundle_from_bins(0, bins)
+    finally:
+        db.close()
+
+
 def test_error_behaviour_on_device():
     import apsu_b200
     sc = Scenario("256K-512", [[5]], planted=2)
