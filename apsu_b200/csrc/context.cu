@@ -20,6 +20,9 @@ static DMod make_mod(uint64_t q)
     uint64_t lo = (uint64_t)((rem << 64) / q);
     m.r0 = lo;
     m.r1 = hi;
+    m.sh = (u32)(hm::bit_length(q) - 1);
+    m.mu = (uint64_t)(((hm::u128)1 << (64 + m.sh)) / q); // < 2^64 because q > 2^sh (q is not a power of two)
+    m.pad_ = 0;
     return m;
 }
 static DShoup make_shoup(uint64_t v, uint64_t q)
@@ -155,22 +158,27 @@ void DeviceContext::build_levels()
             uint64_t Bq = hm::prod_mod(B, q[i]);
             c.B_mod_q[i] = make_shoup(Bq, q[i]);
             c.neg_B_mod_q[i] = make_shoup((q[i] - Bq) % q[i], q[i]);
-            for (uint32_t k = 0; k < nb; k++) c.B_punct_mod_q[i][k] = hm::prod_mod(B, q[i], (int)k);
+            for (uint32_t k = 0; k < nb; k++) c.B_punct_mod_q[i][k] = make_shoup(hm::prod_mod(B, q[i], (int)k), q[i]);
         }
         c.neg_inv_q_mod_mtilde = (u32)((mt - invm(hm::prod_mod(q, mt), mt)) % mt);
         for (uint32_t j = 0; j < bsk.size(); j++) {
             uint64_t p = bsk[j];
             c.bsk[j] = make_mod(p);
-            for (uint32_t i = 0; i < L; i++) c.q_punct_mod_bsk[j][i] = hm::prod_mod(q, p, (int)i);
             uint64_t qp = hm::prod_mod(q, p);
-            c.q_mod_bsk[j] = make_shoup(qp, p);
-            c.inv_q_mod_bsk[j] = make_shoup(invm(qp, p), p);
-            c.inv_mtilde_mod_bsk[j] = make_shoup(invm(mt % p, p), p);
-            c.t_mod_bsk[j] = make_shoup(t, p);
+            const uint64_t inv_q = invm(qp, p), inv_mt = invm(mt % p, p);
+            for (uint32_t i = 0; i < L; i++) {
+                const uint64_t punct = hm::prod_mod(q, p, (int)i);
+                // extension (steps 1-2): the m_tilde^-1 of the Montgomery reduction folded into the conversion
+                c.ext_punct_bsk[j][i] = make_shoup(mulm(punct, inv_mt, p), p);
+                // fast floor (step 7): -(q/q_i) * q^-1
+                c.floor_punct_bsk[j][i] = make_shoup((p - mulm(punct, inv_q, p)) % p, p);
+            }
+            c.ext_q_bsk[j] = make_shoup(mulm(qp, inv_mt, p), p);
+            c.floor_t_bsk[j] = make_shoup(mulm(t % p, inv_q, p), p);
         }
         for (uint32_t k = 0; k < nb; k++) {
             c.inv_punct_B[k] = make_shoup(invm(hm::prod_mod(B, B[k], (int)k), B[k]), B[k]);
-            c.B_punct_mod_msk[k] = hm::prod_mod(B, msk, (int)k);
+            c.B_punct_mod_msk[k] = make_shoup(hm::prod_mod(B, msk, (int)k), msk);
         }
         c.inv_B_mod_msk = make_shoup(invm(hm::prod_mod(B, msk), msk), msk);
 

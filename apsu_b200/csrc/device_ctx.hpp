@@ -37,21 +37,23 @@ struct LevelConsts {
     u64 half_mod[kMaxQ];
     // BEHZ step 1: x_i * (m_tilde * (q/q_i)^-1) mod q_i
     DShoup mtilde_inv_punct_q[kMaxQ];
-    // (q/q_i) mod Bsk_j, (q/q_i) mod 2^32
-    u64 q_punct_mod_bsk[kMaxBsk][kMaxQ];
+    // steps 1-2 fused: x'_j = sum_i tmp_i * ext_punct_bsk[j][i] + r * ext_q_bsk[j]  (mod Bsk_j) with
+    // ext_punct_bsk = (q/q_i) * m_tilde^-1, ext_q_bsk = q * m_tilde^-1; (q/q_i) mod 2^32 for the m_tilde residue
+    DShoup ext_punct_bsk[kMaxBsk][kMaxQ];
+    DShoup ext_q_bsk[kMaxBsk];
     u32 q_punct_mod_mtilde[kMaxQ];
     u32 neg_inv_q_mod_mtilde;
-    DShoup q_mod_bsk[kMaxBsk];          // q mod Bsk_j
-    DShoup inv_mtilde_mod_bsk[kMaxBsk]; // m_tilde^-1 mod Bsk_j
     // steps 6-8
     DShoup t_mod_q[kMaxQ];              // t mod q_i   (multiply by plain modulus)
-    DShoup t_mod_bsk[kMaxBsk];
     DShoup inv_punct_q[kMaxQ];          // (q/q_i)^-1 mod q_i
     DShoup t_inv_punct_q[kMaxQ];        // t * (q/q_i)^-1 mod q_i
-    DShoup inv_q_mod_bsk[kMaxBsk];      // q^-1 mod Bsk_j
-    DShoup inv_punct_B[kMaxBsk];        // (B/B_i)^-1 mod B_i
-    u64 B_punct_mod_q[kMaxQ][kMaxBsk];  // (B/B_i) mod q_j
-    u64 B_punct_mod_msk[kMaxBsk];       // (B/B_i) mod m_sk
+    // step 7 fused: f_j = d_j * floor_t_bsk[j] + sum_i tmp_i * floor_punct_bsk[j][i]  (mod Bsk_j) with
+    // floor_t_bsk = t * q^-1, floor_punct_bsk = -(q/q_i) * q^-1
+    DShoup floor_t_bsk[kMaxBsk];
+    DShoup floor_punct_bsk[kMaxBsk][kMaxQ];
+    DShoup inv_punct_B[kMaxBsk];           // (B/B_i)^-1 mod B_i
+    DShoup B_punct_mod_q[kMaxQ][kMaxBsk];  // (B/B_i) mod q_j
+    DShoup B_punct_mod_msk[kMaxBsk];       // (B/B_i) mod m_sk
     DShoup inv_B_mod_msk;               // B^-1 mod m_sk
     DShoup B_mod_q[kMaxQ];              // B mod q_j
     DShoup neg_B_mod_q[kMaxQ];          // -B mod q_j

@@ -20,10 +20,20 @@ namespace apsu_b200 {
         note_launch();                                                                                                 \
     } while (0)
 
+// specialised (|q|, |Bsk|) instances of the BEHZ kernels; anything else runs the generic <0,0> instance
+#define APSU_DISPATCH_LS(KERN, L, S, ...)                                                                              \
+    do {                                                                                                               \
+        if ((L) == 1 && (S) == 2) KERN<1, 2> __VA_ARGS__;                                                              \
+        else if ((L) == 2 && (S) == 3) KERN<2, 3> __VA_ARGS__;                                                         \
+        else if ((L) == 3 && (S) == 4) KERN<3, 4> __VA_ARGS__;                                                         \
+        else if ((L) == 4 && (S) == 5) KERN<4, 5> __VA_ARGS__;                                                         \
+        else KERN<0, 0> __VA_ARGS__;                                                                                   \
+    } while (0)
+
 void Engine::run_extend(uint32_t L, uint32_t n, const uint32_t *src, const uint32_t *dst)
 {
     if (!n) return;
-    k_behz_extend<<<dim3(ctx.N / kEwThreads, n), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N);
+    APSU_DISPATCH_LS(k_behz_extend, L, (uint32_t)ctx.level[L].S, <<<dim3(ctx.N / kEwThreads, n), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N));
     APSU_LAUNCH_CHECK();
 }
 void Engine::run_tensor(uint32_t L, uint32_t n_ops, const uint32_t *a, const uint32_t *b, const uint32_t *d)
@@ -36,7 +46,7 @@ void Engine::run_tensor(uint32_t L, uint32_t n_ops, const uint32_t *a, const uin
 void Engine::run_scale_down(uint32_t L, uint32_t n, const uint32_t *src, const uint32_t *dst)
 {
     if (!n) return;
-    k_behz_scale_down<<<dim3(ctx.N / kEwThreads, n), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N);
+    APSU_DISPATCH_LS(k_behz_scale_down, L, (uint32_t)ctx.level[L].S, <<<dim3(ctx.N / kEwThreads, n), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N));
     APSU_LAUNCH_CHECK();
 }
 void Engine::run_ks_mac(uint32_t L, uint32_t n_ops, const uint32_t *dig, const uint32_t *out)

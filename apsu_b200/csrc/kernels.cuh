@@ -13,8 +13,30 @@ namespace apsu_b200 {
 
 
 
+// Base conversions multiply residues by CONSTANTS, so every product is a lazy Shoup product (6 IMAD.WIDE, result in
+// [0, 2m)) and a sum of them is reduced once.  Sums are kept below 8m < 2^64 (m < 2^61): a canonical value plus at
+// most three lazy terms between reductions.
+struct LazySum {
+    u64 s = 0;
+    int pending = 0;
+    __device__ __forceinline__ void add(u64 x, const DShoup &w, u64 m)
+    {
+        s += mul_shoup_lazy(x, w.op, w.quot, m);
+        if (++pending == 3) {
+            s = reduce_8q(s, m);
+            pending = 0;
+        }
+    }
+    __device__ __forceinline__ u64 get(u64 m) const { return pending ? reduce_8q(s, m) : s; }
+};
+
 // ---- BEHZ steps (1)-(2): base q -> base Bsk, Montgomery-reduced (fastbconv_m_tilde + sm_mrq) ----
 // grid (N/256, n_polys).  src[rp] -> first prime of an RNS polynomial [L][N]; dst[rp] -> [S][N].
+// x'_j = (y_j + q*r) * m_tilde^-1 with y = FastBConv(x*m_tilde; q -> Bsk): the m_tilde^-1 is folded into the
+// conversion constants (ext_punct_bsk, ext_q_bsk), everything is arithmetic modulo Bsk_j and the output canonical.
+// TL, TS: compile-time |q| and |Bsk| (0: read them from the constants) — the specialised instances are fully
+// unrolled with no predicated-off work; the engine dispatches on (L, S).
+template <int TL, int TS>
 __global__ void __launch_bounds__(kEwThreads)
 k_behz_extend(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst, LevelConsts c, int N)
 {
@@ -22,27 +44,30 @@ k_behz_extend(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst, 
     const u32 rp = blockIdx.y;
     const u64 *x = A + (size_t)src[rp] * N + n;
     u64 *o = A + (size_t)dst[rp] * N + n;
-    u64 tmp[kMaxQ];
+    const int L = TL ? TL : c.L, S = TS ? TS : c.S;
+    constexpr int ML = TL ? TL : kMaxQ, MS = TS ? TS : kMaxBsk;
+    u64 tmp[ML];
     u32 ymt = 0;
 #pragma unroll
-    for (int i = 0; i < kMaxQ; i++) {
-        if (i < c.L) {
+    for (int i = 0; i < ML; i++) {
+        if (i < L) {
             tmp[i] = mul_shoup(x[(size_t)i * N], c.mtilde_inv_punct_q[i], c.q[i].q);
             ymt += (u32)tmp[i] * c.q_punct_mod_mtilde[i];
         }
     }
     const u32 r = ymt * c.neg_inv_q_mod_mtilde; // arithmetic mod m_tilde = 2^32
-    for (int j = 0; j < c.S; j++) {
-        const DMod m = c.bsk[j];
-        Acc128 acc{ 0, 0 };
 #pragma unroll
-        for (int i = 0; i < kMaxQ; i++)
-            if (i < c.L) mac128(acc, tmp[i], c.q_punct_mod_bsk[j][i]);
-        u64 y = barrett128(acc.lo, acc.hi, m);
+    for (int j = 0; j < MS; j++) {
+        if (j >= S) break;
+        const u64 m = c.bsk[j].q;
+        LazySum acc;
+#pragma unroll
+        for (int i = 0; i < ML; i++)
+            if (i < L) acc.add(tmp[i], c.ext_punct_bsk[j][i], m);
         u64 rr = r;
-        if (r >= 0x80000000u) rr += m.q - 0x100000000ull; // centred lift of r
-        u64 v = add_mod(mul_shoup(rr, c.q_mod_bsk[j], m.q), y, m.q);
-        o[(size_t)j * N] = mul_shoup(v, c.inv_mtilde_mod_bsk[j], m.q);
+        if (r >= 0x80000000u) rr += m - 0x100000000ull; // centred lift of r
+        acc.add(rr, c.ext_q_bsk[j], m);
+        o[(size_t)j * N] = acc.get(m);
     }
 }
 
@@ -64,12 +89,13 @@ k_tensor(u64 *A, const u32 *__restrict__ a_idx, const u32 *__restrict__ b_idx, c
     Acc128 acc{ 0, 0 };
     mac128(acc, a0, b1);
     mac128(acc, a1, b0);
-    d[cs] = barrett128(acc.lo, acc.hi, m);
+    d[cs] = barrett_prod(acc.lo, acc.hi, m); // two products of reduced operands: below 2^(64+sh)
     d[2 * cs] = mul_mod(a1, b1, m);
 }
 
 // ---- BEHZ steps (6)-(8): multiply by t, fast floor (divide by q), Shenoy-Kumaresan back to q ----
 // grid (N/256, n_polys).  src[rp] -> [L+S][N] coefficient form; dst[rp] -> [L][N].
+template <int TL, int TS>
 __global__ void __launch_bounds__(kEwThreads)
 k_behz_scale_down(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst, LevelConsts c, int N)
 {
@@ -77,48 +103,49 @@ k_behz_scale_down(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ d
     const u32 rp = blockIdx.y;
     const u64 *d = A + (size_t)src[rp] * N + n;
     u64 *o = A + (size_t)dst[rp] * N + n;
-    const int L = c.L, S = c.S, nb = c.S - 1;
+    const int L = TL ? TL : c.L, S = TS ? TS : c.S, nb = S - 1;
+    constexpr int kMaxQ = TL ? TL : apsu_b200::kMaxQ, kMaxBsk = TS ? TS : apsu_b200::kMaxBsk; // loop bounds of this instance
     u64 tmp[kMaxQ], f[kMaxBsk];
 #pragma unroll
     for (int i = 0; i < kMaxQ; i++)
         if (i < L) tmp[i] = mul_shoup(d[(size_t)i * N], c.t_inv_punct_q[i], c.q[i].q);
+    // f_j = (t*d_j - FastBConv(t*d_q; q -> Bsk_j)) * q^-1, the q^-1 folded into both constants
 #pragma unroll
     for (int j = 0; j < kMaxBsk; j++) {
         if (j < S) {
-            const DMod m = c.bsk[j];
-            Acc128 acc{ 0, 0 };
+            const u64 m = c.bsk[j].q;
+            LazySum acc;
+            acc.add(d[(size_t)(L + j) * N], c.floor_t_bsk[j], m);
 #pragma unroll
             for (int i = 0; i < kMaxQ; i++)
-                if (i < L) mac128(acc, tmp[i], c.q_punct_mod_bsk[j][i]);
-            u64 conv = barrett128(acc.lo, acc.hi, m);
-            u64 tB = mul_shoup(d[(size_t)(L + j) * N], c.t_mod_bsk[j], m.q);
-            f[j] = mul_shoup(sub_mod(tB, conv, m.q), c.inv_q_mod_bsk[j], m.q);
+                if (i < L) acc.add(tmp[i], c.floor_punct_bsk[j][i], m);
+            f[j] = acc.get(m);
         }
     }
     // Shenoy-Kumaresan
     u64 g[kMaxBsk];
-    Acc128 aacc{ 0, 0 };
-    const DMod msk = c.bsk[S - 1];
+    const u64 msk = c.bsk[S - 1].q;
+    LazySum aacc;
 #pragma unroll
     for (int k = 0; k < kMaxBsk; k++) {
         if (k < nb) {
             g[k] = mul_shoup(f[k], c.inv_punct_B[k], c.bsk[k].q);
-            mac128(aacc, g[k], c.B_punct_mod_msk[k]);
+            aacc.add(g[k], c.B_punct_mod_msk[k], msk);
         }
     }
-    u64 alpha = barrett128(aacc.lo, aacc.hi, msk);
-    alpha = mul_shoup(sub_mod(alpha, f[S - 1], msk.q), c.inv_B_mod_msk, msk.q);
-    const bool neg = alpha > (msk.q >> 1);
-    const u64 corr = neg ? msk.q - alpha : alpha;
-    for (int i = 0; i < L; i++) {
-        const DMod m = c.q[i];
-        Acc128 acc{ 0, 0 };
+    u64 alpha = mul_shoup(sub_mod(aacc.get(msk), f[S - 1], msk), c.inv_B_mod_msk, msk);
+    const bool neg = alpha > (msk >> 1);
+    const u64 corr = neg ? msk - alpha : alpha;
+#pragma unroll
+    for (int i = 0; i < kMaxQ; i++) {
+        if (i >= L) break;
+        const u64 m = c.q[i].q;
+        LazySum acc;
 #pragma unroll
         for (int k = 0; k < kMaxBsk; k++)
-            if (k < nb) mac128(acc, g[k], c.B_punct_mod_q[i][k]);
-        u64 conv = barrett128(acc.lo, acc.hi, m);
-        u64 adj = neg ? mul_shoup(corr, c.B_mod_q[i], m.q) : mul_shoup(corr, c.neg_B_mod_q[i], m.q);
-        o[(size_t)i * N] = add_mod(adj, conv, m.q);
+            if (k < nb) acc.add(g[k], c.B_punct_mod_q[i][k], m);
+        acc.add(corr, neg ? c.B_mod_q[i] : c.neg_B_mod_q[i], m);
+        o[(size_t)i * N] = acc.get(m);
     }
 }
 
@@ -138,7 +165,7 @@ k_ks_mac(u64 *A, const u32 *__restrict__ dig_idx, const u32 *__restrict__ out_id
         u64 kv = keys[(((size_t)J * 2 + comp) * c.K + key_index) * N + n];
         mac128(acc, dg[(size_t)J * R * N], kv);
     }
-    A[((size_t)out_idx[o] + (size_t)comp * R + I) * N + n] = barrett128(acc.lo, acc.hi, c.key_mod[I]);
+    A[((size_t)out_idx[o] + (size_t)comp * R + I) * N + n] = barrett_prod(acc.lo, acc.hi, c.key_mod[I]); // <= 5 products of reduced operands
 }
 
 // ---- key switching: divide by the special prime with rounding and add to (c0, c1) ----

@@ -11,10 +11,14 @@ namespace apsu_b200 {
 using u64 = unsigned long long;
 using u32 = unsigned int;
 
-// modulus with its Barrett constant floor(2^128 / q) (two words)
+// modulus with its Barrett constants: floor(2^128 / q) (two words, for arbitrary 128-bit inputs) and
+// mu = floor(2^(64+sh) / q) with sh = bit_length(q) - 1 (one word, for inputs below 2^(64+sh) such as sums of a
+// few products of reduced operands: barrett_prod)
 struct DMod {
     u64 q;
     u64 r0, r1;
+    u64 mu;
+    u32 sh, pad_;
 };
 
 // constant multiplicand in Shoup form: quot = floor(op * 2^64 / q)
@@ -61,7 +65,27 @@ __device__ __forceinline__ u64 barrett64(u64 x, const DMod &m)
     if (r >= m.q) r -= m.q;
     return r;
 }
-__device__ __forceinline__ u64 mul_mod(u64 a, u64 b, const DMod &m) { return barrett128(a * b, mulhi(a, b), m); }
+// (hi:lo) mod q for (hi:lo) < 2^(64+sh), i.e. hi < 2^sh — products of reduced operands and short sums of them.
+// One 64x64 high product instead of barrett128's four: xh = (hi:lo) >> sh fits a word, qhat = floor(xh*mu/2^64)
+// is at most 2 short of the true quotient (both truncations lose less than 1), hence two conditional subtractions.
+// The integer pipe that executes IMAD.WIDE is what bounds the element-wise kernels, so this matters.
+__device__ __forceinline__ u64 barrett_prod(u64 lo, u64 hi, const DMod &m)
+{
+    const u64 xh = (lo >> m.sh) | (hi << (64 - m.sh));
+    u64 r = lo - mulhi(xh, m.mu) * m.q;
+    if (r >= m.q) r -= m.q;
+    if (r >= m.q) r -= m.q;
+    return r;
+}
+__device__ __forceinline__ u64 mul_mod(u64 a, u64 b, const DMod &m) { return barrett_prod(a * b, mulhi(a, b), m); }
+// [0, 8q) -> [0, q)
+__device__ __forceinline__ u64 reduce_8q(u64 x, u64 q)
+{
+    if (x >= 4 * q) x -= 4 * q;
+    if (x >= 2 * q) x -= 2 * q;
+    if (x >= q) x -= q;
+    return x;
+}
 __device__ __forceinline__ u64 add_mod(u64 a, u64 b, u64 q)
 {
     u64 s = a + b;
