@@ -155,6 +155,50 @@ def synth_query(primes, t, N, first_L, K, nsrc, bic, npack, seed):
     return cts, relin, masks
 
 
+def db_build_measure(pj, name, params, device, with_cpu):
+    """Row f1 (BinBundle::regen_cache, bin_bundle.cpp:934-1041) on the device: one FULL BinBundle (every bin
+    between half and completely full) built from its raw bins — polyn_with_roots, encode, NTT, device store —
+    timed through the C ABI with host inputs; beside it the oracle (one thread, like one regen_cache task) on a
+    bundle with 1/16 of the bins (polyn_with_roots is per bin, so its cost is linear in the bins)."""
+    import apsu_b200
+    rng = np.random.default_rng(SEEDS["db"] + 7)
+    nb, cap, t = params.bins_per_bundle(), params.table_params()["max_items_per_bin"] - 1, params.plain_modulus()
+    loads = rng.integers(cap // 2, cap + 1, size=nb)
+    loads[0] = cap
+    bins = [rng.integers(0, t, size=int(k), dtype=np.uint64) for k in loads]
+    sizes = np.ascontiguousarray(loads, dtype=np.uint32)
+    roots = np.ascontiguousarray(np.concatenate(bins))
+    import ctypes as C
+    from apsu_b200 import capi
+    db = apsu_b200.ReceiverDB(params, device)
+    try:
+        ci = C.c_uint32()
+        ms = []
+        for _ in range(3):
+            capi.check(capi.lib().apsu_b200_db_clear(db._h))
+            t0 = time.perf_counter()
+            capi.check(capi.lib().apsu_b200_db_add_binbundle_from_bins(db._h, 0, sizes, roots, C.byref(ci)))
+            ms.append((time.perf_counter() - t0) * 1e3)
+    finally:
+        db.close()
+    out = {"what": "one full BinBundle from raw bins on the device (apsu_b200_db_add_binbundle_from_bins, host inputs)",
+           "items": int(loads.sum()), "bins": int(nb), "ms": float(min(ms)), "items_per_s": float(loads.sum() / (min(ms) / 1e3))}
+    if with_cpu:
+        from oracle import oracle as O
+        p = O.Params(pj, name + ".json")
+        odb = O.ReceiverDB(O.Context.from_params(p), p)
+        sub = max(1, nb // 16)
+        small = [b.tolist() if i < sub else [] for i, b in enumerate(bins)]
+        small[sub - 1] = bins[0].tolist()  # keep the full degree so that every plaintext is built
+        t0 = time.perf_counter()
+        odb.add_bundle_from_bins(0, small)
+        cms = (time.perf_counter() - t0) * 1e3
+        n_items = sum(len(b) for b in small)
+        out["cpu_port"] = {"what": f"oracle, 1 thread, same bundle with {sub} of {nb} bins populated", "items": int(n_items), "ms": float(cms),
+                           "items_per_s": float(n_items / (cms / 1e3))}
+    return out
+
+
 def cpu_baseline(pj, name, degrees, cts, relin, masks, sample_pairs, threads):
     """Times the oracle (CPU restatement of the reference's SEAL path, oracle/) with all host threads busy on a
     bounded sample of the workload: ComputePowers for ONE bundle index (the reference runs bundle indices
@@ -217,6 +261,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--db-log2", type=int, default=DB_LOG2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-db-build", action="store_true", help="skip the device DB-build measurement (row f1)")
     ap.add_argument("--chunk", type=int, default=None, help="BinBundles per evaluation chunk (APSU_B200_CHUNK)")
     args = ap.parse_args()
     if args.chunk:
@@ -413,6 +458,12 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         mac_gbs = (tm["db_stream_bytes"] / 1e9) / (tm["db_stream_ms"] / 1e3) if tm["db_stream_ms"] else 0.0
+        # DRAM traffic of the same launch from the committed ncu --set full capture (profiles/), per launch
+        traffic = None
+        ts = ROOT / "profiles" / "ncu_r01_k_db_mac_kt_summary.json"
+        if ts.exists() and world == 1 and name == WORKLOAD and args.db_log2 == DB_LOG2:
+            tj = json.loads(ts.read_text())
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         launches = max(tm["db_stream_launches"], 1)
         out = {
             "metric": "receiver_query_eval_binbundles_per_s", "value": n_bundles / (ms_step / 1e3), "unit": "BinBundles/s",
@@ -423,7 +474,7 @@ def main():
             "db_stream": {"bytes_per_query": total_bytes, "bytes_rank0": my_bytes, "effective_gbs_whole_eval": (my_bytes / 1e9) / (tm["eval_ms"] / 1e3) if tm["eval_ms"] else None},
             "roofline": {
                 "kernel": "k_db_mac_kt (DB-stream multiply-accumulate, K1)", "bound": "hbm", "achieved": mac_gbs, "peak": hbm_peak,
-                "unit": "GB/s", "frac": mac_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": mac_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "launches_timed": tm["db_stream_launches"], "avg_launch_ms": tm["db_stream_ms"] / launches,
                 "algorithmic_bytes_per_launch": tm["db_stream_bytes"] / launches,
                 "share_of_step": tm["db_stream_ms"] / (tm["compute_powers_ms"] + tm["eval_ms"]) if tm["eval_ms"] else None,
@@ -447,6 +498,8 @@ def main():
             out["parity_sample"] = {"bundles": sample, "bit_exact_vs_oracle": bool(ok)}
             if not ok:
                 out["INVALID"] = "GPU results differ from the oracle on the sampled BinBundles"
+        if not args.no_db_build and world == 1:
+            out["db_build"] = db_build_measure(pj, name, params, local_rank, not args.no_cpu_baseline)
         print(json.dumps(out))
     db.close()
     if dist is not None:
