@@ -279,6 +279,10 @@ int apsu_b200_encode_masks(apsu_b200_ctx *ctx, const uint64_t *slot_values, uint
 {
     return guarded([&] { E(ctx).encode_masks(slot_values, npack, masks_out); });
 }
+int apsu_b200_generate_masks(apsu_b200_ctx *ctx, uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *random_matrix, uint64_t *slot_values)
+{
+    return guarded([&] { E(ctx).generate_masks(seed, padded, npack, random_matrix, slot_values); });
+}
 int apsu_b200_eval_all(apsu_b200_ctx *ctx)
 {
     return guarded([&] { E(ctx).eval_all(); });

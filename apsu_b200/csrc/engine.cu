@@ -492,6 +492,28 @@ void Engine::encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t 
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
 }
 
+// RunQuery's mask generation on the device (receiver_ddh.cpp:241-283): values, their encodings (kept resident as
+// the masks of the next evaluation) and the PEQT blocks.
+void Engine::generate_masks(uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out)
+{
+    if (!padded || !npack) throw std::invalid_argument("generate_masks: bad arguments");
+    const uint32_t N = ctx.N, ipb = ctx.params.items_per_bundle;
+    DBuf<u64> values, blocks;
+    DBuf<unsigned char> pad;
+    values.alloc((size_t)npack * N);
+    blocks.alloc((size_t)npack * ipb * 2);
+    pad.alloc(npack);
+    masks_.ensure((size_t)npack * N);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(pad.p, padded, npack, cudaMemcpyHostToDevice, ctx.stream));
+    k_gen_masks<<<dim3(N / 256, npack), 256, 0, ctx.stream>>>(values.p, masks_.p, blocks.p, pad.p, ctx.slot_map.p, seed, ctx.t, ctx.params.felts_per_item, ipb, (int)N);
+    APSU_LAUNCH_CHECK();
+    ctx.ntt(masks_.p, masks_.p, npack, { ctx.idx_t }, true);
+    npack_ = npack;
+    if (blocks_out) APSU_CUDA_CHECK(cudaMemcpyAsync(blocks_out, blocks.p, blocks.n * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    if (values_out) APSU_CUDA_CHECK(cudaMemcpyAsync(values_out, values.p, values.n * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+
 void Engine::query_begin(const uint32_t *src_powers, uint32_t nsrc, const void *cts, bool on_device)
 {
     const apsu_b200_params &p = ctx.params;

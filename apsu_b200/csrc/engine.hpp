@@ -86,6 +86,7 @@ public:
     void query_begin(const uint32_t *src_powers, uint32_t nsrc, const void *cts, bool on_device);
     void set_masks(const void *masks, uint32_t npack, bool on_device);
     void encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t *out);
+    void generate_masks(uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out);
     void compute_powers();
     void eval_all();
     void fetch_results(uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);

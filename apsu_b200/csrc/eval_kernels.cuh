@@ -274,6 +274,48 @@ __global__ void k_polyn_with_roots(const u32 *__restrict__ bin_first, const u32 
     for (u32 i = lane; i <= d; i += 32) M[(size_t)i * N + bin] = c[i];
 }
 
+// Mask generation of RunQuery (receiver/apsu/receiver_ddh.cpp:241-283): for every (cache_idx, bundle_idx) pair
+// p = pack index, one value r = prng32 % plain_modulus per slot (generate() yields 32-bit words, :258), scattered to
+// its BatchEncoder position (encode = this scatter + the inverse NTT mod t done by the caller), and the items'
+// 128-bit blocks of the PEQT hand-off (vec_to_std_block, :70-92); padded pairs (:247-252) get all-one blocks and no
+// mask.  The reference seeds SEAL's blake2xb PRNG from random_bytes, so its masks are not reproducible; here
+// word (p, i) of the stream is the low half of splitmix64_at(seed, p*N + i).
+// grid (N/256, npack).  values/scattered: [npack][N]; blocks: [npack][items_per_bundle][2] = (low, high) words.
+__global__ void __launch_bounds__(256)
+k_gen_masks(u64 *__restrict__ values, u64 *__restrict__ scattered, u64 *__restrict__ blocks, const unsigned char *__restrict__ padded, const u32 *__restrict__ map,
+            u64 seed, u64 t, u32 felts_per_item, u32 items_per_bundle, int N)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t p = blockIdx.y;
+    const bool pad = padded[p] != 0;
+    const u64 r = pad ? 0 : (u64)(u32)splitmix64_at(seed, p * (size_t)N + i) % t;
+    values[p * N + i] = r;
+    scattered[p * N + map[i]] = r;
+    if (i < items_per_bundle) {
+        u64 lower = 0, higher = 0;
+        if (pad) {
+            lower = higher = ~0ull; // Block::all_one_block
+        } else {
+            u32 len = 1;
+            while (((1ull << len) - 1) < t) len++;
+            const u64 mask = (1ull << len) - 1, mask_lower = (1ull << (len >> 1)) - 1, mask_higher = mask - mask_lower;
+            const size_t base = p * (size_t)N + (size_t)i * felts_per_item;
+            auto val = [&](u32 j) { return (u64)(u32)splitmix64_at(seed, base + j) % t; };
+            if (felts_per_item & 1) {
+                const u64 v = val(felts_per_item - 1);
+                lower = v & mask_lower;
+                higher = (v & mask_higher) >> ((len >> 1) - 1);
+            }
+            for (u32 pla = 0; pla + 1 < felts_per_item; pla += 2) {
+                lower = (val(pla) & mask) | (lower << len);
+                higher = (val(pla + 1) & mask) | (higher << len);
+            }
+        }
+        blocks[(p * items_per_bundle + i) * 2] = lower;
+        blocks[(p * items_per_bundle + i) * 2 + 1] = higher;
+    }
+}
+
 // BatchEncoder::encode scatter: out[p][map[i]] = values[p][i]
 __global__ void k_slot_scatter(const u64 *__restrict__ values, u64 *__restrict__ out, const u32 *__restrict__ map, int N)
 {

@@ -200,6 +200,21 @@ class Receiver:
         masks = np.ascontiguousarray(masks, dtype=np.uint64)
         capi.check(self._L.apsu_b200_set_masks(self.db._h, masks, masks.shape[0]))
 
+    def generate_masks(self, seed: int, cache_counts=None, want_values: bool = False):
+        """receiver_ddh.cpp:241-283 on the device: draws the masks of every (cache_idx, bundle_idx) pair, keeps their
+        encodings resident for the next evaluation and returns random_matrix [npack][items_per_bundle][2] (low, high
+        words of the PEQT blocks; all ones for padded pairs).  cache_counts[bundle_idx] defaults to the DB's."""
+        bic = self.db.params.bundle_idx_count()
+        if cache_counts is None:
+            cache_counts = [self.db.get_bin_bundle_count(b) for b in range(bic)]
+        alpha = max(max(cache_counts), 1)
+        padded = np.ascontiguousarray([1 if c >= cache_counts[b] else 0 for c in range(alpha) for b in range(bic)], dtype=np.uint8)
+        npack = alpha * bic
+        blocks = np.zeros((npack, self.db.params.items_per_bundle(), 2), dtype=np.uint64)
+        values = np.zeros((npack, self.db.params.poly_modulus_degree()), dtype=np.uint64) if want_values else None
+        capi.check(self._L.apsu_b200_generate_masks(self.db._h, seed, capi.ptr(padded), npack, capi.ptr(blocks), capi.ptr(values)))
+        return (blocks, values) if want_values else blocks
+
     def encode_masks(self, slot_values: np.ndarray) -> np.ndarray:
         v = np.ascontiguousarray(slot_values, dtype=np.uint64)
         out = np.zeros_like(v)

@@ -150,6 +150,16 @@ int apsu_b200_get_power(
  * on the device from slot values uint64_t[npack][N]. */
 int apsu_b200_set_masks(apsu_b200_ctx *ctx, const uint64_t *masks, uint32_t npack);
 int apsu_b200_encode_masks(apsu_b200_ctx *ctx, const uint64_t *slot_values, uint32_t npack, uint64_t *masks_out);
+/* "next" row f3 — the mask generation of RunQuery on the device (receiver_ddh.cpp:241-283): for every pack index
+ * p = bundle_idx + cache_idx*bundle_idx_count with padded[p] == 0, r = prng32 % plain_modulus per slot (:258),
+ * BatchEncoder::encode of it (:275; kept device-resident as the masks of the next evaluation, like
+ * apsu_b200_set_masks) and the 128-bit blocks of the PEQT hand-off, random_matrix[p][item] = vec_to_std_block of the
+ * item's felts (:70-92, :263-270) as (low, high) words; padded pairs (:247-252) get Block::all_one_block.  The
+ * reference draws from SEAL's blake2xb PRNG seeded by random_bytes (:223) and is not reproducible; here word (p, i) is
+ * the low half of splitmix64 at counter p*N + i of `seed`, so that fixed seeds give identical ciphertexts.
+ * random_matrix: [npack][items_per_bundle][2]; slot_values (optional, tests): [npack][N]. */
+int apsu_b200_generate_masks(
+    apsu_b200_ctx *ctx, uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *random_matrix, uint64_t *slot_values);
 /* Receiver::ProcessBinBundleCache for every BinBundle — receiver_ddh.cpp:340-369, 485-535 →
  * BatchedPlaintextPolyn::eval / eval_patstock (bin_bundle.cpp:106-174, 192-360).  Results stay on the
  * device until fetched.  Order of results: bundle_idx major, cache_idx minor. */

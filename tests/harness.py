@@ -111,3 +111,57 @@ class Scenario:
         got = self.ctx.decode(plain)
         exp = self.expected_slots(b, c)
         return bool(np.array_equal(got, exp)), budget, got, exp
+
+
+# ---- row f3: mask generation restated (receiver/apsu/receiver_ddh.cpp:70-92, 241-283) ----
+def splitmix64_at(seed: int, k: np.ndarray) -> np.ndarray:
+    """word k of the counter-based splitmix64 stream (same stream as the synthetic DB fill)."""
+    M = (1 << 64) - 1
+    z = (np.uint64(seed) + (k.astype(np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15))
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def ref_vec_to_std_block(vals, felts_per_item: int, plain_modulus: int):
+    """vec_to_std_block (receiver_ddh.cpp:70-92) on Python ints -> (low, high) 64-bit words of the block."""
+    ln = 1
+    while ((1 << ln) - 1) < plain_modulus:
+        ln += 1
+    mask = (1 << ln) - 1
+    mask_lower = (1 << (ln >> 1)) - 1
+    mask_higher = mask - mask_lower
+    lower = higher = 0
+    if felts_per_item & 1:
+        lower = vals[felts_per_item - 1] & mask_lower
+        higher = (vals[felts_per_item - 1] & mask_higher) >> ((ln >> 1) - 1)
+    for pla in range(0, felts_per_item - 1, 2):
+        lower = (vals[pla] & mask) | (lower << ln)
+        higher = (vals[pla + 1] & mask) | (higher << ln)
+    return lower & ((1 << 64) - 1), higher & ((1 << 64) - 1)
+
+
+def ref_generate_masks(p, seed: int, cache_counts):
+    """-> (values [npack][N], blocks [npack][items_per_bundle][2], padded [npack]) in pack order
+    p = bundle_idx + cache_idx * bundle_idx_count (receiver_ddh.cpp:243-246, 346)."""
+    bic, N = p.bundle_idx_count, p.N
+    alpha = max(max(cache_counts), 1)
+    npack = alpha * bic
+    with np.errstate(over="ignore"):
+        words = splitmix64_at(seed, np.arange(npack * N, dtype=np.uint64)) & np.uint64(0xFFFFFFFF)
+    values = (words % np.uint64(p.t)).reshape(npack, N)
+    ipb = p.N // p.felts_per_item
+    blocks = np.zeros((npack, ipb, 2), dtype=np.uint64)
+    padded = np.zeros(npack, dtype=bool)
+    for c in range(alpha):
+        for b in range(bic):
+            k = b + c * bic
+            if c >= cache_counts[b]:
+                padded[k] = True
+                values[k] = 0
+                blocks[k] = np.uint64((1 << 64) - 1)
+                continue
+            for i in range(ipb):
+                lo, hi = ref_vec_to_std_block([int(v) for v in values[k, i * p.felts_per_item:(i + 1) * p.felts_per_item]], p.felts_per_item, p.t)
+                blocks[k, i] = (lo, hi)
+    return values, blocks, padded

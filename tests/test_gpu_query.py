@@ -201,6 +201,37 @@ def test_db_build_on_device(name, degrees):
         db.close()
 
 
+@pytest.mark.parametrize("name,degrees", [("1M-4096-com", [[30, 9], [20], [], [12], [18]]), ("256K-512", [[20]]), ("16M-4096", [[50], [], [46, 3], []])])
+def test_mask_generation_on_device(name, degrees):
+    """row f3: masks drawn, encoded and packed into PEQT blocks on the device (receiver_ddh.cpp:241-283) equal the
+    restatement; a query evaluated with the device-resident masks equals one given the same masks explicitly."""
+    import apsu_b200
+    from harness import ref_generate_masks
+    sc = Scenario(name, degrees, planted=4)
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0)
+    try:
+        _upload(sc, db)
+        rx = apsu_b200.Receiver(db)
+        counts = [len(d) for d in degrees]
+        blocks, values = rx.generate_masks(0x4D4D, want_values=True)
+        rvalues, rblocks, padded = ref_generate_masks(sc.p, 0x4D4D, counts)
+        assert np.array_equal(values, rvalues)
+        assert np.array_equal(blocks, rblocks)
+        # evaluate with the resident masks, then with the same masks passed in
+        q = apsu_b200.Query(sc.src_powers, sc.cts, sc.relin)
+        rx.load_query(q)
+        rx.ComputePowers()
+        rx.ProcessBinBundleCaches()
+        got = {(r.bundle_idx, r.cache_idx): r.psu_result.copy() for r in rx.results()}
+        masks = np.stack([sc.ctx.encode(v) for v in rvalues])
+        again = {(r.bundle_idx, r.cache_idx): r.psu_result for r in rx.RunQuery(q, masks)}
+        assert set(got) == set(again) and len(got) == sum(counts)
+        for key in got:
+            assert np.array_equal(got[key], again[key]), key
+    finally:
+        db.close()
+
+
 def test_error_behaviour_on_device():
     import apsu_b200
     sc = Scenario("256K-512", [[5]], planted=2)
