@@ -13,16 +13,16 @@ namespace apsu_b200 {
 
 
 
-// Base conversions multiply residues by CONSTANTS, so every product is a lazy Shoup product (6 IMAD.WIDE, result in
-// [0, 2m)) and a sum of them is reduced once.  Sums are kept below 8m < 2^64 (m < 2^61): a canonical value plus at
-// most three lazy terms between reductions.
+// Base conversions multiply residues by CONSTANTS, so every product is a lazy Shoup product (mul_shoup_lazy3: 4 IMAD.WIDE
+// + 1 IMAD.HI, result in [0, 3m)) and a sum of them is reduced once.  Sums are kept below 8m < 2^64 (m < 2^61): a
+// canonical value plus at most two lazy terms between reductions.
 struct LazySum {
     u64 s = 0;
     int pending = 0;
     __device__ __forceinline__ void add(u64 x, const DShoup &w, u64 m)
     {
-        s += mul_shoup_lazy(x, w.op, w.quot, m);
-        if (++pending == 3) {
+        s += mul_shoup_lazy3(x, w.op, w.quot, 0 - m);
+        if (++pending == 2) {
             s = reduce_8q(s, m);
             pending = 0;
         }

@@ -30,6 +30,55 @@ __device__ __forceinline__ u64 mulhi(u64 a, u64 b) { return __umul64hi(a, b); }
 
 // x * w mod q for x < 2^64, result in [0, 2q)
 __device__ __forceinline__ u64 mul_shoup_lazy(u64 x, u64 w, u64 wq, u64 q) { return w * x - mulhi(x, wq) * q; }
+// x * w mod q for ANY x < 2^64 with an approximate quotient: result in [0, 3q).  nq = 2^64 - q, wq = floor(w*2^64/q).
+// The quotient estimate drops the low x low partial product (at most 1 short), and the remainder is formed as
+// lo64(w*x + qhat*nq): 4 IMAD.WIDE + 1 IMAD.HI + 4 IMAD in SASS instead of the 6 IMAD.WIDE + 4 IMAD + carries of the
+// exact form.  The integer-multiply pipe (IMAD.WIDE issues at quarter rate on sm_100a) is what bounds the NTT, so
+// the butterflies use this form and keep their values in [0, 6q) (q < 2^61.4).
+__device__ __forceinline__ u64 mul_shoup_lazy3(u64 y, u64 w, u64 wq, u64 nq)
+{
+    const u32 yl = (u32)y, yh = (u32)(y >> 32), wl = (u32)w, wh = (u32)(w >> 32), vl = (u32)wq, vh = (u32)(wq >> 32), nl = (u32)nq, nh = (u32)(nq >> 32);
+    u32 a0, a1, s0, s1, c, q0, q1, r0, r1;
+    asm("{\n\t"
+        "mul.lo.u32 %0, %8, %11;\n\t"         // A = yh*vl
+        "mul.hi.u32 %1, %8, %11;\n\t"
+        "mad.lo.cc.u32 %2, %7, %12, %0;\n\t"  // S = yl*vh + A, carry c
+        "madc.hi.cc.u32 %3, %7, %12, %1;\n\t"
+        "addc.u32 %4, 0, 0;\n\t"
+        "mad.lo.cc.u32 %5, %8, %12, %3;\n\t"  // Q = yh*vh + (S.hi : c)
+        "madc.hi.u32 %6, %8, %12, %4;\n\t"
+        "}"
+        : "=&r"(a0), "=&r"(a1), "=&r"(s0), "=&r"(s1), "=&r"(c), "=&r"(q0), "=&r"(q1)
+        : "r"(yl), "r"(yh), "r"(wl), "r"(wh), "r"(vl), "r"(vh));
+    asm("{\n\t"
+        "mul.lo.u32 %0, %4, %2;\n\t"          // R = wl*yl
+        "mul.hi.u32 %1, %4, %2;\n\t"
+        "mad.lo.cc.u32 %0, %6, %8, %0;\n\t"   // R += q0*nl
+        "madc.hi.u32 %1, %6, %8, %1;\n\t"
+        "mad.lo.u32 %1, %4, %3, %1;\n\t"      // hi word += wl*yh + wh*yl + q0*nh + q1*nl
+        "mad.lo.u32 %1, %5, %2, %1;\n\t"
+        "mad.lo.u32 %1, %6, %9, %1;\n\t"
+        "mad.lo.u32 %1, %7, %8, %1;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(yl), "r"(yh), "r"(wl), "r"(wh), "r"(q0), "r"(q1), "r"(nl), "r"(nh));
+    return ((u64)r1 << 32) | r0;
+}
+// x >= m ? x - m : x with the selection on the borrow of the subtraction (IADD3, IADD3.X, 2 SEL)
+__device__ __forceinline__ u64 csub(u64 x, u64 m)
+{
+    u32 xl = (u32)x, xh = (u32)(x >> 32), ml = (u32)m, mh = (u32)(m >> 32), dl, dh, b;
+    asm("{\n\t"
+        "sub.cc.u32 %0, %3, %5;\n\t"
+        "subc.cc.u32 %1, %4, %6;\n\t"
+        "subc.u32 %2, 0, 0;\n\t" // all ones when x < m
+        "}"
+        : "=r"(dl), "=r"(dh), "=r"(b)
+        : "r"(xl), "r"(xh), "r"(ml), "r"(mh));
+    dl = b ? xl : dl;
+    dh = b ? xh : dh;
+    return ((u64)dh << 32) | dl;
+}
 // result in [0, q)
 __device__ __forceinline__ u64 mul_shoup(u64 x, u64 w, u64 wq, u64 q)
 {
@@ -79,13 +128,8 @@ __device__ __forceinline__ u64 barrett_prod(u64 lo, u64 hi, const DMod &m)
 }
 __device__ __forceinline__ u64 mul_mod(u64 a, u64 b, const DMod &m) { return barrett_prod(a * b, mulhi(a, b), m); }
 // [0, 8q) -> [0, q)
-__device__ __forceinline__ u64 reduce_8q(u64 x, u64 q)
-{
-    if (x >= 4 * q) x -= 4 * q;
-    if (x >= 2 * q) x -= 2 * q;
-    if (x >= q) x -= q;
-    return x;
-}
+__device__ __forceinline__ u64 csub(u64 x, u64 m);
+__device__ __forceinline__ u64 reduce_8q(u64 x, u64 q) { return csub(csub(csub(x, 4 * q), 2 * q), q); }
 __device__ __forceinline__ u64 add_mod(u64 a, u64 b, u64 q)
 {
     u64 s = a + b;

@@ -1,6 +1,7 @@
 // Negacyclic NTT / inverse NTT over one RNS prime, N in {2048, 4096, 8192, ...}: one CTA per
 // polynomial, the whole polynomial staged in shared memory, radix-2^R butterflies done in
-// registers between shared-memory exchanges (kernels K2/K3 of SURVEY.md §2.2).
+// registers between shared-memory exchanges (kernels K2/K3 of SURVEY.md §2.2).  The transform is bound by the
+// integer-multiply pipe (ncu: fmaheavy 65-74 %, DRAM 8 %), so the butterfly is built for few IMAD.WIDE.
 //
 // Convention (SEAL 3.7): psi = minimal primitive 2N-th root; forward = Cooley-Tukey,
 // natural-order input, bit-reversed output, out[k] = a(psi^(2*bitrev(k)+1)); inverse =
@@ -18,8 +19,10 @@ struct NttSrc {
     int reduce_input;        // reduce every input word modulo the target modulus first
 };
 
+// Butterflies with the 3q-lazy Shoup product (modarith.cuh: mul_shoup_lazy3): forward values live in [0, 6q),
+// inverse values in [0, 3q); nq = 2^64 - q, q3 = 3q (q < 2^61.4, so 6q fits a word).
 template <int R>
-__device__ __forceinline__ void fwd_group(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, unsigned hi, int s, u64 q, u64 two_q)
+__device__ __forceinline__ void fwd_group(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, unsigned hi, int s, u64 nq, u64 q3)
 {
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -29,17 +32,16 @@ __device__ __forceinline__ void fwd_group(u64 (&x)[1 << R], const ulonglong2 *__
         for (int k = 0; k < (1 << R); k++) {
             if (k & d) continue;
             ulonglong2 w = __ldg(&tw[mbase + (k >> (R - r))]);
-            u64 u = x[k];
-            if (u >= two_q) u -= two_q;
-            u64 v = mul_shoup_lazy(x[k + d], w.x, w.y, q);
-            x[k] = u + v;
-            x[k + d] = u + two_q - v;
+            const u64 u = csub(x[k], q3);                              // [0, 3q)
+            const u64 v = mul_shoup_lazy3(x[k + d], w.x, w.y, nq);     // [0, 3q)
+            x[k] = u + v;                                              // [0, 6q)
+            x[k + d] = u + q3 - v;                                     // (0, 6q)
         }
     }
 }
 
 template <int R>
-__device__ __forceinline__ void inv_group(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, unsigned hi, int s, u64 q, u64 two_q)
+__device__ __forceinline__ void inv_group(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, unsigned hi, int s, u64 nq, u64 q3)
 {
 #pragma unroll
     for (int r = R - 1; r >= 0; r--) {
@@ -49,11 +51,9 @@ __device__ __forceinline__ void inv_group(u64 (&x)[1 << R], const ulonglong2 *__
         for (int k = 0; k < (1 << R); k++) {
             if (k & d) continue;
             ulonglong2 w = __ldg(&tw[mbase + (k >> (R - r))]);
-            u64 u = x[k], v = x[k + d];
-            u64 sum = u + v;
-            if (sum >= two_q) sum -= two_q;
-            x[k] = sum;
-            x[k + d] = mul_shoup_lazy(u + two_q - v, w.x, w.y, q);
+            const u64 u = x[k], v = x[k + d];                          // [0, 3q)
+            x[k] = csub(u + v, q3);                                    // [0, 3q)
+            x[k + d] = mul_shoup_lazy3(u + q3 - v, w.x, w.y, nq);      // [0, 3q)
         }
     }
 }
@@ -65,7 +65,7 @@ __device__ __forceinline__ unsigned pad_idx(unsigned i) { return i + (i >> 4); }
 
 // one pass over stages [s, s+R) on the shared-memory polynomial
 template <int LOGN, int R, bool FWD>
-__device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict__ tw, int s, u64 q, u64 two_q)
+__device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict__ tw, int s, u64 nq, u64 q3)
 {
     constexpr int N = 1 << LOGN;
     const int log_stride = LOGN - s - R;
@@ -77,9 +77,9 @@ __device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict_
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) x[k] = sm[pad_idx(base + k * stride)];
         if (FWD)
-            fwd_group<R>(x, tw, hi, s, q, two_q);
+            fwd_group<R>(x, tw, hi, s, nq, q3);
         else
-            inv_group<R>(x, tw, hi, s, q, two_q);
+            inv_group<R>(x, tw, hi, s, nq, q3);
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) sm[pad_idx(base + k * stride)] = x[k];
     }
@@ -89,15 +89,15 @@ __device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict_
 // the inverse transform runs the same passes in the opposite order
 template <int LOGN, bool FWD, int S, int COUNT>
 struct MidRunner {
-    __device__ static __forceinline__ void run(u64 *sm, const ulonglong2 *tw, u64 q, u64 two_q)
+    __device__ static __forceinline__ void run(u64 *sm, const ulonglong2 *tw, u64 nq, u64 q3)
     {
         if (FWD) {
-            smem_pass<LOGN, 3, true>(sm, tw, S, q, two_q);
+            smem_pass<LOGN, 3, true>(sm, tw, S, nq, q3);
             __syncthreads();
-            MidRunner<LOGN, FWD, S + 3, COUNT - 1>::run(sm, tw, q, two_q);
+            MidRunner<LOGN, FWD, S + 3, COUNT - 1>::run(sm, tw, nq, q3);
         } else {
-            MidRunner<LOGN, FWD, S + 3, COUNT - 1>::run(sm, tw, q, two_q);
-            smem_pass<LOGN, 3, false>(sm, tw, S, q, two_q);
+            MidRunner<LOGN, FWD, S + 3, COUNT - 1>::run(sm, tw, nq, q3);
+            smem_pass<LOGN, 3, false>(sm, tw, S, nq, q3);
             __syncthreads();
         }
     }
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1 << (14 - LOGN))) ntt_kern
     const unsigned p = blockIdx.x;
     const int slot = p % a.pattern_len;
     const DMod m = a.mod[slot];
-    const u64 q = m.q, two_q = 2 * m.q;
+    const u64 q = m.q, nq = 0 - m.q, q3 = 3 * m.q;
     const ulonglong2 *tw = a.tw + ((size_t)a.table[slot] * 2 + (FWD ? 0 : 1)) * N;
     const u64 *ip = in + (size_t)(src.src_idx ? src.src_idx[p] : p) * N;
     u64 *op = out + (size_t)(src.dst_idx ? src.dst_idx[p] : p) * N;
@@ -137,24 +137,21 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1 << (14 - LOGN))) ntt_kern
                     u64 v = ip[g + k * stride];
                     x[k] = reduce ? barrett64(v, m) : v;
                 }
-                fwd_group<RF>(x, tw, 0, 0, q, two_q);
+                fwd_group<RF>(x, tw, 0, 0, nq, q3);
 #pragma unroll
                 for (int k = 0; k < (1 << RF); k++) sm[pad_idx(g + k * stride)] = x[k];
             }
         }
         __syncthreads();
-        MidRunner<LOGN, true, RF, MID>::run(sm, tw, q, two_q);
+        MidRunner<LOGN, true, RF, MID>::run(sm, tw, nq, q3);
         // stages [LOGN-3, LOGN): shared -> registers -> global, fully reduced
         for (unsigned g = threadIdx.x; g < (N >> 3); g += blockDim.x) {
             u64 x[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = sm[pad_idx(8 * g + k)];
-            fwd_group<3>(x, tw, g, LOGN - 3, q, two_q);
+            fwd_group<3>(x, tw, g, LOGN - 3, nq, q3);
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (x[k] >= two_q) x[k] -= two_q;
-                if (x[k] >= q) x[k] -= q;
-            }
+            for (int k = 0; k < 8; k++) x[k] = csub(csub(csub(x[k], q3), 2 * q), q); // [0, 6q) -> [0, q)
             ulonglong2 *o2 = reinterpret_cast<ulonglong2 *>(op + 8 * g);
 #pragma unroll
             for (int k = 0; k < 4; k++) o2[k] = make_ulonglong2(x[2 * k], x[2 * k + 1]);
@@ -170,12 +167,12 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1 << (14 - LOGN))) ntt_kern
                 x[2 * k] = reduce ? barrett64(v.x, m) : v.x;
                 x[2 * k + 1] = reduce ? barrett64(v.y, m) : v.y;
             }
-            inv_group<3>(x, tw, g, LOGN - 3, q, two_q);
+            inv_group<3>(x, tw, g, LOGN - 3, nq, q3);
 #pragma unroll
             for (int k = 0; k < 8; k++) sm[pad_idx(8 * g + k)] = x[k];
         }
         __syncthreads();
-        MidRunner<LOGN, false, RF, MID>::run(sm, tw, q, two_q);
+        MidRunner<LOGN, false, RF, MID>::run(sm, tw, nq, q3);
         // stages [0, RF) last, then the N^-1 scaling: shared -> registers -> global
         const DShoup inv_n = a.inv_n[slot];
         constexpr unsigned stride = N >> RF;
@@ -183,7 +180,7 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1 << (14 - LOGN))) ntt_kern
             u64 x[1 << RF];
 #pragma unroll
             for (int k = 0; k < (1 << RF); k++) x[k] = sm[pad_idx(g + k * stride)];
-            inv_group<RF>(x, tw, 0, 0, q, two_q);
+            inv_group<RF>(x, tw, 0, 0, nq, q3);
 #pragma unroll
             for (int k = 0; k < (1 << RF); k++) op[g + k * stride] = mul_shoup(x[k], inv_n, q);
         }
