@@ -91,6 +91,7 @@ void DeviceContext::build_moduli()
     std::vector<ulonglong2> tw(M * 2 * N);
     mod_host.resize(M);
     inv_n_host.resize(M);
+    inv_n_w_host.resize(M);
     for (size_t m = 0; m < M; m++) {
         uint64_t q = mod_values[m];
         mod_host[m] = make_mod(q);
@@ -105,6 +106,8 @@ void DeviceContext::build_moduli()
             b = mulm(b, ipsi, q);
         }
         inv_n_host[m] = make_shoup(invm(N % q, q), q);
+        // inverse table entry 1 = psi^-bitrev(1) = psi^-(N/2): the only twiddle of the last Gentleman-Sande stage
+        inv_n_w_host[m] = make_shoup(mulm(tw[(m * 2 + 1) * N + 1].x, invm(N % q, q), q), q);
     }
     twiddles.upload(tw, stream);
 
@@ -236,6 +239,7 @@ NttArgs DeviceContext::make_args(const std::vector<uint32_t> &pattern) const
         if (pattern[i] >= mod_values.size()) throw std::invalid_argument("NTT modulus index is out of range");
         a.mod[i] = mod_host[pattern[i]];
         a.inv_n[i] = inv_n_host[pattern[i]];
+        a.inv_n_w[i] = inv_n_w_host[pattern[i]];
         a.table[i] = (int)pattern[i];
     }
     return a;

@@ -80,7 +80,7 @@ public:
     std::vector<uint64_t> mod_values;
     uint32_t idx_msk = 0, idx_B0 = 0, idx_t = 0, nB = 0;
     std::vector<DMod> mod_host;
-    std::vector<DShoup> inv_n_host;
+    std::vector<DShoup> inv_n_host, inv_n_w_host;
     DBuf<ulonglong2> twiddles; // [modulus][2][N]
     DBuf<uint32_t> slot_map;   // BatchEncoder index map
 

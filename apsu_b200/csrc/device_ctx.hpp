@@ -20,6 +20,7 @@ struct NttArgs {
     const ulonglong2 *tw; // [modulus][fwd|inv][N] Shoup pairs, bit-reversed order
     DMod mod[kMaxPattern];
     DShoup inv_n[kMaxPattern];
+    DShoup inv_n_w[kMaxPattern]; // N^-1 times the twiddle of the last inverse stage (psi^-(N/2)): the scaling rides on that stage
     int table[kMaxPattern]; // modulus-table index (for the twiddle offset)
     int pattern_len;
 };

@@ -58,6 +58,25 @@ __device__ __forceinline__ void inv_group(u64 (&x)[1 << R], const ulonglong2 *__
     }
 }
 
+// stages R-1 .. 1 of the first (last executed) inverse group, i.e. inv_group without its stage-0 butterflies
+template <int R>
+__device__ __forceinline__ void inv_group_upper(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, u64 nq, u64 q3)
+{
+#pragma unroll
+    for (int r = R - 1; r >= 1; r--) {
+        const int d = 1 << (R - 1 - r);
+        const unsigned mbase = 1u << r;
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) {
+            if (k & d) continue;
+            ulonglong2 w = __ldg(&tw[mbase + (k >> (R - r))]);
+            const u64 u = x[k], v = x[k + d];
+            x[k] = csub(u + v, q3);
+            x[k + d] = mul_shoup_lazy3(u + q3 - v, w.x, w.y, nq);
+        }
+    }
+}
+
 // Shared-memory layout: one pad word after every 16 coefficients.  The butterflies of the late passes
 // touch coefficients at strides 1..8; with the pad a half-warp's 16 eight-byte accesses fall into 16
 // distinct bank pairs instead of colliding 8-way (measured: 54% of LSU wavefronts were bank conflicts).
@@ -173,16 +192,25 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1 << (14 - LOGN))) ntt_kern
         }
         __syncthreads();
         MidRunner<LOGN, false, RF, MID>::run(sm, tw, nq, q3);
-        // stages [0, RF) last, then the N^-1 scaling: shared -> registers -> global
-        const DShoup inv_n = a.inv_n[slot];
+        // stages [0, RF) last: shared -> registers -> global.  The N^-1 scaling rides on the very last stage (one
+        // twiddle, psi^-(N/2)): x[k] = (u+v)*N^-1, x[k+d] = (u-v)*(w*N^-1), two lazy products instead of one lazy and
+        // two exact ones
+        const DShoup inv_n = a.inv_n[slot], inv_n_w = a.inv_n_w[slot];
         constexpr unsigned stride = N >> RF;
         for (unsigned g = threadIdx.x; g < stride; g += blockDim.x) {
             u64 x[1 << RF];
 #pragma unroll
             for (int k = 0; k < (1 << RF); k++) x[k] = sm[pad_idx(g + k * stride)];
-            inv_group<RF>(x, tw, 0, 0, nq, q3);
+            inv_group_upper<RF>(x, tw, nq, q3); // stages RF-1 .. 1
+            constexpr int d = 1 << (RF - 1);
 #pragma unroll
-            for (int k = 0; k < (1 << RF); k++) op[g + k * stride] = mul_shoup(x[k], inv_n, q);
+            for (int k = 0; k < d; k++) {
+                const u64 u = x[k], v = x[k + d];
+                const u64 lo = mul_shoup_lazy3(u + v, inv_n.op, inv_n.quot, nq);
+                const u64 hi = mul_shoup_lazy3(u + q3 - v, inv_n_w.op, inv_n_w.quot, nq);
+                op[g + k * stride] = csub(csub(lo, 2 * q), q);
+                op[g + (k + d) * stride] = csub(csub(hi, 2 * q), q);
+            }
         }
     }
 }
