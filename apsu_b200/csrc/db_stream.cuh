@@ -159,18 +159,22 @@ __device__ __forceinline__ void kt_load(KtRegs &r, const u64 *sb)
 }
 // MASKED: term t0+h of job k only counts while t0+h < nt[k] (ragged groups and the last, partial stage); the
 // shared-memory words of absent terms are stale and are multiplied by zero
+// lo + hi as a THREE-input add with a run-time zero: ptxas turns a plain two-input 32-bit add into IMAD.IADD to
+// "balance" the pipes, but the FMA-heavy pipe (IMAD.WIDE) is exactly what bounds this kernel; IADD3 runs on the ALU
+__device__ __forceinline__ u32 add3(u32 a, u32 b, u32 zero) { return a + b + zero; }
+
 template <bool MASKED>
-__device__ __forceinline__ void kt_mac(const KtRegs &r, AccK (&acc)[kKtG][2], const u32 (&nt)[kKtG], u32 t0)
+__device__ __forceinline__ void kt_mac(const KtRegs &r, AccK (&acc)[kKtG][2], const u32 (&nt)[kKtG], u32 t0, u32 zero)
 {
 #pragma unroll
     for (int h = 0; h < kKtTS; h++) {
         const u32 p0l = (u32)r.p[h][0], p0h = (u32)(r.p[h][0] >> 32), p1l = (u32)r.p[h][1], p1h = (u32)(r.p[h][1] >> 32);
-        const u32 p0s = p0l + p0h, p1s = p1l + p1h;
+        const u32 p0s = add3(p0l, p0h, zero), p1s = add3(p1l, p1h, zero);
 #pragma unroll
         for (int k = 0; k < kKtG; k++) {
             u64 w = r.w[k][h];
             if (MASKED) w = (t0 + h < nt[k]) ? w : 0ull;
-            const u32 wl = (u32)w, wh = (u32)(w >> 32), ws = wl + wh;
+            const u32 wl = (u32)w, wh = (u32)(w >> 32), ws = add3(wl, wh, zero);
             mac_k(acc[k][0], wl, wh, ws, p0l, p0h, p0s);
             mac_k(acc[k][1], wl, wh, ws, p1l, p1h, p1s);
         }
@@ -182,10 +186,10 @@ __device__ __forceinline__ void kt_mac(const KtRegs &r, AccK (&acc)[kKtG][2], co
 // ring never drains between items (the producer prefetches the next item while the consumers reduce and
 // store the current one).
 // split = bit position the operands were split at; fold_stages = ring stages between lane folds (host:
-// largest count for which the kk lane cannot overflow, from the bit size of the largest prime).
+// largest count for which the kk lane cannot overflow, from the bit size of the largest prime); zero = 0 (see add3).
 template <int STAGES, int MINB>
 __global__ void __launch_bounds__(kKtThreads, MINB)
-k_db_mac_kt(u64 *A, const KtGroup *__restrict__ groups, u32 n_groups, LevelConsts c, int N, int split, u32 fold_stages)
+k_db_mac_kt(u64 *A, const KtGroup *__restrict__ groups, u32 n_groups, LevelConsts c, int N, int split, u32 fold_stages, u32 zero)
 {
     extern __shared__ __align__(128) u64 smem[];
     u64 *ring = smem;                              // [stage][kKtStageWords]
@@ -278,7 +282,7 @@ k_db_mac_kt(u64 *A, const KtGroup *__restrict__ groups, u32 n_groups, LevelConst
                 kt_load(r, ring + (size_t)s * kKtStageWords + tid);
                 __syncwarp();
                 if (lane0) mbar_arrive(&empty[s]); // the stage is in registers: hand it back before the MACs
-                kt_mac<false>(r, acc, nt, 0);
+                kt_mac<false>(r, acc, nt, 0, zero);
             }
 #pragma unroll 1
             for (u32 st = p1; st < b1; st++, it++) {
@@ -288,7 +292,7 @@ k_db_mac_kt(u64 *A, const KtGroup *__restrict__ groups, u32 n_groups, LevelConst
                 kt_load(r, ring + (size_t)s * kKtStageWords + tid);
                 __syncwarp();
                 if (lane0) mbar_arrive(&empty[s]);
-                kt_mac<true>(r, acc, nt, st * kKtTS);
+                kt_mac<true>(r, acc, nt, st * kKtTS, zero);
             }
             if (b1 < nst) {
 #pragma unroll

@@ -1030,7 +1030,7 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<KtGroup> &grou
         APSU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device));
         const uint32_t items = n * (L * ctx.N / kKtCols);
         const uint32_t grid = std::min<uint32_t>(items, (uint32_t)(sms * per_sm));
-        kern<<<grid, kKtThreads, smem, ctx.stream>>>(arena_.buf.p, gd, n, ctx.level[L], (int)ctx.N, split_, fold_stages_);
+        kern<<<grid, kKtThreads, smem, ctx.stream>>>(arena_.buf.p, gd, n, ctx.level[L], (int)ctx.N, split_, fold_stages_, 0u);
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;
         if (timed) {

@@ -177,7 +177,7 @@ static void run(Timer &tm, const Scenario &sc)
     CK(cudaFuncGetAttributes(&fa, kern));
     const u32 items = (u32)groups.size() * ntiles;
     const u32 grid = std::min<u32>(items, g_sms * per_sm);
-    float ms = tm.run([&] { kern<<<grid, kKtThreads, smem>>>(A, gd, (u32)groups.size(), c, (int)N, split, fold_stages); });
+    float ms = tm.run([&] { kern<<<grid, kKtThreads, smem>>>(A, gd, (u32)groups.size(), c, (int)N, split, fold_stages, 0u); });
 
     std::vector<u64> h(owords);
     CK(cudaMemcpy(h.data(), A + pwords, owords * 8, cudaMemcpyDeviceToHost));
