@@ -279,6 +279,22 @@ int apsu_b200_encode_masks(apsu_b200_ctx *ctx, const uint64_t *slot_values, uint
 {
     return guarded([&] { E(ctx).encode_masks(slot_values, npack, masks_out); });
 }
+int apsu_b200_set_powers_partition(apsu_b200_ctx *ctx, uint32_t rank, uint32_t size)
+{
+    return guarded([&] { E(ctx).set_powers_partition(rank, size); });
+}
+int apsu_b200_powers_stage_count(apsu_b200_ctx *ctx, uint32_t *count)
+{
+    return guarded([&] { *need(count, "count") = E(ctx).powers_stage_count(); });
+}
+int apsu_b200_compute_powers_stage(apsu_b200_ctx *ctx, uint32_t stage)
+{
+    return guarded([&] { E(ctx).compute_powers_stage(stage); });
+}
+int apsu_b200_powers_exchange_regions(apsu_b200_ctx *ctx, uint32_t level, void **device_ptrs, uint64_t *chunk_bytes, uint32_t capacity, uint32_t *count)
+{
+    return guarded([&] { *need(count, "count") = E(ctx).powers_exchange_regions(level, device_ptrs, chunk_bytes, capacity); });
+}
 int apsu_b200_generate_masks(apsu_b200_ctx *ctx, uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *random_matrix, uint64_t *slot_values)
 {
     return guarded([&] { E(ctx).generate_masks(seed, padded, npack, random_matrix, slot_values); });

@@ -566,14 +566,28 @@ void Engine::build_plan()
     std::vector<std::vector<uint32_t>> loc(bic, std::vector<uint32_t>(maxp + 1, kNoSrc)); // [2][Lf][N] at first level
     for (uint32_t k = 0; k < nsrc; k++)
         for (uint32_t b = 0; b < bic; b++) loc[b][sources[k]] = query_region_ + (k * bic + b) * 2 * Lf;
+    // Products live level by level, node by node, in one contiguous region per (level, bundle index): with the
+    // PowersDag split over `powers_part_size_` ranks rank r computes the nodes of its chunk
+    // [r*chunk, (r+1)*chunk) of every level and the region is exactly the all-gather buffer of that level.
+    const uint32_t part = std::max<uint32_t>(1, powers_part_size_), prank = powers_part_rank_;
+    auto dag_levels = dag.levels();
+    powers_exchange_.clear();
     std::set<uint32_t> parents;
-    for (uint32_t e : targets) {
-        const PowersNode &nd = dag.node(e);
-        if (nd.is_source()) continue;
-        parents.insert(nd.parent1);
-        parents.insert(nd.parent2);
-        for (uint32_t b = 0; b < bic; b++)
-            if (active[b]) loc[b][e] = arena_.take(2 * Lf);
+    for (uint32_t d = 1; d < dag_levels.size(); d++) {
+        const uint32_t n = (uint32_t)dag_levels[d].size(), chunk = (n + part - 1) / part;
+        for (uint32_t k = 0; k < n; k++) {
+            const PowersNode &nd = dag_levels[d][k];
+            if (k / chunk == prank) { // extended forms are only needed for the products this rank computes
+                parents.insert(nd.parent1);
+                parents.insert(nd.parent2);
+            }
+        }
+        for (uint32_t b = 0; b < bic; b++) {
+            if (!active[b]) continue;
+            const uint32_t region = arena_.take((size_t)part * chunk * 2 * Lf);
+            for (uint32_t k = 0; k < n; k++) loc[b][dag_levels[d][k].power] = region + k * 2 * Lf;
+            powers_exchange_.push_back(ExchangeRegion{ d, region, chunk * 2 * Lf });
+        }
     }
     std::vector<std::map<uint32_t, uint32_t>> ext_loc(bic);
     for (uint32_t b = 0; b < bic; b++)
@@ -603,12 +617,17 @@ void Engine::build_plan()
     {
         ProgramBuilder pb(*this, powers_prog_);
         std::set<uint32_t> extended;
-        auto levels = dag.levels();
+        auto &levels = dag_levels;
+        powers_stage_end_.clear();
         for (uint32_t d = 1; d < levels.size(); d++) {
             arena_.top = persistent_top;
+            const uint32_t n = (uint32_t)levels[d].size(), chunk = (n + part - 1) / part;
+            std::vector<PowersNode> mine; // this rank's chunk of the level
+            for (uint32_t k = 0; k < n; k++)
+                if (k / chunk == prank) mine.push_back(levels[d][k]);
             std::vector<uint32_t> ext_cts, ext_dst, a, bb, prod, dst;
             std::set<uint32_t> need;
-            for (auto &nd : levels[d]) {
+            for (auto &nd : mine) {
                 if (!extended.count(nd.parent1)) need.insert(nd.parent1);
                 if (!extended.count(nd.parent2)) need.insert(nd.parent2);
             }
@@ -622,14 +641,14 @@ void Engine::build_plan()
             extended.insert(need.begin(), need.end());
             uint32_t n_ops = 0;
             for (uint32_t b = 0; b < bic; b++)
-                if (active[b]) n_ops += (uint32_t)levels[d].size();
+                if (active[b]) n_ops += (uint32_t)mine.size();
             uint32_t prod0 = arena_.take((size_t)n_ops * 3 * Lf);
             uint32_t mscr = arena_.take(ProgramBuilder::multiply_scratch(ctx, Lf, n_ops));
             uint32_t rscr = arena_.take(ProgramBuilder::relin_scratch(Lf, n_ops));
             uint32_t o = 0;
             for (uint32_t b = 0; b < bic; b++) {
                 if (!active[b]) continue;
-                for (auto &nd : levels[d]) {
+                for (auto &nd : mine) {
                     a.push_back(ext_loc[b][nd.parent1]);
                     bb.push_back(ext_loc[b][nd.parent2]);
                     prod.push_back(prod0 + o * 3 * Lf);
@@ -640,6 +659,7 @@ void Engine::build_plan()
             pb.extend(Lf, ext_cts, ext_dst);
             pb.multiply(Lf, a, bb, prod, mscr);
             pb.relinearize(Lf, prod, dst, rscr); // relinearize == using_keyswitching (checked in ctor)
+            powers_stage_end_.push_back(powers_prog_.size());
         }
         // tail: mod-switch every target to its level; low powers to NTT form (:446-478)
         arena_.top = persistent_top;
@@ -712,6 +732,7 @@ void Engine::build_plan()
             pb.pack_powers(Ll, nlow, lsrc, ldst);
             pb.pack_powers(Lh, nhigh, hsrc, hdst);
         }
+        powers_stage_end_.push_back(powers_prog_.size()); // the tail is the last stage
     }
     const uint32_t powers_top = (uint32_t)arena_.high_water;
     // coefficient-form high powers must survive for get_power(); keep eval scratch above the powers scratch
@@ -1079,15 +1100,61 @@ void Engine::emit_finalize(ProgramBuilder &pb, uint32_t Ls, std::vector<Finalize
 // ------------------------------------------------------------------------------------------------
 void Engine::compute_powers()
 {
+    if (powers_part_size_ > 1) throw std::logic_error("the PowersDag is split over several ranks: run compute_powers_stage and exchange between stages");
+    const uint32_t n = powers_stage_count();
+    for (uint32_t s = 0; s < n; s++) compute_powers_stage(s);
+}
+
+uint32_t Engine::powers_stage_count()
+{
+    if (!plan_valid_) build_plan();
+    return (uint32_t)powers_stage_end_.size();
+}
+
+// stage s < depth: the products of DAG level s+1 this rank owns; last stage: mod-switches, NTTs, power tables.
+// With a split DAG the caller all-gathers the exchange regions of level s+1 between the ranks after stage s.
+void Engine::compute_powers_stage(uint32_t stage)
+{
     if (!plan_valid_ || !query_loaded_) throw std::logic_error("compute_powers called before query_begin (or the DB changed since)");
     if (ctx.using_keyswitching() && dag.depth() > 0 && !have_keys_) throw std::invalid_argument("relinearization keys have not been set");
-    ctx.launches = 0;
-    APSU_CUDA_CHECK(cudaEventRecord(ev_[0], ctx.stream));
-    for (auto &s : powers_prog_) s.run();
-    APSU_CUDA_CHECK(cudaEventRecord(ev_[1], ctx.stream));
-    powers_done_ = true;
-    eval_done_ = false;
-    powers_launches_ = ctx.launches;
+    if (stage >= powers_stage_end_.size()) throw std::invalid_argument("powers stage is out of range");
+    if (stage == 0) {
+        ctx.launches = 0;
+        APSU_CUDA_CHECK(cudaEventRecord(ev_[0], ctx.stream));
+        powers_done_ = eval_done_ = false;
+    }
+    const size_t lo = stage ? powers_stage_end_[stage - 1] : 0, hi = powers_stage_end_[stage];
+    for (size_t k = lo; k < hi; k++) powers_prog_[k].run();
+    if (stage + 1 == powers_stage_end_.size()) {
+        APSU_CUDA_CHECK(cudaEventRecord(ev_[1], ctx.stream));
+        powers_done_ = true;
+        powers_launches_ = ctx.launches;
+    }
+}
+
+void Engine::set_powers_partition(uint32_t rank, uint32_t size)
+{
+    if (!size || rank >= size) throw std::invalid_argument("powers partition: rank must be below size");
+    powers_part_rank_ = rank;
+    powers_part_size_ = size;
+    invalidate_plan();
+}
+
+// exchange regions of one DAG level (one per active bundle index): device pointer of the all-gather buffer
+// [size][chunk_bytes] and the chunk size; this rank's chunk is at rank*chunk_bytes
+uint32_t Engine::powers_exchange_regions(uint32_t level, void **ptrs, uint64_t *chunk_bytes, uint32_t capacity)
+{
+    if (!plan_valid_) build_plan();
+    uint32_t n = 0;
+    for (auto &r : powers_exchange_) {
+        if (r.level != level) continue;
+        if (n < capacity) {
+            if (ptrs) ptrs[n] = arena_.buf.p + (size_t)r.region * ctx.N;
+            if (chunk_bytes) chunk_bytes[n] = (uint64_t)r.chunk_polys * ctx.N * 8;
+        }
+        n++;
+    }
+    return n;
 }
 
 void Engine::eval_all()

@@ -88,6 +88,11 @@ public:
     void encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t *out);
     void generate_masks(uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out);
     void compute_powers();
+    // PowersDag split over the ranks that share a bundle index (collective C2)
+    void set_powers_partition(uint32_t rank, uint32_t size);
+    uint32_t powers_stage_count();
+    void compute_powers_stage(uint32_t stage);
+    uint32_t powers_exchange_regions(uint32_t level, void **ptrs, uint64_t *chunk_bytes, uint32_t capacity);
     void eval_all();
     void fetch_results(uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
     void get_power(uint32_t bundle_idx, uint32_t power, uint64_t *out, uint32_t *L, int *is_ntt);
@@ -124,6 +129,12 @@ private:
     std::vector<uint8_t> desc_host_; // kernel descriptor structs (KtGroup, FinalizeJob, ...)
     DBuf<uint8_t> desc_dev_;
     std::vector<Step> powers_prog_, eval_prog_;
+    std::vector<size_t> powers_stage_end_; // powers_prog_ index after each DAG level and after the tail
+    uint32_t powers_part_rank_ = 0, powers_part_size_ = 1;
+    struct ExchangeRegion {
+        uint32_t level, region, chunk_polys;
+    };
+    std::vector<ExchangeRegion> powers_exchange_;
     bool plan_valid_ = false;
     bool query_loaded_ = false, powers_done_ = false, eval_done_ = false;
     uint32_t query_region_ = 0; // arena index of the uploaded query [nsrc][bic][2][first_L]

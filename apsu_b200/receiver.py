@@ -188,6 +188,7 @@ class Receiver:
     def __init__(self, db: ReceiverDB):
         self.db = db
         self._L = capi.lib()
+        self._part_rank, self._part_size = 0, 1
 
     # ---- staged API (ComputePowers / ProcessBinBundleCache) ----
     def load_query(self, query: Query):
@@ -221,8 +222,30 @@ class Receiver:
         capi.check(self._L.apsu_b200_encode_masks(self.db._h, v, v.shape[0], out))
         return out
 
-    def ComputePowers(self):
-        capi.check(self._L.apsu_b200_compute_powers(self.db._h))
+    def ComputePowers(self, exchange=None):
+        """Receiver::ComputePowers for every bundle index.  With a split PowersDag (set_powers_partition) `exchange`
+        is called after every DAG level as exchange(level, regions) with regions = [(device_ptr, chunk_bytes), ...]
+        and must all-gather them between the ranks of the partition (apsu_b200/sharding.py::exchange_powers)."""
+        if self._part_size == 1:
+            capi.check(self._L.apsu_b200_compute_powers(self.db._h))
+            return
+        n = C.c_uint32()
+        capi.check(self._L.apsu_b200_powers_stage_count(self.db._h, C.byref(n)))
+        for s in range(n.value):
+            capi.check(self._L.apsu_b200_compute_powers_stage(self.db._h, s))
+            if s + 1 < n.value:
+                exchange(s + 1, self.powers_exchange_regions(s + 1))
+
+    def set_powers_partition(self, rank: int, size: int):
+        """collective C2: this receiver computes chunk `rank` of `size` of every PowersDag level."""
+        capi.check(self._L.apsu_b200_set_powers_partition(self.db._h, rank, size))
+        self._part_rank, self._part_size = rank, size
+
+    def powers_exchange_regions(self, level: int):
+        cap = self.db.params.bundle_idx_count()
+        ptrs, sizes, n = (C.c_void_p * cap)(), (C.c_uint64 * cap)(), C.c_uint32()
+        capi.check(self._L.apsu_b200_powers_exchange_regions(self.db._h, level, ptrs, sizes, cap, C.byref(n)))
+        return [(int(ptrs[i]), int(sizes[i])) for i in range(n.value)]
 
     def ProcessBinBundleCaches(self):
         capi.check(self._L.apsu_b200_eval_all(self.db._h))

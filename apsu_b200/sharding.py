@@ -3,8 +3,9 @@
 BinBundles are independent units (receiver/apsu/receiver_ddh.cpp:340-364): each needs only the query powers
 of its bundle index and its own mask.  A rank owns a contiguous run of the (bundle_idx, cache_idx) list so
 that it touches as few bundle indices as possible (it recomputes the powers of every index it owns — no
-collective on the data path).  The only exchanges are the query broadcast and the result gather, done with
-torch.distributed (NCCL over NVLink on GPUs, gloo in CPU tests)."""
+collective on the data path).  The exchanges are the query broadcast and the result gather and, when there are more ranks than bundle indices, the
+all-gather of the ciphertext powers between the ranks that share a bundle index and split its PowersDag
+(collective C2), all done with torch.distributed (NCCL over NVLink on GPUs, gloo in CPU tests)."""
 from __future__ import annotations
 
 
@@ -44,3 +45,48 @@ def gather_results(local, counts, N: int, dst: int = 0):
     if rank != dst:
         return None
     return torch.cat([o[:n] for o, n in zip(out, counts)], dim=0)
+
+
+def powers_partition(parts, rank: int):
+    """PowersDag split (collective C2): if every rank owns BinBundles of exactly one bundle index, the ranks owning
+    the same index form a group that splits ComputePowers.  parts = shard_bundles(...).
+    -> (sorted ranks of this rank's group, index of `rank` in it, all groups) ; groups of one rank mean no split."""
+    owner = []
+    for part in parts:
+        idx = sorted({b for (b, _, _) in part})
+        if len(idx) != 1:
+            return [rank], 0, [[r] for r in range(len(parts))]
+        owner.append(idx[0])
+    groups = {}
+    for r, b in enumerate(owner):
+        groups.setdefault(b, []).append(r)
+    all_groups = [groups[b] for b in sorted(groups)]
+    mine = groups[owner[rank]]
+    return mine, mine.index(rank), all_groups
+
+
+class _DeviceRegion:
+    """a device buffer known by address, for torch.as_tensor (CUDA array interface)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def allgather_region(full, index: int, size: int, group=None):
+    """`full` = flat tensor of `size` equal chunks, this rank's data in chunk `index`: fills the other chunks."""
+    import torch.distributed as dist
+    words = full.numel() // size
+    mine = full[index * words:(index + 1) * words].clone()
+    dist.all_gather(list(full.view(size, words).unbind(0)), mine, group=group)
+
+
+def exchange_powers(regions, index: int, size: int, group=None):
+    """all-gather of one DAG level between the `size` ranks of a group: every region is a device buffer of `size`
+    chunks, this rank's products in chunk `index` (apsu_b200_powers_exchange_regions)."""
+    import torch
+    import torch.distributed as dist
+    for ptr, chunk_bytes in regions:
+        full = torch.as_tensor(_DeviceRegion(ptr, chunk_bytes * size), device="cuda")
+        words = chunk_bytes // 8
+        mine = full[index * words:(index + 1) * words].clone()
+        dist.all_gather_into_tensor(full, mine, group=group)

@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--db-log2", type=int, default=DB_LOG2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-db-build", action="store_true", help="skip the device DB-build measurement (row f1)")
+    ap.add_argument("--no-dag-split", action="store_true", help="ranks sharing a bundle index recompute its powers instead of splitting the PowersDag")
     ap.add_argument("--chunk", type=int, default=None, help="BinBundles per evaluation chunk (APSU_B200_CHUNK)")
     args = ap.parse_args()
     if args.chunk:
@@ -336,7 +337,26 @@ def main():
     capi.check(capi.lib().apsu_b200_ctx_set_stream(db._h, C.c_void_p(stream.cuda_stream)))
 
     # this rank's shard; local cache indices are dense per bundle index
-    mine = shard(degrees, world)[rank]
+    parts = shard(degrees, world)
+    mine = parts[rank]
+    # more ranks than bundle indices: the ranks sharing an index split its PowersDag and all-gather the powers
+    # level by level (collective C2) instead of each recomputing them
+    part_group, part_index, part_pg = [rank], 0, None
+    if world > 1:
+        from apsu_b200 import sharding
+        part_group, part_index, all_groups = sharding.powers_partition(parts, rank)
+        if args.no_dag_split:
+            part_group, part_index, all_groups = [rank], 0, []
+        if any(len(g) > 1 for g in all_groups):
+            for g in all_groups:  # every rank creates every group
+                pg = dist.new_group(g)
+                if g == part_group:
+                    part_pg = pg
+        if len(part_group) > 1:
+            rx.set_powers_partition(part_index, len(part_group))
+        if len(part_group) > 1:
+            config["parallelism"] = (f"BinBundles sharded over {world} GPU(s); PowersDag of a bundle index split over the "
+                                     f"{len(part_group)} rank(s) that share it, powers all-gathered per DAG level (NCCL)")
     local_of = {}
     for (b, c, d) in mine:
         local_of[(b, c)] = db.add_bin_bundle_synthetic(b, d + 1, SEEDS["db"] * 1000 + b * 64 + c)
@@ -378,8 +398,14 @@ def main():
         capi.check(lib.apsu_b200_set_masks(h, masks_p.reshape(-1), masks_p.shape[0]))
         rx.set_profiling(True)
 
+        def compute_powers():
+            if len(part_group) > 1:
+                rx.ComputePowers(exchange=lambda level, regs: sharding.exchange_powers(regs, part_index, len(part_group), part_pg))
+            else:
+                capi.check(lib.apsu_b200_compute_powers(h))
+
         def step_resident():
-            capi.check(lib.apsu_b200_compute_powers(h))
+            compute_powers()
             capi.check(lib.apsu_b200_eval_all(h))
 
         for _ in range(args.warmup):
@@ -405,8 +431,7 @@ def main():
         if dist is not None:
             d_cts = torch.empty(cts_t.shape, dtype=torch.int64, device="cuda")
             d_relin = torch.empty(relin_t.shape, dtype=torch.int64, device="cuda")
-            counts = [len(x) for x in shard(degrees, world)]
-            from apsu_b200 import sharding
+            counts = [len(x) for x in parts]
 
         def step_e2e():
             if dist is None:
@@ -421,7 +446,7 @@ def main():
                 capi.check(lib.apsu_b200_query_begin_device(h, src_powers, nsrc, C.c_void_p(d_cts.data_ptr())))
                 capi.check(lib.apsu_b200_set_relin_keys_device(h, C.c_void_p(d_relin.data_ptr())))
                 capi.check(lib.apsu_b200_set_masks(h, masks_p.reshape(-1), masks_p.shape[0]))
-                capi.check(lib.apsu_b200_compute_powers(h))
+                compute_powers()
                 capi.check(lib.apsu_b200_eval_all(h))
                 res = torch.empty((max(n_local, 1), 2, N), dtype=torch.int64, device="cuda")
                 if n_local:

@@ -150,6 +150,19 @@ int apsu_b200_get_power(
  * on the device from slot values uint64_t[npack][N]. */
 int apsu_b200_set_masks(apsu_b200_ctx *ctx, const uint64_t *masks, uint32_t npack);
 int apsu_b200_encode_masks(apsu_b200_ctx *ctx, const uint64_t *slot_values, uint32_t npack, uint64_t *masks_out);
+/* Multi-GPU, collective C2 of SURVEY.md §8e: when more GPUs than bundle indices serve a DB, the ranks that share a
+ * bundle index split the PowersDag of ComputePowers (receiver_ddh.cpp:390-483) instead of each recomputing it.
+ * Rank r of `size` computes chunk r of every DAG level (ceil(n/size) consecutive nodes of PowersDag's level order);
+ * stage s < dag_depth of apsu_b200_compute_powers_stage runs level s+1, after which the caller all-gathers that
+ * level's exchange regions between the ranks (one region per populated bundle index: a device buffer of `size`
+ * chunks of chunk_bytes, this rank's chunk at rank*chunk_bytes — e.g. ncclAllGather in place); the last stage
+ * (mod-switches, NTTs, power tables) needs every power and runs on every rank.  size == 1 (default) keeps
+ * apsu_b200_compute_powers as one call. */
+int apsu_b200_set_powers_partition(apsu_b200_ctx *ctx, uint32_t rank, uint32_t size);
+int apsu_b200_powers_stage_count(apsu_b200_ctx *ctx, uint32_t *count);
+int apsu_b200_compute_powers_stage(apsu_b200_ctx *ctx, uint32_t stage);
+int apsu_b200_powers_exchange_regions(
+    apsu_b200_ctx *ctx, uint32_t level, void **device_ptrs, uint64_t *chunk_bytes, uint32_t capacity, uint32_t *count);
 /* "next" row f3 — the mask generation of RunQuery on the device (receiver_ddh.cpp:241-283): for every pack index
  * p = bundle_idx + cache_idx*bundle_idx_count with padded[p] == 0, r = prng32 % plain_modulus per slot (:258),
  * BatchEncoder::encode of it (:275; kept device-resident as the masks of the next evaluation, like

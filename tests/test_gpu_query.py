@@ -232,6 +232,67 @@ def test_mask_generation_on_device(name, degrees):
         db.close()
 
 
+@pytest.mark.parametrize("name,degrees,size", [("16M-4096", [[140, 45]], 2), ("1M-4096-com", [[97, 12]], 3), ("256K-512", [[63]], 2)])
+def test_split_powers_dag(name, degrees, size):
+    """collective C2 on one GPU: `size` receivers (one context each) split the PowersDag of a bundle index, the
+    all-gather between DAG levels is emulated with device copies, and every receiver ends with the oracle's powers
+    and result ciphertexts."""
+    import torch
+    import apsu_b200
+    from apsu_b200.sharding import _DeviceRegion
+    bic_deg = degrees + [[] for _ in range(100)]
+    from oracle import oracle as O
+    p0 = O.Params.load(name)
+    sc = Scenario(name, bic_deg[:p0.bundle_idx_count], planted=4)
+    dbs = [apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0) for _ in range(size)]
+    try:
+        rxs = []
+        q = apsu_b200.Query(sc.src_powers, sc.cts, sc.relin)
+        for r, db in enumerate(dbs):
+            _upload(sc, db)
+            rx = apsu_b200.Receiver(db)
+            rx.set_powers_partition(r, size)
+            rx.load_query(q)
+            rx.set_masks(sc.masks)
+            rxs.append(rx)
+        lib = apsu_b200.capi.lib()
+        import ctypes as C
+        n = C.c_uint32()
+        apsu_b200.capi.check(lib.apsu_b200_powers_stage_count(dbs[0]._h, C.byref(n)))
+        for s in range(n.value):
+            for db in dbs:
+                apsu_b200.capi.check(lib.apsu_b200_compute_powers_stage(db._h, s))
+            for db in dbs:
+                apsu_b200.capi.check(lib.apsu_b200_ctx_synchronize(db._h))
+            if s + 1 < n.value:
+                regs = [rx.powers_exchange_regions(s + 1) for rx in rxs]
+                for k in range(len(regs[0])):
+                    words = regs[0][k][1] // 8
+                    full = [torch.as_tensor(_DeviceRegion(regs[r][k][0], regs[r][k][1] * size), device="cuda") for r in range(size)]
+                    for src in range(size):
+                        for dst in range(size):
+                            if src != dst:
+                                full[dst][src * words:(src + 1) * words] = full[src][src * words:(src + 1) * words]
+                torch.cuda.synchronize()
+        pses = sc.db.run_query(sc.src_powers, sc.cts, sc.relin, None, threads=8, powers_only=True)
+        exp = {(b, c): ct for b, c, ct in sc.db.run_query(sc.src_powers, sc.cts, sc.relin, sc.masks, threads=8).results()}
+        for rx in rxs:
+            for e in rx_targets(sc.p):
+                want = pses.power(0, e)
+                L, ntt, got = rx.get_power(0, e)
+                assert (L, ntt) == (want[0], want[1]) and np.array_equal(got, want[2]), e
+            rx.ProcessBinBundleCaches()
+            got = {(r.bundle_idx, r.cache_idx): r.psu_result for r in rx.results()}
+            assert set(got) == set(exp)
+            for key in exp:
+                assert np.array_equal(got[key].reshape(2, -1), exp[key]), key
+        with pytest.raises(AssertionError):  # logic_error: the one-call ComputePowers needs an unsplit DAG
+            apsu_b200.capi.check(lib.apsu_b200_compute_powers(dbs[0]._h))
+    finally:
+        for db in dbs:
+            db.close()
+
+
 def test_error_behaviour_on_device():
     import apsu_b200
     sc = Scenario("256K-512", [[5]], planted=2)

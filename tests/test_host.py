@@ -128,6 +128,18 @@ if rank == 0:
     for k, (b, c) in enumerate(order):
         assert int(gathered[k, 0, 0]) == b * 100 + c
     print("OK")
+# PowersDag split (collective C2): both ranks own BinBundles of bundle index 0 only -> one group of two
+parts1 = sharding.shard_bundles([[5, 3, 1, 4]], world)
+group, index, groups = sharding.powers_partition(parts1, rank)
+assert group == [0, 1] and index == rank and groups == [[0, 1]]
+assert sharding.powers_partition(parts, rank)[0] == [rank]   # ranks owning several indices do not split
+pg = dist.new_group(group)
+full = torch.full((2 * 6,), -1, dtype=torch.int64)
+full[index * 6:(index + 1) * 6] = torch.arange(6) + 100 * rank
+sharding.allgather_region(full, index, len(group), pg)
+assert torch.equal(full, torch.cat([torch.arange(6), torch.arange(6) + 100])), full
+if rank == 0:
+    print("OK2")
 dist.destroy_process_group()
 '''
 
@@ -139,4 +151,4 @@ def test_sharded_exchange_on_gloo(tmp_path):
     out = subprocess.check_output([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                                    "--master-addr", "127.0.0.1", "--master-port", "29517", str(script), str(ROOT)],
                                   env=env, text=True, stderr=subprocess.STDOUT, timeout=300)
-    assert "OK" in out
+    assert "OK" in out and "OK2" in out
