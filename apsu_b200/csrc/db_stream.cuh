@@ -37,6 +37,18 @@ constexpr size_t kt_smem_bytes(int stages) { return (size_t)stages * kKtStageWor
 // launch shape used by the engine: 4 stages x 24 KB, 2 CTAs/SM (tools/lab: 6.4 TB/s; 3 stages x 3 CTAs 6.2)
 constexpr int kKtStages = 4;
 constexpr int kKtCtasPerSm = 2;
+// Work items are ordered (tile block, group, tile in block): the CTAs running at any moment work on the same
+// kKtTileBlock tiles across many groups, so the power tiles of those columns (pstride*2 KB each, shared by every
+// group of a bundle index) stay in L2 however long the sums are.  With tiles fastest over ALL tiles the reuse
+// distance was a whole group sweep: fine for 16M-4096 (88 KB per tile, 50 MB per sweep) but not for 256M-4096
+// (620 KB per tile, 357 MB per sweep), where the powers were re-read from HBM for every group.
+constexpr u32 kKtTileBlock = 16; // divides L*N/128 for every N >= 2048
+__device__ __forceinline__ void kt_item(u32 item, u32 n_groups, u32 &group, u32 &tile)
+{
+    const u32 per_block = n_groups * kKtTileBlock, tb = item / per_block, rem = item - tb * per_block;
+    group = rem / kKtTileBlock;
+    tile = tb * kKtTileBlock + (rem - group * kKtTileBlock);
+}
 
 // One group = up to kKtG accumulation jobs over the same ciphertext powers (power j+1 multiplies term j).
 // job k: out_k[c][l][n] = sum_{j < nterms_k} power_j[c][l][n] * w_k[j][l][n]   (mod q_l)
@@ -182,7 +194,7 @@ __device__ __forceinline__ void kt_mac(const KtRegs &r, AccK (&acc)[kKtG][2], co
 }
 
 // Persistent kernel: grid = SMs x CTAs/SM, block 160 (4 consumer warps + 1 producer warp).  Work item =
-// (group, 128-coefficient tile); a CTA walks items blockIdx.x, +gridDim.x, ... with tiles fastest and the
+// (group, 128-coefficient tile) in the order of kt_item; a CTA walks items blockIdx.x, +gridDim.x, ... and the
 // ring never drains between items (the producer prefetches the next item while the consumers reduce and
 // store the current one).
 // split = bit position the operands were split at; fold_stages = ring stages between lane folds (host:
@@ -216,8 +228,9 @@ k_db_mac_kt(u64 *A, const KtGroup *__restrict__ groups, u32 n_groups, LevelConst
         if (tid != kKtCols) return;
         const u64 pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
         for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const u32 tile = item % n_tiles;
-            const KtGroup *g = &groups[item / n_tiles];
+            u32 tile, gi;
+            kt_item(item, n_groups, gi, tile);
+            const KtGroup *g = &groups[gi];
             const u32 max_terms = g->max_terms;
             u32 nt[kKtG];
             const u64 *wk[kKtG];
@@ -254,8 +267,9 @@ k_db_mac_kt(u64 *A, const KtGroup *__restrict__ groups, u32 n_groups, LevelConst
     // ---------------- consumer warps: one (prime, coefficient) column per thread ----------------
     const bool lane0 = (tid & 31) == 0;
     for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const u32 tile = item % n_tiles;
-        const KtGroup *g = &groups[item / n_tiles];
+        u32 tile, gi;
+        kt_item(item, n_groups, gi, tile);
+        const KtGroup *g = &groups[gi];
         const u32 max_terms = __ldg(&g->max_terms);
         const bool ragged = __ldg(&g->ragged) != 0;
         u32 nt[kKtG];
