@@ -143,7 +143,8 @@ __device__ __forceinline__ u64 reduce_k(const AccK &a, const DMod &m, int s)
     t = a.hh << (2 * s);
     lo += t;
     hi += (a.hh >> (64 - 2 * s)) + (lo < t);
-    return barrett128(lo, hi, m);
+    // the fold period keeps the sum below 2^(62-b) products of b-bit residues, i.e. below 2^(64+sh): one-word Barrett
+    return barrett_prod(lo, hi, m);
 }
 // replaces the lanes by the ones of the reduced value (keeps the 64-bit lanes from overflowing on long sums)
 __device__ __forceinline__ void fold_k(AccK &a, const DMod &m, int s)

@@ -61,6 +61,11 @@ static DMod make_mod(u64 q)
     unsigned __int128 r = (~(unsigned __int128)0) / q;
     m.r0 = (u64)r;
     m.r1 = (u64)(r >> 64);
+    int k = 0;
+    while ((q >> k) != 0) k++;
+    m.sh = (u32)(k - 1);
+    m.mu = (u64)((((unsigned __int128)1) << (64 + m.sh)) / q);
+    m.pad_ = 0;
     return m;
 }
 static int bits(u64 v)
