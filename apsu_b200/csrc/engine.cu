@@ -247,12 +247,14 @@ Engine::Engine(const apsu_b200_params &p, int device) : ctx(p, device)
         fold_stages_ = (uint32_t)std::min<unsigned __int128>(cap / kKtTS, 0x7FFFFFFFu);
     }
     levels_dev_.upload(ctx.level, ctx.stream);
+    if (const char *ev = std::getenv("APSU_B200_NO_GRAPH")) use_graphs_ = atoi(ev) == 0;
     for (auto &ev : ev_) APSU_CUDA_CHECK(cudaEventCreate(&ev));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
 }
 
 Engine::~Engine()
 {
+    drop_graphs();
     for (auto &e : ev_)
         if (e) cudaEventDestroy(e);
     for (auto &pr : mac_events_) {
@@ -980,6 +982,69 @@ size_t Engine::add_desc(const void *data, size_t bytes)
     return off;
 }
 
+// cudaEventRecord that also works while the stream is being captured into a graph (an event-record node)
+static cudaError_t record_event(cudaEvent_t ev, cudaStream_t st)
+{
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaError_t e = cudaStreamIsCapturing(st, &cs);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecordWithFlags(ev, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
+void Engine::drop_graphs()
+{
+    for (auto &g : powers_graphs_)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    powers_graphs_.clear();
+    if (eval_graph_.exec) cudaGraphExecDestroy(eval_graph_.exec);
+    eval_graph_ = ProgGraph();
+}
+
+// runs steps [lo, hi) of a program: captured into a graph on first use (and whenever a buffer the kernels were
+// given has moved), replayed afterwards
+void Engine::run_steps(std::vector<Step> &prog, size_t lo, size_t hi, ProgGraph &g)
+{
+    if (!use_graphs_) {
+        for (size_t k = lo; k < hi; k++) prog[k].run();
+        return;
+    }
+    const void *key[4] = { arena_.buf.p, masks_.p, relin_keys_.p, results_.p };
+    const bool fresh = g.exec && g.profiling == profiling && std::equal(key, key + 4, g.key);
+    if (!fresh) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = ProgGraph();
+        const uint32_t l0 = ctx.launches;
+        const size_t e0 = mac_events_used_;
+        const uint64_t b0 = timed_mac_bytes_;
+        APSU_CUDA_CHECK(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeRelaxed));
+        cudaGraph_t graph = nullptr;
+        try {
+            for (size_t k = lo; k < hi; k++) prog[k].run();
+        } catch (...) {
+            cudaStreamEndCapture(ctx.stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        APSU_CUDA_CHECK(cudaStreamEndCapture(ctx.stream, &graph));
+        cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        APSU_CUDA_CHECK(e);
+        g.launches = ctx.launches - l0;
+        g.mac_events = mac_events_used_ - e0;
+        g.mac_bytes = timed_mac_bytes_ - b0;
+        std::copy(key, key + 4, g.key);
+        g.profiling = profiling;
+        // the capture ran the host side of the steps only; undo its bookkeeping, the launch below redoes it
+        ctx.launches = l0;
+        mac_events_used_ = e0;
+        timed_mac_bytes_ = b0;
+    }
+    APSU_CUDA_CHECK(cudaGraphLaunch(g.exec, ctx.stream));
+    ctx.launches += g.launches;
+    mac_events_used_ += g.mac_events;
+    timed_mac_bytes_ += g.mac_bytes;
+}
+
 void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<KtGroup> &groups, uint64_t bytes)
 {
     if (groups.empty()) return;
@@ -1037,7 +1102,7 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<KtGroup> &grou
             a = mac_events_[mac_events_used_].first;
             b2 = mac_events_[mac_events_used_].second;
             mac_events_used_++;
-            APSU_CUDA_CHECK(cudaEventRecord(a, ctx.stream));
+            APSU_CUDA_CHECK(record_event(a, ctx.stream));
         }
         const KtGroup *gd = reinterpret_cast<const KtGroup *>(desc_dev_.p + off);
         // one persistent launch over all groups
@@ -1055,7 +1120,7 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<KtGroup> &grou
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;
         if (timed) {
-            APSU_CUDA_CHECK(cudaEventRecord(b2, ctx.stream));
+            APSU_CUDA_CHECK(record_event(b2, ctx.stream));
             timed_mac_bytes_ += mac_step_bytes_[slot];
         }
     });
@@ -1124,7 +1189,11 @@ void Engine::compute_powers_stage(uint32_t stage)
         powers_done_ = eval_done_ = false;
     }
     const size_t lo = stage ? powers_stage_end_[stage - 1] : 0, hi = powers_stage_end_[stage];
-    for (size_t k = lo; k < hi; k++) powers_prog_[k].run();
+    if (powers_graphs_.size() != powers_stage_end_.size()) {
+        drop_graphs();
+        powers_graphs_.resize(powers_stage_end_.size());
+    }
+    run_steps(powers_prog_, lo, hi, powers_graphs_[stage]);
     if (stage + 1 == powers_stage_end_.size()) {
         APSU_CUDA_CHECK(cudaEventRecord(ev_[1], ctx.stream));
         powers_done_ = true;
@@ -1165,7 +1234,7 @@ void Engine::eval_all()
     mac_events_used_ = 0;
     timed_mac_bytes_ = 0;
     APSU_CUDA_CHECK(cudaEventRecord(ev_[2], ctx.stream));
-    for (auto &s : eval_prog_) s.run();
+    run_steps(eval_prog_, 0, eval_prog_.size(), eval_graph_);
     APSU_CUDA_CHECK(cudaEventRecord(ev_[3], ctx.stream));
     eval_done_ = true;
     eval_launches_ = ctx.launches;

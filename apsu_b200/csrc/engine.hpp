@@ -153,7 +153,26 @@ private:
     uint64_t timed_mac_bytes_ = 0;
     uint32_t powers_launches_ = 0, eval_launches_ = 0;
 
-    void invalidate_plan() { plan_valid_ = false; }
+    // The two programs are fixed launch sequences: they are captured once into CUDA graphs (one per ComputePowers
+    // stage, one for the evaluation) and replayed per query; the small parameter sets are launch-bound.
+    struct ProgGraph {
+        cudaGraphExec_t exec = nullptr;
+        uint32_t launches = 0;
+        size_t mac_events = 0;
+        uint64_t mac_bytes = 0;
+        const void *key[4] = { nullptr, nullptr, nullptr, nullptr }; // arena, masks, relin keys, results at capture
+        bool profiling = false;
+    };
+    std::vector<ProgGraph> powers_graphs_;
+    ProgGraph eval_graph_;
+    bool use_graphs_ = true;
+    void run_steps(std::vector<Step> &prog, size_t lo, size_t hi, ProgGraph &g);
+    void drop_graphs();
+    void invalidate_plan()
+    {
+        plan_valid_ = false;
+        drop_graphs();
+    }
     void build_plan();
     void prepare_plain_high(BinBundleStore &s);
     void pack_tile(const u64 *src, u64 *dst, uint32_t rows, uint32_t L);
