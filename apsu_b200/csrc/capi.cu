@@ -279,6 +279,11 @@ int apsu_b200_encode_masks(apsu_b200_ctx *ctx, const uint64_t *slot_values, uint
 {
     return guarded([&] { E(ctx).encode_masks(slot_values, npack, masks_out); });
 }
+int apsu_b200_decrypt_results(
+    apsu_b200_ctx *ctx, const uint64_t *secret_key_ntt_q0, const uint64_t *cts, uint32_t n, uint64_t *slot_values, uint64_t *blocks, int32_t *noise_budget)
+{
+    return guarded([&] { E(ctx).decrypt_results(secret_key_ntt_q0, cts, n, slot_values, blocks, noise_budget); });
+}
 int apsu_b200_set_powers_partition(apsu_b200_ctx *ctx, uint32_t rank, uint32_t size)
 {
     return guarded([&] { E(ctx).set_powers_partition(rank, size); });

@@ -516,6 +516,46 @@ void Engine::generate_masks(uint64_t seed, const uint8_t *padded, uint32_t npack
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
 }
 
+// ResultPackage::extract for a batch of result ciphertexts (result_package.cpp:175-213, sender_ddh.cpp:580-605):
+// decrypt at the last level with the secret key (NTT form modulo q0, i.e. the first N words of seal::SecretKey),
+// BatchEncoder::decode, and the items' 128-bit blocks.
+void Engine::decrypt_results(const uint64_t *secret_ntt_q0, const uint64_t *cts, uint32_t n, uint64_t *values_out, uint64_t *blocks_out, int32_t *budget_out)
+{
+    if (!secret_ntt_q0 || !cts || !n || !values_out) throw std::invalid_argument("decrypt_results: bad arguments");
+    const uint32_t N = ctx.N, ipb = ctx.params.items_per_bundle;
+    const DMod q0 = ctx.mod_host[0];
+    DBuf<u64> d_ct, d_s, tmp, plain, values, blocks;
+    DBuf<int> budget;
+    DBuf<uint32_t> src_idx;
+    d_ct.alloc((size_t)n * 2 * N);
+    d_s.alloc(N);
+    tmp.alloc((size_t)n * N);
+    plain.alloc((size_t)n * N);
+    values.alloc((size_t)n * N);
+    blocks.alloc((size_t)n * ipb * 2);
+    budget.alloc(n);
+    std::vector<uint32_t> idx(n);
+    for (uint32_t k = 0; k < n; k++) idx[k] = 2 * k + 1; // the c1 polynomials
+    src_idx.upload(idx, ctx.stream);
+    std::vector<int> big(n, 1 << 20);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(d_ct.p, cts, d_ct.n * 8, cudaMemcpyHostToDevice, ctx.stream));
+    APSU_CUDA_CHECK(cudaMemcpyAsync(d_s.p, secret_ntt_q0, (size_t)N * 8, cudaMemcpyHostToDevice, ctx.stream));
+    APSU_CUDA_CHECK(cudaMemcpyAsync(budget.p, big.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+    ctx.ntt(d_ct.p, tmp.p, n, { 0 }, false, src_idx.p, nullptr);
+    k_mul_secret<<<dim3(N / 256, n), 256, 0, ctx.stream>>>(tmp.p, d_s.p, q0, (int)N);
+    APSU_LAUNCH_CHECK();
+    ctx.ntt(tmp.p, tmp.p, n, { 0 }, true);
+    k_decrypt_round<<<dim3(N / 256, n), 256, 0, ctx.stream>>>(d_ct.p, tmp.p, plain.p, budget.p, q0, ctx.t, (int)N);
+    APSU_LAUNCH_CHECK();
+    ctx.ntt(plain.p, plain.p, n, { ctx.idx_t }, false);
+    k_decode_gather<<<dim3(N / 256, n), 256, 0, ctx.stream>>>(plain.p, values.p, blocks_out ? blocks.p : nullptr, ctx.slot_map.p, ctx.t, ctx.params.felts_per_item, ipb, (int)N);
+    APSU_LAUNCH_CHECK();
+    APSU_CUDA_CHECK(cudaMemcpyAsync(values_out, values.p, values.n * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    if (blocks_out) APSU_CUDA_CHECK(cudaMemcpyAsync(blocks_out, blocks.p, blocks.n * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    if (budget_out) APSU_CUDA_CHECK(cudaMemcpyAsync(budget_out, budget.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+
 void Engine::query_begin(const uint32_t *src_powers, uint32_t nsrc, const void *cts, bool on_device)
 {
     const apsu_b200_params &p = ctx.params;

@@ -87,6 +87,7 @@ public:
     void set_masks(const void *masks, uint32_t npack, bool on_device);
     void encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t *out);
     void generate_masks(uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out);
+    void decrypt_results(const uint64_t *secret_ntt_q0, const uint64_t *cts, uint32_t n, uint64_t *values_out, uint64_t *blocks_out, int32_t *budget_out);
     void compute_powers();
     // PowersDag split over the ranks that share a bundle index (collective C2)
     void set_powers_partition(uint32_t rank, uint32_t size);

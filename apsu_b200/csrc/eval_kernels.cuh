@@ -274,6 +274,26 @@ __global__ void k_polyn_with_roots(const u32 *__restrict__ bin_first, const u32 
     for (u32 i = lane; i <= d; i += 32) M[(size_t)i * N + bin] = c[i];
 }
 
+// vec_to_std_block (receiver/apsu/receiver_ddh.cpp:70-92, sender/apsu/sender_ddh.cpp has the same helper): packs
+// the felts of one item into a 128-bit block, returned as (low, high) words.  val(j) = felt j of the item.
+template <typename F>
+__device__ __forceinline__ void vec_to_std_block(F val, u32 felts_per_item, u64 t, u64 &lower, u64 &higher)
+{
+    u32 len = 1;
+    while (((1ull << len) - 1) < t) len++;
+    const u64 mask = (1ull << len) - 1, mask_lower = (1ull << (len >> 1)) - 1, mask_higher = mask - mask_lower;
+    lower = higher = 0;
+    if (felts_per_item & 1) {
+        const u64 v = val(felts_per_item - 1);
+        lower = v & mask_lower;
+        higher = (v & mask_higher) >> ((len >> 1) - 1);
+    }
+    for (u32 pla = 0; pla + 1 < felts_per_item; pla += 2) {
+        lower = (val(pla) & mask) | (lower << len);
+        higher = (val(pla + 1) & mask) | (higher << len);
+    }
+}
+
 // Mask generation of RunQuery (receiver/apsu/receiver_ddh.cpp:241-283): for every (cache_idx, bundle_idx) pair
 // p = pack index, one value r = prng32 % plain_modulus per slot (generate() yields 32-bit words, :258), scattered to
 // its BatchEncoder position (encode = this scatter + the inverse NTT mod t done by the caller), and the items'
@@ -296,21 +316,66 @@ k_gen_masks(u64 *__restrict__ values, u64 *__restrict__ scattered, u64 *__restri
         if (pad) {
             lower = higher = ~0ull; // Block::all_one_block
         } else {
-            u32 len = 1;
-            while (((1ull << len) - 1) < t) len++;
-            const u64 mask = (1ull << len) - 1, mask_lower = (1ull << (len >> 1)) - 1, mask_higher = mask - mask_lower;
             const size_t base = p * (size_t)N + (size_t)i * felts_per_item;
-            auto val = [&](u32 j) { return (u64)(u32)splitmix64_at(seed, base + j) % t; };
-            if (felts_per_item & 1) {
-                const u64 v = val(felts_per_item - 1);
-                lower = v & mask_lower;
-                higher = (v & mask_higher) >> ((len >> 1) - 1);
-            }
-            for (u32 pla = 0; pla + 1 < felts_per_item; pla += 2) {
-                lower = (val(pla) & mask) | (lower << len);
-                higher = (val(pla + 1) & mask) | (higher << len);
-            }
+            vec_to_std_block([&](u32 j) { return (u64)(u32)splitmix64_at(seed, base + j) % t; }, felts_per_item, t, lower, higher);
         }
+        blocks[(p * items_per_bundle + i) * 2] = lower;
+        blocks[(p * items_per_bundle + i) * 2 + 1] = higher;
+    }
+}
+
+// ---- sender side of the exchange: ResultPackage::extract (common/apsu/network/result_package.cpp:175-213) ----
+// Decryptor::decrypt at the last level (one prime q0): x = c0 + c1*s, m = round(t*x/q0) mod t, and the invariant
+// noise budget (bits) of the ciphertext.  prod = iNTT(NTT(c1) * s) is computed by the caller.
+// grid (N/256, n_ct).  cts [n][2][N], prod [n][N] -> plain [n][N] (coefficient form), budget[n] (atomicMin).
+__global__ void __launch_bounds__(256)
+k_decrypt_round(const u64 *__restrict__ cts, const u64 *__restrict__ prod, u64 *__restrict__ plain, int *__restrict__ budget, DMod q0, u64 t, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t k = blockIdx.y;
+    const u64 x = add_mod(cts[(k * 2) * N + i], prod[k * N + i], q0.q);
+    // t*x = quo*q0 + rem, by Barrett with the two-word ratio (estimate at most 2 short)
+    const u64 lo = t * x, hi = mulhi(t, x);
+    u64 carry = mulhi(lo, q0.r0);
+    u64 t_lo = lo * q0.r1, t_hi = mulhi(lo, q0.r1);
+    u64 s1 = t_lo + carry;
+    u64 tmp3 = t_hi + (s1 < t_lo);
+    u64 u_lo = hi * q0.r0, u_hi = mulhi(hi, q0.r0);
+    u64 s2 = s1 + u_lo;
+    u64 quo = hi * q0.r1 + tmp3 + u_hi + (s2 < u_lo);
+    u64 rem = lo - quo * q0.q;
+    while (rem >= q0.q) {
+        rem -= q0.q;
+        quo++;
+    }
+    // round to nearest: floor((t*x + q0/2) / q0)
+    u64 m = quo + (rem >= q0.q - (q0.q >> 1) ? 1 : 0);
+    m = m >= t ? m - t : m;
+    plain[k * N + i] = m;
+    const u64 dist = rem > q0.q - rem ? q0.q - rem : rem;
+    const int b = (int)(q0.sh + 1) - (dist ? 64 - __clzll((long long)dist) : 0) - 1;
+    atomicMin(&budget[k], b);
+}
+// tmp[k][i] *= s[i]  (NTT domain, modulo q0).  grid (N/256, n_ct)
+__global__ void __launch_bounds__(256) k_mul_secret(u64 *__restrict__ tmp, const u64 *__restrict__ s, DMod q0, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t k = blockIdx.y;
+    tmp[k * N + i] = mul_mod(tmp[k * N + i], s[i], q0);
+}
+// BatchEncoder::decode gather (values[p][i] = ntt(plain)[p][map[i]]) and the items' blocks (sender_ddh.cpp:588-594)
+// grid (N/256, n_ct)
+__global__ void __launch_bounds__(256)
+k_decode_gather(const u64 *__restrict__ ntt_plain, u64 *__restrict__ values, u64 *__restrict__ blocks, const u32 *__restrict__ map, u64 t, u32 felts_per_item,
+                u32 items_per_bundle, int N)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t p = blockIdx.y;
+    values[p * N + i] = ntt_plain[p * N + map[i]];
+    if (blocks && i < items_per_bundle) {
+        u64 lower, higher;
+        const size_t base = p * (size_t)N;
+        vec_to_std_block([&](u32 j) { return ntt_plain[base + map[i * felts_per_item + j]]; }, felts_per_item, t, lower, higher);
         blocks[(p * items_per_bundle + i) * 2] = lower;
         blocks[(p * items_per_bundle + i) * 2 + 1] = higher;
     }

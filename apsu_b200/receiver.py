@@ -216,6 +216,18 @@ class Receiver:
         capi.check(self._L.apsu_b200_generate_masks(self.db._h, seed, capi.ptr(padded), npack, capi.ptr(blocks), capi.ptr(values)))
         return (blocks, values) if want_values else blocks
 
+    def decrypt_results(self, secret_key_ntt_q0: np.ndarray, cts: np.ndarray, want_blocks: bool = True):
+        """sender side (ResultPackage::extract, result_package.cpp:175-213 + sender_ddh.cpp:588-594) on the device:
+        cts [n][2][N] -> (slot values [n][N], blocks [n][items_per_bundle][2] or None, noise budgets [n])."""
+        cts = np.ascontiguousarray(cts, dtype=np.uint64).reshape(-1, 2, self.db.params.poly_modulus_degree())
+        sk = np.ascontiguousarray(secret_key_ntt_q0, dtype=np.uint64)
+        n, N = cts.shape[0], cts.shape[2]
+        values = np.zeros((n, N), dtype=np.uint64)
+        blocks = np.zeros((n, self.db.params.items_per_bundle(), 2), dtype=np.uint64) if want_blocks else None
+        budget = np.zeros(n, dtype=np.int32)
+        capi.check(self._L.apsu_b200_decrypt_results(self.db._h, capi.ptr(sk), capi.ptr(cts), n, capi.ptr(values), capi.ptr(blocks), capi.ptr(budget)))
+        return values, blocks, budget
+
     def encode_masks(self, slot_values: np.ndarray) -> np.ndarray:
         v = np.ascontiguousarray(slot_values, dtype=np.uint64)
         out = np.zeros_like(v)

@@ -150,6 +150,15 @@ int apsu_b200_get_power(
  * on the device from slot values uint64_t[npack][N]. */
 int apsu_b200_set_masks(apsu_b200_ctx *ctx, const uint64_t *masks, uint32_t npack);
 int apsu_b200_encode_masks(apsu_b200_ctx *ctx, const uint64_t *slot_values, uint32_t npack, uint64_t *masks_out);
+/* "next" row f4 — the sender's side of the exchange for a batch of results: ResultPackage::extract
+ * (common/apsu/network/result_package.cpp:175-213: Decryptor::decrypt, invariant_noise_budget, BatchEncoder::decode)
+ * and the items' 128-bit blocks (vec_to_std_block, sender/apsu/sender_ddh.cpp:588-594).  cts: [n][2][N] result
+ * ciphertexts at the last level (what apsu_b200_fetch_results returns); secret_key_ntt_q0: the secret key in NTT form
+ * modulo the first coefficient prime (the first N words of seal::SecretKey::data()); slot_values: [n][N];
+ * blocks (optional): [n][items_per_bundle][2] (low, high); noise_budget (optional): [n] bits. */
+int apsu_b200_decrypt_results(
+    apsu_b200_ctx *ctx, const uint64_t *secret_key_ntt_q0, const uint64_t *cts, uint32_t n, uint64_t *slot_values, uint64_t *blocks,
+    int32_t *noise_budget);
 /* Multi-GPU, collective C2 of SURVEY.md §8e: when more GPUs than bundle indices serve a DB, the ranks that share a
  * bundle index split the PowersDag of ComputePowers (receiver_ddh.cpp:390-483) instead of each recomputing it.
  * Rank r of `size` computes chunk r of every DAG level (ceil(n/size) consecutive nodes of PowersDag's level order);

@@ -293,6 +293,37 @@ def test_split_powers_dag(name, degrees, size):
             db.close()
 
 
+@pytest.mark.parametrize("name,degrees", [("1M-4096-com", [[30, 9], [20], [], [12], [18]]), ("256K-512", [[40]]), ("16M-4096", [[60], [], [], [46]])])
+def test_sender_decrypt_on_device(name, degrees):
+    """row f4: ResultPackage::extract for a batch (decrypt at the last level, noise budget, BatchEncoder::decode) and
+    the items' blocks on the device equal the oracle's decrypt + decode and the restated vec_to_std_block; the decoded
+    slots are P_bin(x) + r, i.e. the whole receiver -> sender exchange closes on the GPU."""
+    import apsu_b200
+    from harness import ref_vec_to_std_block
+    sc = Scenario(name, degrees, planted=4)
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0)
+    try:
+        _upload(sc, db)
+        rx = apsu_b200.Receiver(db)
+        res = rx.RunQuery(apsu_b200.Query(sc.src_powers, sc.cts, sc.relin), sc.masks)
+        cts = np.stack([r.psu_result.reshape(2, -1) for r in res])
+        q0 = sc.p.primes[0]
+        s_lift = np.array([int(v) % q0 for v in sc.keys.secret.astype(np.int64)], dtype=np.uint64)
+        s_ntt = sc.ctx.ntt(0, s_lift)
+        values, blocks, budget = rx.decrypt_results(s_ntt, cts)
+        f, t = sc.p.felts_per_item, sc.p.t
+        for k, r in enumerate(res):
+            plain, b = sc.keys.decrypt_last(cts[k].reshape(2, 1, -1))
+            assert np.array_equal(values[k], sc.ctx.decode(plain)), k
+            assert int(budget[k]) == b and b > 0
+            assert np.array_equal(values[k], sc.expected_slots(r.bundle_idx, r.cache_idx))
+            for item in (0, 1, sc.p.N // f - 1):
+                lo, hi = ref_vec_to_std_block([int(v) for v in values[k, item * f:(item + 1) * f]], f, t)
+                assert (int(blocks[k, item, 0]), int(blocks[k, item, 1])) == (lo, hi), (k, item)
+    finally:
+        db.close()
+
+
 def test_error_behaviour_on_device():
     import apsu_b200
     sc = Scenario("256K-512", [[5]], planted=2)
