@@ -340,15 +340,6 @@ __global__ void __launch_bounds__(128) k_pack_tile(const u64 *__restrict__ src, 
     for (u32 r = r0; r < r0 + 8; r++)
         if (r < rows) dst[((size_t)tile * rows + r) * kKtCols + c] = split_word(src[(size_t)r * LN + (size_t)tile * kKtCols + c], split);
 }
-// inverse of k_pack_tile (DB read-back)
-__global__ void __launch_bounds__(128) k_unpack_tile(const u64 *__restrict__ src, u64 *__restrict__ dst, u32 rows, u32 LN, int split)
-{
-    const u32 tile = blockIdx.x, c = threadIdx.x;
-    const u32 r0 = blockIdx.y * 8;
-#pragma unroll
-    for (u32 r = r0; r < r0 + 8; r++)
-        if (r < rows) dst[(size_t)r * LN + (size_t)tile * kKtCols + c] = unsplit_word(src[((size_t)tile * rows + r) * kKtCols + c], split);
-}
 // ciphertext powers from the arena into the tile-major split table one bundle index streams against:
 // dst[((tile*T + t)*2 + comp)*128 + c] = split(A[(src[t*2+comp] + l)*N + n]),  l*N + n = tile*128 + c.
 // src[t*2+comp] = arena index of prime 0 of component comp of term t (its L primes are consecutive polynomials).
