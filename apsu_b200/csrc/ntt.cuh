@@ -146,19 +146,33 @@ __global__ void __launch_bounds__((1 << LOGN) / 16, (1 << (14 - LOGN))) ntt_kern
     const bool reduce = src.reduce_input != 0;
 
     if (FWD) {
-        // stages [0, RF): global -> registers -> shared
+        // stages [0, RF): global -> registers -> shared.  The trip count is a compile-time constant and the loads of
+        // kBatch iterations are issued together: with a run-time loop every iteration waited a full memory latency
+        // on its own two loads (long-scoreboard was the top stall of the forward transform)
         {
             constexpr unsigned stride = N >> RF;
-            for (unsigned g = threadIdx.x; g < stride; g += blockDim.x) {
-                u64 x[1 << RF];
+            constexpr unsigned kThreads = N / 16, kIters = stride / kThreads, kBatch = (RF == 1) ? 4 : 1;
+            static_assert(kIters % kBatch == 0, "first-pass batching");
+#pragma unroll 1
+            for (unsigned it = 0; it < kIters; it += kBatch) {
+                u64 x[kBatch][1 << RF];
 #pragma unroll
-                for (int k = 0; k < (1 << RF); k++) {
-                    u64 v = ip[g + k * stride];
-                    x[k] = reduce ? barrett64(v, m) : v;
+                for (unsigned b = 0; b < kBatch; b++) {
+                    const unsigned g = threadIdx.x + (it + b) * kThreads;
+#pragma unroll
+                    for (int k = 0; k < (1 << RF); k++) x[b][k] = ip[g + k * stride];
                 }
-                fwd_group<RF>(x, tw, 0, 0, nq, q3);
 #pragma unroll
-                for (int k = 0; k < (1 << RF); k++) sm[pad_idx(g + k * stride)] = x[k];
+                for (unsigned b = 0; b < kBatch; b++) {
+                    const unsigned g = threadIdx.x + (it + b) * kThreads;
+                    if (reduce) {
+#pragma unroll
+                        for (int k = 0; k < (1 << RF); k++) x[b][k] = barrett64(x[b][k], m);
+                    }
+                    fwd_group<RF>(x[b], tw, 0, 0, nq, q3);
+#pragma unroll
+                    for (int k = 0; k < (1 << RF); k++) sm[pad_idx(g + k * stride)] = x[b][k];
+                }
             }
         }
         __syncthreads();
