@@ -248,7 +248,7 @@ NttArgs DeviceContext::make_args(const std::vector<uint32_t> &pattern) const
 template <int LOGN>
 static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, bool inverse, cudaStream_t st)
 {
-    constexpr int threads = (1 << LOGN) / 16;
+    constexpr int threads = (1 << LOGN) / APSU_NTT_DIV;
     constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4)); // + one pad word per 16
     static bool configured = false;
     if (!configured) {

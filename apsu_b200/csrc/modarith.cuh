@@ -38,17 +38,18 @@ __device__ __forceinline__ u64 mul_shoup_lazy(u64 x, u64 w, u64 wq, u64 q) { ret
 __device__ __forceinline__ u64 mul_shoup_lazy3(u64 y, u64 w, u64 wq, u64 nq)
 {
     const u32 yl = (u32)y, yh = (u32)(y >> 32), wl = (u32)w, wh = (u32)(w >> 32), vl = (u32)wq, vh = (u32)(wq >> 32), nl = (u32)nq, nh = (u32)(nq >> 32);
-    u32 a0, a1, s0, s1, c, q0, q1, r0, r1;
+    u32 q0, q1, r0, r1;
     asm("{\n\t"
-        "mul.lo.u32 %0, %8, %11;\n\t"         // A = yh*vl
-        "mul.hi.u32 %1, %8, %11;\n\t"
-        "mad.lo.cc.u32 %2, %7, %12, %0;\n\t"  // S = yl*vh + A, carry c
-        "madc.hi.cc.u32 %3, %7, %12, %1;\n\t"
-        "addc.u32 %4, 0, 0;\n\t"
-        "mad.lo.cc.u32 %5, %8, %12, %3;\n\t"  // Q = yh*vh + (S.hi : c)
-        "madc.hi.u32 %6, %8, %12, %4;\n\t"
+        ".reg .u32 a0, a1, s0, s1, c;\n\t"
+        "mul.lo.u32 a0, %3, %6;\n\t"          // A = yh*vl
+        "mul.hi.u32 a1, %3, %6;\n\t"
+        "mad.lo.cc.u32 s0, %2, %7, a0;\n\t"   // S = yl*vh + A, carry c
+        "madc.hi.cc.u32 s1, %2, %7, a1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "mad.lo.cc.u32 %0, %3, %7, s1;\n\t"   // Q = yh*vh + (S.hi : c)
+        "madc.hi.u32 %1, %3, %7, c;\n\t"
         "}"
-        : "=&r"(a0), "=&r"(a1), "=&r"(s0), "=&r"(s1), "=&r"(c), "=&r"(q0), "=&r"(q1)
+        : "=&r"(q0), "=&r"(q1)
         : "r"(yl), "r"(yh), "r"(wl), "r"(wh), "r"(vl), "r"(vh));
     asm("{\n\t"
         "mul.lo.u32 %0, %4, %2;\n\t"          // R = wl*yl
