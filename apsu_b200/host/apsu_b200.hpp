@@ -209,6 +209,25 @@ public:
         detail::check(apsu_b200_db_add_binbundle_synthetic(ctx_, bundle_idx, ncoeffs, seed, &ci));
         return ci;
     }
+    // RunQuery's mask loop on the device (receiver_ddh.cpp:241-283): returns random_matrix as (low, high) words per
+    // item, [alpha_max*bundle_idx_count][items_per_bundle][2]; the masks stay device-resident for the next query
+    std::vector<std::uint64_t> generate_masks(std::uint64_t seed)
+    {
+        std::unique_lock<std::shared_mutex> lock(db_lock_);
+        const std::uint32_t bic = params_.bundle_idx_count();
+        std::uint32_t alpha = 1;
+        std::vector<std::uint32_t> cnt(bic);
+        for (std::uint32_t b = 0; b < bic; b++) {
+            detail::check(apsu_b200_db_bin_bundle_count(ctx_, b, &cnt[b]));
+            alpha = std::max(alpha, cnt[b]);
+        }
+        std::vector<std::uint8_t> padded(static_cast<std::size_t>(alpha) * bic);
+        for (std::uint32_t c = 0; c < alpha; c++)
+            for (std::uint32_t b = 0; b < bic; b++) padded[b + static_cast<std::size_t>(c) * bic] = c >= cnt[b];
+        std::vector<std::uint64_t> blocks(padded.size() * params_.items_per_bundle() * 2);
+        detail::check(apsu_b200_generate_masks(ctx_, seed, padded.data(), static_cast<std::uint32_t>(padded.size()), blocks.data(), nullptr));
+        return blocks;
+    }
     // BinBundle::regen_cache on the device (bin_bundle.cpp:934-1041): item_bins -> matching polynomials ->
     // batched plaintexts, all built and kept on the GPU
     std::uint32_t add_bin_bundle_from_bins(std::uint32_t bundle_idx, const std::vector<std::vector<std::uint64_t>> &item_bins)

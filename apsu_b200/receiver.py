@@ -189,6 +189,7 @@ class Receiver:
         self.db = db
         self._L = capi.lib()
         self._part_rank, self._part_size = 0, 1
+        self._stage_regions = None
 
     # ---- staged API (ComputePowers / ProcessBinBundleCache) ----
     def load_query(self, query: Query):
@@ -241,17 +242,23 @@ class Receiver:
         if self._part_size == 1:
             capi.check(self._L.apsu_b200_compute_powers(self.db._h))
             return
-        n = C.c_uint32()
-        capi.check(self._L.apsu_b200_powers_stage_count(self.db._h, C.byref(n)))
-        for s in range(n.value):
+        # the regions are fixed per (parameters, DB, partition); one probe per query notices a rebuilt plan
+        if self._stage_regions is not None and self._stage_regions[0] != self.powers_exchange_regions(1):
+            self._stage_regions = None
+        if self._stage_regions is None:
+            n = C.c_uint32()
+            capi.check(self._L.apsu_b200_powers_stage_count(self.db._h, C.byref(n)))
+            self._stage_regions = [self.powers_exchange_regions(s + 1) if s + 1 < n.value else None for s in range(n.value)]
+        for s, regions in enumerate(self._stage_regions):
             capi.check(self._L.apsu_b200_compute_powers_stage(self.db._h, s))
-            if s + 1 < n.value:
-                exchange(s + 1, self.powers_exchange_regions(s + 1))
+            if regions is not None:
+                exchange(s + 1, regions)
 
     def set_powers_partition(self, rank: int, size: int):
         """collective C2: this receiver computes chunk `rank` of `size` of every PowersDag level."""
         capi.check(self._L.apsu_b200_set_powers_partition(self.db._h, rank, size))
         self._part_rank, self._part_size = rank, size
+        self._stage_regions = None
 
     def powers_exchange_regions(self, level: int):
         cap = self.db.params.bundle_idx_count()

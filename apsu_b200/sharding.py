@@ -80,13 +80,21 @@ def allgather_region(full, index: int, size: int, group=None):
     dist.all_gather(list(full.view(size, words).unbind(0)), mine, group=group)
 
 
+_REGION_VIEWS = {}
+
+
 def exchange_powers(regions, index: int, size: int, group=None):
     """all-gather of one DAG level between the `size` ranks of a group: every region is a device buffer of `size`
-    chunks, this rank's products in chunk `index` (apsu_b200_powers_exchange_regions)."""
+    chunks, this rank's products in chunk `index` (apsu_b200_powers_exchange_regions).  In place (NCCL's in-place
+    all-gather: the send buffer is this rank's chunk of the receive buffer); the tensor views of a region are built
+    once, the call is on the per-query path of every rank."""
     import torch
     import torch.distributed as dist
     for ptr, chunk_bytes in regions:
-        full = torch.as_tensor(_DeviceRegion(ptr, chunk_bytes * size), device="cuda")
-        words = chunk_bytes // 8
-        mine = full[index * words:(index + 1) * words].clone()
-        dist.all_gather_into_tensor(full, mine, group=group)
+        key = (ptr, chunk_bytes, index, size)
+        views = _REGION_VIEWS.get(key)
+        if views is None:
+            full = torch.as_tensor(_DeviceRegion(ptr, chunk_bytes * size), device="cuda")
+            words = chunk_bytes // 8
+            views = _REGION_VIEWS[key] = (full, full[index * words:(index + 1) * words])
+        dist.all_gather_into_tensor(views[0], views[1], group=group)
