@@ -324,6 +324,38 @@ def test_sender_decrypt_on_device(name, degrees):
         db.close()
 
 
+def test_successive_queries_replay_the_captured_graphs():
+    """the launch sequences are captured into CUDA graphs on the first query; later queries with other ciphertexts,
+    keys and masks, and a query after the DB grew (new plan, new graphs), still match the oracle."""
+    import apsu_b200
+    sc = Scenario("1M-4096-com", [[30, 9], [20], [], [12], [18]], planted=4)
+    other = Scenario("1M-4096-com", [[1], [], [], [], []], planted=1, seed=5, build_db=False)  # another sender: keys, query, masks
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0)
+    try:
+        _upload(sc, db)
+        rx = apsu_b200.Receiver(db)
+
+        def check(q_sc):
+            masks = q_sc.masks
+            if masks.shape[0] < sc.masks.shape[0]:
+                masks = np.concatenate([masks] * (sc.masks.shape[0] // masks.shape[0] + 1))[:sc.masks.shape[0]]
+            exp = {(b, c): ct for b, c, ct in sc.db.run_query(q_sc.src_powers, q_sc.cts, q_sc.relin, masks, threads=8).results()}
+            got = {(r.bundle_idx, r.cache_idx): r.psu_result for r in rx.RunQuery(apsu_b200.Query(q_sc.src_powers, q_sc.cts, q_sc.relin), masks)}
+            assert set(got) == set(exp)
+            for key in exp:
+                assert np.array_equal(got[key].reshape(2, -1), exp[key]), key
+        check(sc)
+        check(other)
+        check(sc)
+        # the DB grows: plan and graphs are rebuilt
+        bins = sc.bins[(0, 1)]
+        assert sc.db.add_bundle_from_bins(2, bins) == 0
+        assert db.add_bin_bundle_from_bins(2, bins) == 0
+        check(other)
+    finally:
+        db.close()
+
+
 def test_error_behaviour_on_device():
     import apsu_b200
     sc = Scenario("256K-512", [[5]], planted=2)
