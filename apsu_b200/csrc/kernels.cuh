@@ -85,12 +85,17 @@ k_tensor(u64 *A, const u32 *__restrict__ a_idx, const u32 *__restrict__ b_idx, c
     u64 *d = A + ((size_t)d_idx[o] + j) * N + n;
     const size_t cs = (size_t)LS * N; // component stride
     u64 a0 = a[0], a1 = a[cs], b0 = b[0], b1 = b[cs];
-    d[0] = mul_mod(a0, b0, m);
-    Acc128 acc{ 0, 0 };
-    mac128(acc, a0, b1);
-    mac128(acc, a1, b0);
-    d[cs] = barrett_prod(acc.lo, acc.hi, m); // two products of reduced operands: below 2^(64+sh)
-    d[2 * cs] = mul_mod(a1, b1, m);
+    // three full products instead of four: a0*b1 + a1*b0 = (a0+a1)*(b0+b1) - a0*b0 - a1*b1 on the unreduced 128-bit
+    // products (operands < 2^61, so the sums fit a word and nothing wraps); each of the three values is below
+    // 2^(64+sh) and is reduced with the one-word Barrett
+    const u64 p0l = a0 * b0, p0h = mulhi(a0, b0), p2l = a1 * b1, p2h = mulhi(a1, b1);
+    const u64 sa = a0 + a1, sb = b0 + b1;
+    u64 ml = sa * sb, mh = mulhi(sa, sb);
+    asm("sub.cc.u64 %0, %0, %2;\n\tsubc.u64 %1, %1, %3;" : "+l"(ml), "+l"(mh) : "l"(p0l), "l"(p0h));
+    asm("sub.cc.u64 %0, %0, %2;\n\tsubc.u64 %1, %1, %3;" : "+l"(ml), "+l"(mh) : "l"(p2l), "l"(p2h));
+    d[0] = barrett_prod(p0l, p0h, m);
+    d[cs] = barrett_prod(ml, mh, m);
+    d[2 * cs] = barrett_prod(p2l, p2h, m);
 }
 
 // ---- BEHZ steps (6)-(8): multiply by t, fast floor (divide by q), Shenoy-Kumaresan back to q ----
