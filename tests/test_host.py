@@ -31,6 +31,17 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in capi.lib().apsu_b200_version()
 
 
+def test_header_is_plain_c_and_cites_the_reference():
+    """the drop-in boundary is a C ABI: the header compiles as C99 and every entry point's comment names the reference
+    interface it replaces."""
+    hdr = ROOT / "include" / "apsu_b200.h"
+    subprocess.check_call(["gcc", "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", str(hdr)])
+    text = hdr.read_text()
+    assert "#include <torch" not in text and "at::Tensor" not in text  # plain pointers and sizes only
+    for cite in ("receiver_ddh.cpp", "bin_bundle.cpp", "psu_params.cpp", "powers.cpp", "result_package.cpp", "receiver_db.cpp"):
+        assert cite in text, cite
+
+
 def test_params_and_powers_dag_match_oracle_for_all_parameter_sets():
     import apsu_b200
     for name, obj in TABLE.items():
