@@ -245,21 +245,34 @@ NttArgs DeviceContext::make_args(const std::vector<uint32_t> &pattern) const
     return a;
 }
 
-template <int LOGN>
-static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, bool inverse, cudaStream_t st)
+template <int LOGN, int DIV>
+static void launch_ntt_shape(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, bool inverse, cudaStream_t st)
 {
-    constexpr int threads = (1 << LOGN) / APSU_NTT_DIV;
+    constexpr int threads = (1 << LOGN) / DIV;
     constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4)); // + one pad word per 16
     static bool configured = false;
     if (!configured) {
-        APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     if (inverse)
-        ntt_kernel<LOGN, false><<<count, threads, smem, st>>>(in, out, a, s);
+        ntt_kernel<LOGN, false, DIV><<<count, threads, smem, st>>>(in, out, a, s);
     else
-        ntt_kernel<LOGN, true><<<count, threads, smem, st>>>(in, out, a, s);
+        ntt_kernel<LOGN, true, DIV><<<count, threads, smem, st>>>(in, out, a, s);
+}
+
+// picks the launch shape by batch size (ntt.cuh): more threads per polynomial while the batch leaves SMs idle
+template <int LOGN>
+static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, bool inverse, cudaStream_t st, int sms)
+{
+    // measured (N = 8192, one bundle index): 24..112 polynomials take 16 us with N/8 threads and 20-22 us with N/32;
+    // N/16 threads for 150..300 polynomials made no difference
+    constexpr int kLatDiv = LOGN >= 12 ? 8 : 16;
+    if (count <= (uint32_t)sms * ntt_min_blocks(LOGN, kLatDiv))
+        launch_ntt_shape<LOGN, kLatDiv>(in, out, count, a, s, inverse, st);
+    else
+        launch_ntt_shape<LOGN, 32>(in, out, count, a, s, inverse, st);
 }
 
 void DeviceContext::ntt(const u64 *in, u64 *out, uint32_t count, const std::vector<uint32_t> &pattern, bool inverse,
@@ -268,11 +281,13 @@ void DeviceContext::ntt(const u64 *in, u64 *out, uint32_t count, const std::vect
     if (!count) return;
     NttArgs a = make_args(pattern);
     NttSrc s{ src_idx, dst_idx, reduce_input ? 1 : 0 };
+    static int sms = 0;
+    if (!sms) APSU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     switch (logN) {
-    case 11: launch_ntt<11>(in, out, count, a, s, inverse, stream); break;
-    case 12: launch_ntt<12>(in, out, count, a, s, inverse, stream); break;
-    case 13: launch_ntt<13>(in, out, count, a, s, inverse, stream); break;
-    case 14: launch_ntt<14>(in, out, count, a, s, inverse, stream); break;
+    case 11: launch_ntt<11>(in, out, count, a, s, inverse, stream, sms); break;
+    case 12: launch_ntt<12>(in, out, count, a, s, inverse, stream, sms); break;
+    case 13: launch_ntt<13>(in, out, count, a, s, inverse, stream, sms); break;
+    case 14: launch_ntt<14>(in, out, count, a, s, inverse, stream, sms); break;
     default: throw std::invalid_argument("unsupported poly_modulus_degree");
     }
     APSU_CUDA_CHECK(cudaGetLastError());

@@ -129,18 +129,22 @@ struct MidRunner<LOGN, FWD, S, 0> {
 // One CTA per polynomial.  Stages are grouped as [RF | 3 | 3 | ... | 3] with RF = 1..3; the pass that touches
 // global memory on the way in and the one on the way out do their butterflies straight from / to global
 // memory (coalesced), so a transform costs (number of passes - 1) shared-memory round trips.
-// Launch shape: N/32 threads per CTA (each thread does four radix-8 groups per pass) and as many CTAs per SM as
-// shared memory allows (3 at N = 8192): 80 registers per thread without spills and three independent CTAs to fill
-// each other's barrier stalls.  Measured against N/16 threads x 2 CTAs (64 registers, spills): 79 -> 75 ns/poly.
-#ifndef APSU_NTT_DIV
-#define APSU_NTT_DIV 32
-#endif
-constexpr int ntt_min_blocks(int logn) { return logn >= 14 ? 1 : 3 << (13 - (logn >= 14 ? 13 : logn)); }
-#ifndef APSU_NTT_MINB
-#define APSU_NTT_MINB(LOGN) ntt_min_blocks(LOGN)
-#endif
-template <int LOGN, bool FWD>
-__global__ void __launch_bounds__((1 << LOGN) / APSU_NTT_DIV, APSU_NTT_MINB(LOGN)) ntt_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, NttArgs a, NttSrc src)
+// Launch shape: DIV = coefficients per thread.  Throughput shape (batches of more than a wave): DIV = 32, i.e. N/32
+// threads per CTA (each thread does four radix-8 groups per pass) and as many CTAs per SM as shared memory allows
+// (3 at N = 8192): 80 registers per thread without spills and three independent CTAs to fill each other's barrier
+// stalls; measured against N/16 threads x 2 CTAs (64 registers, spills): 79 -> 75 ns/poly.  Latency shapes: a batch
+// that does not fill the GPU (one bundle index on one of 8 GPUs: 24..300 polynomials) takes one CTA's latency
+// whatever its size (20 us at DIV = 32), so batches of at most one CTA per SM use DIV = 8 (N/8 threads, 16 us).
+constexpr int ntt_min_blocks(int logn, int div)
+{
+    // CTAs per SM: shared memory allows 3 << (13 - logn) (1 at logn = 14); at most 1024 resident threads so that
+    // every shape has at least 64 registers per thread
+    const int by_smem = logn >= 14 ? 1 : 3 << (13 - (logn >= 14 ? 13 : logn));
+    const int threads = (1 << logn) / div, by_threads = threads >= 1024 ? 1 : 1024 / threads;
+    return by_smem < by_threads ? by_smem : by_threads;
+}
+template <int LOGN, bool FWD, int DIV>
+__global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) ntt_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, NttArgs a, NttSrc src)
 {
     constexpr int N = 1 << LOGN;
     constexpr int RF = (LOGN % 3 == 0) ? 3 : (LOGN % 3);
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__((1 << LOGN) / APSU_NTT_DIV, APSU_NTT_MINB(LOGN
         // on its own two loads (long-scoreboard was the top stall of the forward transform)
         {
             constexpr unsigned stride = N >> RF;
-            constexpr unsigned kThreads = N / APSU_NTT_DIV, kIters = stride / kThreads, kBatch = (RF == 1) ? 4 : 1;
+            constexpr unsigned kThreads = N / DIV, kIters = stride / kThreads, kBatch = (RF == 1 && kIters % 4 == 0) ? 4 : 1;
             static_assert(kIters % kBatch == 0, "first-pass batching");
 #pragma unroll 1
             for (unsigned it = 0; it < kIters; it += kBatch) {

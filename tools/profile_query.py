@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--db-log2", type=int, default=bench.DB_LOG2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--bundles-per-idx", type=int, default=0, help="truncate every bundle index to this many BinBundles")
+    ap.add_argument("--only-idx", type=int, default=-1, help="populate this bundle index only (what one rank of an 8-GPU run holds)")
     args = ap.parse_args()
     import torch
     import apsu_b200
@@ -35,6 +36,8 @@ def main():
     degrees = bench.simulate_bundle_degrees(pj, args.db_log2, bench.SEEDS["db"])
     if args.bundles_per_idx:
         degrees = [row[:args.bundles_per_idx] for row in degrees]
+    if args.only_idx >= 0:
+        degrees = [row if b == args.only_idx else [] for b, row in enumerate(degrees)]
     params = apsu_b200.PSUParams.Load(json.dumps(pj))
     db = apsu_b200.ReceiverDB(params, 0)
     rx = apsu_b200.Receiver(db)
