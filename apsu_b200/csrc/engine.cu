@@ -393,8 +393,6 @@ uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bi
         if (bin_sizes[b] >= p.max_items_per_bin) throw std::invalid_argument("a bin holds max_items_per_bin or more items");
     }
     if (total >= (1ull << 32)) throw std::invalid_argument("too many items in one BinBundle");
-    for (size_t i = 0; i < total; i++)
-        if (roots[i] >= ctx.t) throw std::invalid_argument("bin item is not a field element (>= plain_modulus)");
     const uint32_t ncoeffs = max_deg + 1;
 
     auto s = std::make_unique<BinBundleStore>();
@@ -411,6 +409,9 @@ uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bi
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
     DBuf<uint32_t> d_first, d_size, d_rows;
     DBuf<u64> d_roots, M, enc;
+    DBuf<int> d_bad;
+    d_bad.alloc(1);
+    APSU_CUDA_CHECK(cudaMemsetAsync(d_bad.p, 0, sizeof(int), ctx.stream));
     d_first.upload(first, ctx.stream);
     d_size.alloc(nbins);
     APSU_CUDA_CHECK(cudaMemcpyAsync(d_size.p, bin_sizes, nbins * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx.stream));
@@ -429,8 +430,12 @@ uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bi
         const bool small = ctx.t < (1ull << 32);
         auto kern = small ? k_polyn_with_roots<true> : k_polyn_with_roots<false>;
         APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(nbins + warps - 1) / warps, warps * 32, smem, ctx.stream>>>(d_first.p, d_size.p, d_roots.p, M.p, nbins, max_deg, mt, (int)N);
+        kern<<<(nbins + warps - 1) / warps, warps * 32, smem, ctx.stream>>>(d_first.p, d_size.p, d_roots.p, M.p, nbins, max_deg, mt, (int)N, d_bad.p);
         APSU_LAUNCH_CHECK();
+        int bad = 0;
+        APSU_CUDA_CHECK(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+        APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+        if (bad) throw std::invalid_argument("bin item is not a field element (>= plain_modulus)");
     }
     // BatchEncoder::encode: slot permutation + inverse NTT modulo t
     k_slot_scatter<<<dim3(N / 256, ncoeffs), 256, 0, ctx.stream>>>(M.p, enc.p, ctx.slot_map.p, (int)N);

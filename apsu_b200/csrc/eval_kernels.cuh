@@ -69,7 +69,8 @@ k_ms_sum_last(u64 *A, const u32 *__restrict__ sum_idx, const u32 *__restrict__ l
 #pragma unroll
     for (int i = 0; i < kMaxQ; i++) s[i] = 0;
     const u64 *t = A + ((size_t)last_idx[b] + comp) * N + n;
-    for (u32 j = 0; j < nterms; j++) {
+#pragma unroll 4
+    for (u32 j = 0; j < nterms; j++) { // independent loads: unrolled so that four are in flight
         const u64 a = add_mod(t[(size_t)j * 2 * N], half, qk);
 #pragma unroll
         for (int i = 0; i < kMaxQ - 1; i++)
@@ -241,7 +242,7 @@ __global__ void k_fill_db(u64 *__restrict__ out, size_t count, u64 seed, int mod
 // SMALL: t < 2^32, products fit one word.
 template <bool SMALL>
 __global__ void k_polyn_with_roots(const u32 *__restrict__ bin_first, const u32 *__restrict__ bin_size, const u64 *__restrict__ roots, u64 *__restrict__ M,
-                                   u32 nbins, u32 max_deg, DMod mt, int N)
+                                   u32 nbins, u32 max_deg, DMod mt, int N, int *__restrict__ bad_input)
 {
     extern __shared__ u64 poly_smem[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
@@ -255,6 +256,10 @@ __global__ void k_polyn_with_roots(const u32 *__restrict__ bin_first, const u32 
     __syncwarp();
     for (u32 k = 0; k < d; k++) {
         const u64 a = r[k];
+        if (a >= t) { // not a field element: reported by the host after the launch
+            if (lane == 0) atomicExch(bad_input, 1);
+            return;
+        }
         const u64 neg_a = a ? t - a : 0; // negate_uint_mod
         // polynomial currently has k+1 coefficients c[0..k]; after this root k+2: c[0..k+1]
         // top coefficient first: c[k+1] = c[k] (old c[k+1] = 0)
