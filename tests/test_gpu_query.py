@@ -197,6 +197,10 @@ def test_db_build_on_device(name, degrees):
             bins = [[] for _ in range(sc.p.bins_per_bundle)]
             bins[3] = list(range(sc.p.max_items_per_bin))
             db.add_bin_bundle_from_bins(0, bins)
+        with pytest.raises(ValueError):  # an item that is not a field element
+            bins = [[] for _ in range(sc.p.bins_per_bundle)]
+            bins[5] = [1, sc.p.t, 2]
+            db.add_bin_bundle_from_bins(0, bins)
     finally:
         db.close()
 
