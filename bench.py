@@ -263,6 +263,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-db-build", action="store_true", help="skip the device DB-build measurement (row f1)")
     ap.add_argument("--no-dag-split", action="store_true", help="ranks sharing a bundle index recompute its powers instead of splitting the PowersDag")
+    ap.add_argument("--dag-split", action="store_true", help="split the PowersDag whenever ranks share a bundle index (default: only for large DAGs)")
     ap.add_argument("--chunk", type=int, default=None, help="BinBundles per evaluation chunk (APSU_B200_CHUNK)")
     args = ap.parse_args()
     if args.chunk:
@@ -345,7 +346,9 @@ def main():
     if world > 1:
         from apsu_b200 import sharding
         part_group, part_index, all_groups = sharding.powers_partition(parts, rank)
-        if args.no_dag_split:
+        dagp = apsu_b200.PowersDag(params)
+        n_products = len(dagp.nodes) - dagp.source_count()
+        if args.no_dag_split or not (args.dag_split or sharding.worth_splitting(n_products, len(part_group))):
             part_group, part_index, all_groups = [rank], 0, []
         if any(len(g) > 1 for g in all_groups):
             for g in all_groups:  # every rank creates every group

@@ -144,6 +144,7 @@ parts1 = sharding.shard_bundles([[5, 3, 1, 4]], world)
 group, index, groups = sharding.powers_partition(parts1, rank)
 assert group == [0, 1] and index == rank and groups == [[0, 1]]
 assert sharding.powers_partition(parts, rank)[0] == [rank]   # ranks owning several indices do not split
+assert sharding.worth_splitting(311, 2) and not sharding.worth_splitting(66, 2) and not sharding.worth_splitting(311, 1)
 pg = dist.new_group(group)
 full = torch.full((2 * 6,), -1, dtype=torch.int64)
 full[index * 6:(index + 1) * 6] = torch.arange(6) + 100 * rank
