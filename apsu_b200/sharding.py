@@ -47,6 +47,39 @@ def gather_results(local, counts, N: int, dst: int = 0):
     return torch.cat([o[:n] for o, n in zip(out, counts)], dim=0)
 
 
+class ResultGatherer:
+    """gather_results with every buffer allocated once (the call is on the per-query path): padded per-rank device
+    buffers, the NCCL gather, and a pinned host buffer on `dst` for the final device-to-host copy."""
+
+    def __init__(self, counts, N: int, device, dst: int = 0):
+        import torch
+        import torch.distributed as dist
+        self.counts, self.N, self.dst, self.rank = list(counts), N, dst, dist.get_rank()
+        self.pad = max(max(counts), 1)
+        self.buf = torch.zeros((self.pad, 2, N), dtype=torch.int64, device=device)
+        self.out = [torch.empty_like(self.buf) for _ in counts] if self.rank == dst else None
+        pin = device is not None and str(device) != "cpu"
+        self.host = torch.empty((sum(counts), 2, N), dtype=torch.int64, pin_memory=pin) if self.rank == dst else None
+
+    def local_buffer(self):
+        """device tensor [pad][2][N] the rank writes its results into (first counts[rank] rows)"""
+        return self.buf
+
+    def gather(self):
+        """-> host tensor [sum(counts)][2][N] on dst (rank order), None elsewhere; the copies to the host are queued on
+        the current stream, the caller synchronises."""
+        import torch.distributed as dist
+        dist.gather(self.buf, self.out, dst=self.dst)
+        if self.rank != self.dst:
+            return None
+        o = 0
+        for t, n in zip(self.out, self.counts):
+            if n:
+                self.host[o:o + n].copy_(t[:n], non_blocking=True)
+            o += n
+        return self.host
+
+
 def powers_partition(parts, rank: int):
     """PowersDag split (collective C2): if every rank owns BinBundles of exactly one bundle index, the ranks owning
     the same index form a group that splits ComputePowers.  parts = shard_bundles(...).

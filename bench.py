@@ -432,31 +432,35 @@ def main():
         bidx = np.zeros(max(n_local, 1), dtype=np.uint32)
         cidx = np.zeros(max(n_local, 1), dtype=np.uint32)
         if dist is not None:
-            d_cts = torch.empty(cts_t.shape, dtype=torch.int64, device="cuda")
-            d_relin = torch.empty(relin_t.shape, dtype=torch.int64, device="cuda")
+            # one pinned host block and one device block for the whole query (ciphertexts + relinearisation keys):
+            # one H2D copy on the rank that received it, one NCCL broadcast
+            q_host = torch.empty(cts_t.numel() + relin_t.numel(), dtype=torch.int64).pin_memory()
+            q_host[:cts_t.numel()] = cts_t.reshape(-1)
+            q_host[cts_t.numel():] = relin_t.reshape(-1)
+            d_query = torch.empty(q_host.shape, dtype=torch.int64, device="cuda")
+            d_cts, d_relin = d_query[:cts_t.numel()], d_query[cts_t.numel():]
             counts = [len(x) for x in parts]
+            gatherer = sharding.ResultGatherer(counts, N, torch.device("cuda", local_rank), dst=0)
 
         def step_e2e():
             if dist is None:
                 capi.check(lib.apsu_b200_run_query(h, src_powers, nsrc, capi.ptr(cts_p), capi.ptr(relin_p), capi.ptr(masks_p),
                                                    masks_p.shape[0], capi.ptr(out_p), capi.ptr(bidx), capi.ptr(cidx)))
             else:
-                # rank 0 holds the query on the host: H2D once, NCCL broadcast over NVLink, evaluate, gather
+                # rank 0 holds the query on the host: H2D once, NCCL broadcast over NVLink, evaluate, gather, D2H
                 if rank == 0:
-                    d_cts.copy_(cts_t, non_blocking=True)
-                    d_relin.copy_(relin_t, non_blocking=True)
-                sharding.broadcast_query([d_cts, d_relin], src=0)
+                    d_query.copy_(q_host, non_blocking=True)
+                sharding.broadcast_query([d_query], src=0)
                 capi.check(lib.apsu_b200_query_begin_device(h, src_powers, nsrc, C.c_void_p(d_cts.data_ptr())))
                 capi.check(lib.apsu_b200_set_relin_keys_device(h, C.c_void_p(d_relin.data_ptr())))
                 capi.check(lib.apsu_b200_set_masks(h, masks_p.reshape(-1), masks_p.shape[0]))
                 compute_powers()
                 capi.check(lib.apsu_b200_eval_all(h))
-                res = torch.empty((max(n_local, 1), 2, N), dtype=torch.int64, device="cuda")
                 if n_local:
-                    capi.check(lib.apsu_b200_copy_results_device(h, C.c_void_p(res.data_ptr())))
-                allres = sharding.gather_results(res[:n_local], counts, N, dst=0)
+                    capi.check(lib.apsu_b200_copy_results_device(h, C.c_void_p(gatherer.local_buffer().data_ptr())))
+                gatherer.gather()
                 if rank == 0:
-                    allres.cpu()
+                    stream.synchronize()  # the results are on the host
 
         for _ in range(args.warmup):
             step_e2e()

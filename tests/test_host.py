@@ -139,6 +139,12 @@ if rank == 0:
     for k, (b, c) in enumerate(order):
         assert int(gathered[k, 0, 0]) == b * 100 + c
     print("OK")
+# the preallocated variant used on the per-query path
+gt = sharding.ResultGatherer([len(p) for p in parts], N, "cpu", dst=0)
+gt.local_buffer()[: local.shape[0]] = local
+host = gt.gather()
+if rank == 0:
+    assert torch.equal(host, gathered)
 # PowersDag split (collective C2): both ranks own BinBundles of bundle index 0 only -> one group of two
 parts1 = sharding.shard_bundles([[5, 3, 1, 4]], world)
 group, index, groups = sharding.powers_partition(parts1, rank)
