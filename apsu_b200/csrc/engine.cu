@@ -422,15 +422,29 @@ uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bi
     APSU_CUDA_CHECK(cudaMemsetAsync(M.p, 0, M.n * 8, ctx.stream));
     APSU_CUDA_CHECK(cudaMemsetAsync(enc.p, 0, enc.n * 8, ctx.stream));
     {
-        // one warp per bin; as many warps per block as the polynomials leave shared memory for
-        const size_t per_warp = (size_t)(max_deg + 2) * 8;
-        int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (160 * 1024) / per_warp));
-        const size_t smem = per_warp * warps;
+        // one warp per bin: registers for plain moduli below 2^30 and up to 2048 coefficients, shared memory otherwise
         const DMod mt = ctx.mod_host[ctx.idx_t];
-        const bool small = ctx.t < (1ull << 32);
-        auto kern = small ? k_polyn_with_roots<true> : k_polyn_with_roots<false>;
-        APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(nbins + warps - 1) / warps, warps * 32, smem, ctx.stream>>>(d_first.p, d_size.p, d_roots.p, M.p, nbins, max_deg, mt, (int)N, d_bad.p);
+        const uint32_t need_regs = (max_deg + 1 + 31) / 32;
+        if (ctx.t < (1ull << 30) && need_regs <= 64) {
+            const int warps = 8;
+            const unsigned grid = (nbins + warps - 1) / warps;
+            auto launch = [&](auto kern) { kern<<<grid, warps * 32, 0, ctx.stream>>>(d_first.p, d_size.p, d_roots.p, M.p, nbins, (u32)ctx.t, (int)N, d_bad.p); };
+            if (need_regs <= 4) launch(k_polyn_with_roots_reg<4>);
+            else if (need_regs <= 8) launch(k_polyn_with_roots_reg<8>);
+            else if (need_regs <= 16) launch(k_polyn_with_roots_reg<16>);
+            else if (need_regs <= 32) launch(k_polyn_with_roots_reg<32>);
+            else if (need_regs <= 44) launch(k_polyn_with_roots_reg<44>);
+            else launch(k_polyn_with_roots_reg<64>);
+        } else {
+            // as many warps per block as the polynomials leave shared memory for
+            const size_t per_warp = (size_t)(max_deg + 2) * 8;
+            int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (160 * 1024) / per_warp));
+            const size_t smem = per_warp * warps;
+            const bool small = ctx.t < (1ull << 32);
+            auto kern = small ? k_polyn_with_roots<true> : k_polyn_with_roots<false>;
+            APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(nbins + warps - 1) / warps, warps * 32, smem, ctx.stream>>>(d_first.p, d_size.p, d_roots.p, M.p, nbins, max_deg, mt, (int)N, d_bad.p);
+        }
         APSU_LAUNCH_CHECK();
         int bad = 0;
         APSU_CUDA_CHECK(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));

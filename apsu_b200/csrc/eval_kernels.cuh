@@ -279,6 +279,87 @@ __global__ void k_polyn_with_roots(const u32 *__restrict__ bin_first, const u32 
     for (u32 i = lane; i <= d; i += 32) M[(size_t)i * N + bin] = c[i];
 }
 
+// polyn_with_roots for plain moduli below 2^30 and degrees up to 32*J - 1, the polynomial in REGISTERS: one warp
+// per bin, coefficient i lives in register i/32 of lane i%32, so a root's update
+// polyn[i] = polyn[i-1] - a*polyn[i] is one shuffle (the left neighbour's old value; lane 0 takes lane 31's value
+// of the register below) and one 32-bit Shoup multiply-add per register: no shared memory, no barriers.  The
+// Shoup quotients of 32 roots are computed by the 32 lanes at once.  The shared-memory kernel above (one step per
+// 32 coefficients = two shared-memory round trips and two warp barriers, 64-bit Barrett) ran at 220 G steps/s
+// and was 54 % of a BinBundle build.  block = 32*warps, grid = ceil(nbins / warps).
+// one root applied to registers 0 .. A-1 (highest first: lane 0 needs the OLD value of the register below)
+template <int J, int A>
+__device__ __forceinline__ void polyn_apply_root(u32 (&c)[J], u32 neg_a, u32 quot, u32 lane, u32 t, u32 two_t)
+{
+#pragma unroll
+    for (int j = (A < J ? A : J) - 1; j >= 0; j--) {
+        u32 prev = __shfl_up_sync(0xffffffffu, c[j], 1);
+        const u32 below = j > 0 ? __shfl_sync(0xffffffffu, c[j > 0 ? j - 1 : 0], 31) : 0u;
+        if (lane == 0) prev = below;
+        // c*neg_a mod t, lazy in [0, 2t); + prev < 3t < 2^32
+        u32 v = c[j] * neg_a - __umulhi(c[j], quot) * t + prev;
+        v = v >= two_t ? v - two_t : v;
+        c[j] = v >= t ? v - t : v;
+    }
+}
+template <int J, int A>
+__device__ __forceinline__ void polyn_apply_block(u32 (&c)[J], u32 my_neg, u32 my_quot, u32 nk, u32 lane, u32 t, u32 two_t)
+{
+    for (u32 kk = 0; kk < nk; kk++)
+        polyn_apply_root<J, A>(c, __shfl_sync(0xffffffffu, my_neg, kk), __shfl_sync(0xffffffffu, my_quot, kk), lane, t, two_t);
+}
+// dispatch on the number of active registers (a multiple of four, at most J)
+template <int J>
+__device__ __forceinline__ void polyn_apply_roots(u32 (&c)[J], u32 my_neg, u32 my_quot, u32 nk, u32 active, u32 lane, u32 t, u32 two_t)
+{
+    switch (active) {
+#define APSU_POLYN_CASE(A) \
+    case A: \
+        if (A <= ((J + 3) & ~3)) polyn_apply_block<J, A>(c, my_neg, my_quot, nk, lane, t, two_t); \
+        break;
+        APSU_POLYN_CASE(4) APSU_POLYN_CASE(8) APSU_POLYN_CASE(12) APSU_POLYN_CASE(16) APSU_POLYN_CASE(20) APSU_POLYN_CASE(24)
+        APSU_POLYN_CASE(28) APSU_POLYN_CASE(32) APSU_POLYN_CASE(36) APSU_POLYN_CASE(40) APSU_POLYN_CASE(44) APSU_POLYN_CASE(48)
+        APSU_POLYN_CASE(52) APSU_POLYN_CASE(56) APSU_POLYN_CASE(60) APSU_POLYN_CASE(64)
+#undef APSU_POLYN_CASE
+    default: polyn_apply_block<J, J>(c, my_neg, my_quot, nk, lane, t, two_t);
+    }
+}
+
+template <int J>
+__global__ void __launch_bounds__(256, (J <= 16 ? 4 : J <= 44 ? 2 : 1))
+k_polyn_with_roots_reg(const u32 *__restrict__ bin_first, const u32 *__restrict__ bin_size, const u64 *__restrict__ roots, u64 *__restrict__ M, u32 nbins,
+                       u32 t, int N, int *__restrict__ bad_input)
+{
+    const u32 lane = threadIdx.x & 31, bin = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (bin >= nbins) return;
+    const u32 d = bin_size[bin];
+    const u64 *r = roots + bin_first[bin];
+    u32 c[J];
+#pragma unroll
+    for (int j = 0; j < J; j++) c[j] = 0;
+    if (lane == 0) c[0] = 1;
+    const u32 two_t = 2 * t;
+    for (u32 k0 = 0; k0 < d; k0 += 32) {
+        // lane l prepares root k0 + l: -a mod t and its Shoup quotient floor(-a * 2^32 / t)
+        u32 my_neg = 0, my_quot = 0;
+        if (k0 + lane < d) {
+            const u64 a = r[k0 + lane];
+            if (a >= t) atomicExch(bad_input, 1);
+            my_neg = a ? t - (u32)(a % t) : 0;
+            my_quot = (u32)(((u64)my_neg << 32) / t);
+        }
+        const u32 nk = min(32u, d - k0);
+        // registers that can hold a coefficient while these 32 roots are applied: 0 .. (k0 + 32) / 32, rounded up to
+        // a multiple of four so that the update runs as one of J/4 branch-free instances
+        const u32 active = min((u32)J, (((k0 >> 5) + 2) + 3) & ~3u);
+        polyn_apply_roots<J>(c, my_neg, my_quot, nk, active, lane, t, two_t);
+    }
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+        const u32 i = 32 * j + lane;
+        if (i <= d) M[(size_t)i * N + bin] = c[j];
+    }
+}
+
 // vec_to_std_block (receiver/apsu/receiver_ddh.cpp:70-92, sender/apsu/sender_ddh.cpp has the same helper): packs
 // the felts of one item into a 128-bit block, returned as (low, high) words.  val(j) = felt j of the item.
 template <typename F>
