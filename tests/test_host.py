@@ -42,6 +42,25 @@ def test_header_is_plain_c_and_cites_the_reference():
         assert cite in text, cite
 
 
+def test_db_stream_lane_bounds_hold_for_every_prime_size():
+    """the Karatsuba lanes of the DB-stream kernel (csrc/db_stream.cuh, split / fold period as computed in
+    Engine::Engine): for every prime size the kk lane cannot overflow between folds and the rebuilt sum stays below
+    2^(64+sh), the precondition of the one-word Barrett of the epilogue."""
+    TS = 4
+    for b in range(12, 61):
+        s = max(1, (b + 1) // 2)
+        sum_max = (2**s - 1) + (2**max(0, b - s) - 1)
+        cap = ((2**64 - 1) - 2**(s + 1)) // (sum_max * sum_max)
+        assert cap >= TS, b
+        terms = (cap // TS) * TS                       # terms between two folds
+        q = 2**b - 1                                   # any modulus of b bits is below this
+        # lanes after a fold: ll < 2^s, kk = lo + hi < 2^(s+1), hh = 0; then `terms` products
+        assert 2**(s + 1) + terms * sum_max * sum_max < 2**64, b
+        assert 2**s + terms * (2**s - 1)**2 < 2**64 and terms * (2**max(0, b - s) - 1)**2 < 2**64, b
+        # value of the lanes: the folded residue plus `terms` products of residues
+        assert q + terms * q * q < 2**(64 + b - 1), b
+
+
 def test_params_and_powers_dag_match_oracle_for_all_parameter_sets():
     import apsu_b200
     for name, obj in TABLE.items():
