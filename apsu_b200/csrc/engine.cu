@@ -282,6 +282,7 @@ void Engine::clear_db()
 {
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
     for (auto &v : db) v.clear();
+    for (DBuf<u64> *b : { &build_roots_, &build_M_, &build_enc_, &stage_ }) b->release(); // build scratch
     invalidate_plan();
 }
 
@@ -407,20 +408,21 @@ uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bi
     s->plain_coeffs.alloc((size_t)s->n_plain * N);
 
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
-    DBuf<uint32_t> d_first, d_size, d_rows;
-    DBuf<u64> d_roots, M, enc;
-    DBuf<int> d_bad;
-    d_bad.alloc(1);
+    // scratch of the build is kept between calls (a DB build is dozens of BinBundles of the same shape)
+    DBuf<uint32_t> &d_first = build_first_, &d_size = build_size_, &d_rows = build_rows_;
+    DBuf<u64> &d_roots = build_roots_, &M = build_M_, &enc = build_enc_;
+    DBuf<int> &d_bad = build_bad_;
+    d_bad.ensure(1);
     APSU_CUDA_CHECK(cudaMemsetAsync(d_bad.p, 0, sizeof(int), ctx.stream));
     d_first.upload(first, ctx.stream);
-    d_size.alloc(nbins);
+    d_size.ensure(nbins);
     APSU_CUDA_CHECK(cudaMemcpyAsync(d_size.p, bin_sizes, nbins * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx.stream));
-    d_roots.alloc(std::max<size_t>(total, 1));
+    d_roots.ensure(std::max<size_t>(total, 1));
     if (total) APSU_CUDA_CHECK(cudaMemcpyAsync(d_roots.p, roots, total * 8, cudaMemcpyHostToDevice, ctx.stream));
-    M.alloc((size_t)ncoeffs * N);
-    enc.alloc((size_t)ncoeffs * N);
-    APSU_CUDA_CHECK(cudaMemsetAsync(M.p, 0, M.n * 8, ctx.stream));
-    APSU_CUDA_CHECK(cudaMemsetAsync(enc.p, 0, enc.n * 8, ctx.stream));
+    M.ensure((size_t)ncoeffs * N);
+    enc.ensure((size_t)ncoeffs * N);
+    APSU_CUDA_CHECK(cudaMemsetAsync(M.p, 0, (size_t)ncoeffs * N * 8, ctx.stream));
+    APSU_CUDA_CHECK(cudaMemsetAsync(enc.p, 0, (size_t)ncoeffs * N * 8, ctx.stream));
     {
         // one warp per bin: registers for plain moduli below 2^30 and up to 2048 coefficients, shared memory otherwise
         const DMod mt = ctx.mod_host[ctx.idx_t];

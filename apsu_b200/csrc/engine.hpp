@@ -178,6 +178,9 @@ private:
     void prepare_plain_high(BinBundleStore &s);
     void pack_tile(const u64 *src, u64 *dst, uint32_t rows, uint32_t L);
     DBuf<u64> stage_;         // staging for uploads in the standard layout
+    DBuf<uint32_t> build_first_, build_size_, build_rows_; // scratch of add_binbundle_from_bins, kept between calls
+    DBuf<u64> build_roots_, build_M_, build_enc_;
+    DBuf<int> build_bad_;
     int split_ = 30;          // bit position the DB-stream operands are split at
     uint32_t fold_stages_ = 1; // ring stages between lane folds in the DB-stream kernel
     size_t add_desc(const void *data, size_t bytes);
