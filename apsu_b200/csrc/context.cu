@@ -268,7 +268,7 @@ static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a
 {
     // measured (N = 8192, one bundle index): 24..112 polynomials take 16 us with N/8 threads and 20-22 us with N/32;
     // N/16 threads for 150..300 polynomials made no difference
-    constexpr int kLatDiv = LOGN >= 12 ? 8 : 16;
+    constexpr int kLatDiv = (LOGN == 12 || LOGN == 13) ? 8 : 16; // at most 1024 threads per CTA
     if (count <= (uint32_t)sms * ntt_min_blocks(LOGN, kLatDiv))
         launch_ntt_shape<LOGN, kLatDiv>(in, out, count, a, s, inverse, st);
     else

@@ -126,7 +126,7 @@ struct MidRunner<LOGN, FWD, S, 0> {
     __device__ static __forceinline__ void run(u64 *, const ulonglong2 *, u64, u64) {}
 };
 
-// One CTA per polynomial.  Stages are grouped as [RF | 3 | 3 | ... | 3] with RF = 1..3; the pass that touches
+// One CTA per polynomial.  Stages are grouped as [RF | 3 | 3 | ... | 3] with RF = 2..4; the pass that touches
 // global memory on the way in and the one on the way out do their butterflies straight from / to global
 // memory (coalesced), so a transform costs (number of passes - 1) shared-memory round trips.
 // Launch shape: DIV = coefficients per thread.  Throughput shape (batches of more than a wave): DIV = 32, i.e. N/32
@@ -147,7 +147,7 @@ template <int LOGN, bool FWD, int DIV>
 __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) ntt_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, NttArgs a, NttSrc src)
 {
     constexpr int N = 1 << LOGN;
-    constexpr int RF = (LOGN % 3 == 0) ? 3 : (LOGN % 3);
+    constexpr int RF = (LOGN % 3 == 0) ? 3 : (LOGN % 3 == 1 ? 4 : 2); // 13 = 4+3+3+3: one shared-memory round trip less than 1+3+3+3+3
     constexpr int MID = (LOGN - RF - 3) / 3;
     extern __shared__ u64 sm[];
     const unsigned p = blockIdx.x;
@@ -165,10 +165,11 @@ __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) 
         // on its own two loads (long-scoreboard was the top stall of the forward transform)
         {
             constexpr unsigned stride = N >> RF;
-            constexpr unsigned kThreads = N / DIV, kIters = stride / kThreads, kBatch = (RF == 1 && kIters % 4 == 0) ? 4 : 1;
+            constexpr unsigned kThreads = N / DIV, kIters = (stride + kThreads - 1) / kThreads, kBatch = (RF == 1 && kIters % 4 == 0) ? 4 : 1;
             static_assert(kIters % kBatch == 0, "first-pass batching");
 #pragma unroll 1
             for (unsigned it = 0; it < kIters; it += kBatch) {
+                if (stride < kThreads && threadIdx.x >= stride) break; // more threads than groups (latency shape)
                 u64 x[kBatch][1 << RF];
 #pragma unroll
                 for (unsigned b = 0; b < kBatch; b++) {
