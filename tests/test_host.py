@@ -61,6 +61,21 @@ def test_db_stream_lane_bounds_hold_for_every_prime_size():
         assert q + terms * q * q < 2**(64 + b - 1), b
 
 
+def test_vec_to_std_block_restatement_matches_a_hand_computed_block():
+    """tests/harness.py::ref_vec_to_std_block (the checker of row f3/f4) against a value worked out by hand from
+    receiver/apsu/receiver_ddh.cpp:70-92: t = 65537 -> len 17, masks 0x1FFFF / 0xFF / 0x1FF00; felts [1,2,3,4,5]."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from harness import ref_vec_to_std_block
+    # odd count: lower = 5 & 0xFF = 5, higher = (5 & 0x1FF00) >> 7 = 0
+    # pla = 0: lower = 1 | 5 << 17 = 0xA0001, higher = 2 | 0 << 17 = 2
+    # pla = 2: lower = 3 | 0xA0001 << 17 = 0x1400020003, higher = 4 | 2 << 17 = 0x40004
+    assert ref_vec_to_std_block([1, 2, 3, 4, 5], 5, 65537) == (0x1400020003, 0x40004)
+    # even count, the shift quirk of the odd branch is not taken: [7, 9] -> lower 7, higher 9
+    assert ref_vec_to_std_block([7, 9], 2, 65537) == (7, 9)
+    # a high felt bit reaches `higher` through mask_higher >> (len/2 - 1): 0x1FF00 >> 7 = 0x3FE
+    assert ref_vec_to_std_block([0x1FF00], 1, 65537) == (0, 0x3FE)
+
+
 def test_params_and_powers_dag_match_oracle_for_all_parameter_sets():
     import apsu_b200
     for name, obj in TABLE.items():
