@@ -515,6 +515,8 @@ def main():
                     "h2d_bytes_per_step": int(cts.nbytes + relin.nbytes + masks_local.nbytes),
                     "d2h_bytes_per_step": int(n_bundles * 2 * N * 8)},
             "gpu_launches": int(tm["kernel_launches"]) * args.steps,
+            "launch_mode": "eager" if os.environ.get("APSU_B200_NO_GRAPH", "0") not in ("", "0") else
+                           f"CUDA graphs replayed per query ({int(tm['kernel_launches'])} kernel nodes of this repo's kernels per query)",
         }
         if not args.no_cpu_baseline and world == 1:
             # bounded CPU sample of the same workload + bit-exact spot check of those BinBundles
