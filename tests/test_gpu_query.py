@@ -360,6 +360,34 @@ def test_successive_queries_replay_the_captured_graphs():
         db.close()
 
 
+@pytest.mark.parametrize("name,big,few", [("16M-4096", 1303, 3), ("256M-4096", 2100, 2), ("1M-1-32", 227, 5)])
+def test_db_build_large_degrees(name, big, few):
+    """row f1 at the degrees the small scenarios do not reach: a full 16M-4096 bin (1303 items: the 44-register
+    instance of k_polyn_with_roots_reg and every active-register case below it) and a 2100-item bin of 256M-4096 (more
+    than 2048 coefficients: the shared-memory kernel).  Device-built plaintexts equal the oracle-built ones."""
+    import apsu_b200
+    from oracle import oracle as O
+    p = O.Params.load(name)
+    ctx = O.Context.from_params(p)
+    rng = np.random.default_rng(11)
+    bins = [[] for _ in range(p.bins_per_bundle)]
+    for i in range(few):
+        bins[i * 97 % p.bins_per_bundle] = rng.integers(0, p.t, size=big - i, dtype=np.uint64).tolist()
+    for i in range(few, 40):
+        bins[(i * 131 + 7) % p.bins_per_bundle] = rng.integers(0, p.t, size=int(rng.integers(0, 70)), dtype=np.uint64).tolist()
+    odb = O.ReceiverDB(ctx, p)
+    assert odb.add_bundle_from_bins(0, bins) == 0
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(p.to_json()), 0)
+    try:
+        assert db.add_bin_bundle_from_bins(0, bins) == 0
+        coeffs = odb.bundle_coeffs(0, 0)
+        assert len(coeffs) == big + 1
+        for k, (L, arr) in enumerate(coeffs):
+            assert np.array_equal(db.bin_bundle_coeff(0, 0, k), arr), k
+    finally:
+        db.close()
+
+
 def test_error_behaviour_on_device():
     import apsu_b200
     sc = Scenario("256K-512", [[5]], planted=2)
