@@ -115,9 +115,11 @@ int apsu_b200_db_add_binbundle(
  * the device from a counter-based splitmix64 stream (same stream as the oracle's synthetic fill). */
 int apsu_b200_db_add_binbundle_synthetic(
     apsu_b200_ctx *ctx, uint32_t bundle_idx, uint32_t ncoeffs, uint64_t seed, uint32_t *cache_idx);
-/* "next" row f1 — BinBundle::regen_cache (bin_bundle.cpp:934-1041): build the cache on the device from
+/* Row f1 — BinBundle::regen_cache (bin_bundle.cpp:934-1041): build the cache on the device from
  * raw bins: polyn_with_roots per bin (interpolate.cpp:63-80), column gather, BatchEncoder::encode,
- * transform_to_ntt (bin_bundle.cpp:366-430).  bin_sizes[bins_per_bundle], roots concatenated. */
+ * transform_to_ntt (bin_bundle.cpp:366-430); the plaintexts are bit-identical to the ones the reference
+ * builds.  bin_sizes[bins_per_bundle] (each below max_items_per_bin, receiver_db.cpp:388-389), roots = the
+ * bins' field elements concatenated (each below plain_modulus, else APSU_B200_ERR_INVALID_ARGUMENT). */
 int apsu_b200_db_add_binbundle_from_bins(
     apsu_b200_ctx *ctx, uint32_t bundle_idx, const uint32_t *bin_sizes, const uint64_t *roots, uint32_t *cache_idx);
 /* ReceiverDB::get_bin_bundle_count(bundle_idx) / () — receiver_db.cpp:742-760. */
