@@ -92,7 +92,11 @@ SIGNATURES = {
     "apsu_b200_get_power": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]),
     "apsu_b200_set_masks": (C.c_int, [vp, u64p, C.c_uint32]),
     "apsu_b200_encode_masks": (C.c_int, [vp, u64p, C.c_uint32, u64p]),
-    "apsu_b200_generate_masks": (C.c_int, [vp, C.c_uint64, vp, C.c_uint32, vp, vp]),
+    "apsu_b200_generate_masks": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp]),
+    "apsu_b200_query_begin_seeded": (C.c_int, [vp, u32p, C.c_uint32, vp, vp]),
+    "apsu_b200_set_relin_keys_seeded": (C.c_int, [vp, vp, vp]),
+    "apsu_b200_op_prng_stream": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64]),
+    "apsu_b200_op_expand_seeds": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp]),
     "apsu_b200_decrypt_results": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, vp]),
     "apsu_b200_set_powers_partition": (C.c_int, [vp, C.c_uint32, C.c_uint32]),
     "apsu_b200_powers_stage_count": (C.c_int, [vp, C.POINTER(C.c_uint32)]),

@@ -236,7 +236,7 @@ int apsu_b200_set_relin_keys(apsu_b200_ctx *ctx, const uint64_t *keys)
     return guarded([&] {
         Engine &e = E(ctx);
         e.set_relin_keys(keys, false);
-        APSU_CUDA_CHECK(cudaStreamSynchronize(e.ctx.stream));
+        e.throw_if_query_invalid();
     });
 }
 int apsu_b200_set_relin_keys_device(apsu_b200_ctx *ctx, const void *keys_device)
@@ -248,7 +248,7 @@ int apsu_b200_query_begin(apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32
     return guarded([&] {
         Engine &e = E(ctx);
         e.query_begin(src_powers, nsrc, cts, false);
-        APSU_CUDA_CHECK(cudaStreamSynchronize(e.ctx.stream));
+        e.throw_if_query_invalid();
     });
 }
 int apsu_b200_query_begin_device(apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const void *cts_device)
@@ -300,7 +300,23 @@ int apsu_b200_powers_exchange_regions(apsu_b200_ctx *ctx, uint32_t level, void *
 {
     return guarded([&] { *need(count, "count") = E(ctx).powers_exchange_regions(level, device_ptrs, chunk_bytes, capacity); });
 }
-int apsu_b200_generate_masks(apsu_b200_ctx *ctx, uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *random_matrix, uint64_t *slot_values)
+int apsu_b200_query_begin_seeded(apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *c0, const uint8_t *seeds)
+{
+    return guarded([&] {
+        Engine &e = E(ctx);
+        e.query_begin_seeded(src_powers, nsrc, c0, seeds);
+        e.throw_if_query_invalid();
+    });
+}
+int apsu_b200_set_relin_keys_seeded(apsu_b200_ctx *ctx, const uint64_t *c0, const uint8_t *seeds)
+{
+    return guarded([&] {
+        Engine &e = E(ctx);
+        e.set_relin_keys_seeded(c0, seeds);
+        e.throw_if_query_invalid();
+    });
+}
+int apsu_b200_generate_masks(apsu_b200_ctx *ctx, const uint8_t *seed, const uint8_t *padded, uint32_t npack, uint64_t *random_matrix, uint64_t *slot_values)
 {
     return guarded([&] { E(ctx).generate_masks(seed, padded, npack, random_matrix, slot_values); });
 }
@@ -376,6 +392,15 @@ int apsu_b200_op_relinearize(apsu_b200_ctx *ctx, uint32_t num_primes, const uint
 int apsu_b200_op_mod_switch_next(apsu_b200_ctx *ctx, uint32_t num_primes, const uint64_t *in, uint64_t *out, uint32_t n_polys)
 {
     return guarded([&] { E(ctx).op_mod_switch_next(num_primes, in, out, n_polys); });
+}
+
+int apsu_b200_op_prng_stream(apsu_b200_ctx *ctx, const uint8_t *seed, uint64_t first_refill, uint64_t *out, uint64_t n_words)
+{
+    return guarded([&] { E(ctx).op_prng_stream(seed, first_refill, out, (size_t)n_words); });
+}
+int apsu_b200_op_expand_seeds(apsu_b200_ctx *ctx, uint32_t num_primes, const uint8_t *seeds, uint32_t n, uint64_t *out)
+{
+    return guarded([&] { E(ctx).op_expand_seeds(num_primes, seeds, n, out); });
 }
 
 int apsu_b200_last_timings(apsu_b200_ctx *ctx, apsu_b200_timings *out)

@@ -9,6 +9,9 @@ namespace apsu_b200 {
 using hm::invm;
 using hm::mulm;
 
+template <int LOGN>
+static void configure_ntt(); // below, with the launch shapes
+
 static DMod make_mod(uint64_t q)
 {
     DMod m;
@@ -56,6 +59,13 @@ DeviceContext::DeviceContext(const apsu_b200_params &p, int dev) : params(p), de
     high_L = level_for_chain(1);
     APSU_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     owns_stream = true;
+    APSU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    switch (logN) {
+    case 11: configure_ntt<11>(); break;
+    case 12: configure_ntt<12>(); break;
+    case 13: configure_ntt<13>(); break;
+    default: configure_ntt<14>(); break;
+    }
     build_moduli();
     build_levels();
     APSU_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -250,12 +260,6 @@ static void launch_ntt_shape(const u64 *in, u64 *out, uint32_t count, const NttA
 {
     constexpr int threads = (1 << LOGN) / DIV;
     constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4)); // + one pad word per 16
-    static bool configured = false;
-    if (!configured) {
-        APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     if (inverse)
         ntt_kernel<LOGN, false, DIV><<<count, threads, smem, st>>>(in, out, a, s);
     else
@@ -263,6 +267,23 @@ static void launch_ntt_shape(const u64 *in, u64 *out, uint32_t count, const NttA
 }
 
 // picks the launch shape by batch size (ntt.cuh): more threads per polynomial while the batch leaves SMs idle
+// Function attributes are per device: every DeviceContext opts its device's kernel instances into the large
+// dynamic shared-memory size once, in its constructor (two contexts on different GPUs of one process both work).
+template <int LOGN, int DIV>
+static void configure_ntt_shape()
+{
+    constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4));
+    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+template <int LOGN>
+static void configure_ntt()
+{
+    constexpr int kLatDiv = (LOGN == 12 || LOGN == 13) ? 8 : 16;
+    configure_ntt_shape<LOGN, kLatDiv>();
+    configure_ntt_shape<LOGN, 32>();
+}
+
 template <int LOGN>
 static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, bool inverse, cudaStream_t st, int sms)
 {
@@ -281,8 +302,6 @@ void DeviceContext::ntt(const u64 *in, u64 *out, uint32_t count, const std::vect
     if (!count) return;
     NttArgs a = make_args(pattern);
     NttSrc s{ src_idx, dst_idx, reduce_input ? 1 : 0 };
-    static int sms = 0;
-    if (!sms) APSU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     switch (logN) {
     case 11: launch_ntt<11>(in, out, count, a, s, inverse, stream, sms); break;
     case 12: launch_ntt<12>(in, out, count, a, s, inverse, stream, sms); break;

@@ -69,6 +69,7 @@ public:
 
     apsu_b200_params params;
     int device = 0;
+    int sms = 0; // SM count of `device`
     uint32_t N = 0, logN = 0, K = 0;
     uint64_t t = 0;
     uint32_t first_L = 0; // primes at the first data level

@@ -1,4 +1,5 @@
 #include "engine.hpp"
+#include "blake2.cuh"
 #include "db_stream.cuh"
 #include "eval_kernels.cuh"
 #include "hostmath.hpp"
@@ -8,6 +9,7 @@
 #include <cstring>
 #include <array>
 #include <map>
+#include <sys/random.h>
 
 namespace apsu_b200 {
 
@@ -247,6 +249,18 @@ Engine::Engine(const apsu_b200_params &p, int device) : ctx(p, device)
         fold_stages_ = (uint32_t)std::min<unsigned __int128>(cap / kKtTS, 0x7FFFFFFFu);
     }
     levels_dev_.upload(ctx.level, ctx.stream);
+    query_bad_.alloc(2);
+    APSU_CUDA_CHECK(cudaMemsetAsync(query_bad_.p, 0, 2 * sizeof(int), ctx.stream));
+    {
+        // function attributes are per device: set once per context, not per launch
+        auto kern = k_db_mac_kt<kKtStages, kKtCtasPerSm>;
+        constexpr size_t smem = kt_smem_bytes(kKtStages);
+        APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        APSU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kKtThreads, smem));
+        per_sm = std::max(1, std::min(per_sm, kKtCtasPerSm));
+        kt_grid_cap_ = (uint32_t)(ctx.sms * per_sm);
+    }
     if (const char *ev = std::getenv("APSU_B200_NO_GRAPH")) use_graphs_ = atoi(ev) == 0;
     for (auto &ev : ev_) APSU_CUDA_CHECK(cudaEventCreate(&ev));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
@@ -489,6 +503,7 @@ void Engine::set_relin_keys(const void *keys, bool on_device)
     size_t words = (size_t)(ctx.K - 1) * 2 * ctx.K * ctx.N;
     relin_keys_.ensure(words);
     APSU_CUDA_CHECK(cudaMemcpyAsync(relin_keys_.p, keys, words * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
+    check_range(relin_keys_.p, (ctx.K - 1) * 2 * ctx.K, ctx.params.coeff_modulus, ctx.K); // is_valid_for(relin_keys), query.cpp:45-51
     have_keys_ = true;
 }
 
@@ -504,9 +519,9 @@ void Engine::encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t 
 {
     if (!slot_values || !out || !npack) throw std::invalid_argument("encode_masks: bad arguments");
     const uint32_t N = ctx.N;
-    DBuf<u64> in, enc;
-    in.alloc((size_t)npack * N);
-    enc.alloc((size_t)npack * N);
+    DBuf<u64> &in = aux_[0], &enc = aux_[1]; // scratch kept between calls
+    in.ensure((size_t)npack * N);
+    enc.ensure((size_t)npack * N);
     APSU_CUDA_CHECK(cudaMemcpyAsync(in.p, slot_values, (size_t)npack * N * 8, cudaMemcpyHostToDevice, ctx.stream));
     k_slot_scatter<<<dim3(N / 256, npack), 256, 0, ctx.stream>>>(in.p, enc.p, ctx.slot_map.p, (int)N);
     APSU_LAUNCH_CHECK();
@@ -515,26 +530,73 @@ void Engine::encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t 
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
 }
 
-// RunQuery's mask generation on the device (receiver_ddh.cpp:241-283): values, their encodings (kept resident as
-// the masks of the next evaluation) and the PEQT blocks.
-void Engine::generate_masks(uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out)
+// RunQuery's mask generation on the device (receiver_ddh.cpp:218-283): SEAL's blake2xb generator keyed with 64 seed
+// bytes (the reference takes them from random_bytes, :221-225; a NULL seed does the same here through getrandom),
+// one 32-bit draw per slot in (cache_idx, bundle_idx) order skipping padded pairs, the values' encodings (kept
+// resident as the masks of the next evaluation) and the PEQT blocks.
+void Engine::generate_masks(const uint8_t *seed64, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out)
 {
     if (!padded || !npack) throw std::invalid_argument("generate_masks: bad arguments");
     const uint32_t N = ctx.N, ipb = ctx.params.items_per_bundle;
-    DBuf<u64> values, blocks;
-    DBuf<unsigned char> pad;
-    values.alloc((size_t)npack * N);
-    blocks.alloc((size_t)npack * ipb * 2);
-    pad.alloc(npack);
+    PrngSeed seed;
+    if (seed64) {
+        std::memcpy(seed.w, seed64, sizeof(seed.w));
+    } else {
+        size_t got = 0; // random_bytes (receiver_ddh.cpp:223)
+        while (got < sizeof(seed.w)) {
+            ssize_t r = getrandom(reinterpret_cast<unsigned char *>(seed.w) + got, sizeof(seed.w) - got, 0);
+            if (r < 0) throw std::runtime_error("getrandom failed");
+            got += (size_t)r;
+        }
+    }
+    std::vector<uint32_t> seq(npack);
+    uint32_t s = 0;
+    for (uint32_t p = 0; p < npack; p++) seq[p] = padded[p] ? 0xFFFFFFFFu : s++;
+    DBuf<u64> &values = aux_[0], &blocks = aux_[1];
+    values.ensure((size_t)npack * N);
+    blocks.ensure((size_t)npack * ipb * 2);
+    aux_bytes_.ensure(npack);
     masks_.ensure((size_t)npack * N);
-    APSU_CUDA_CHECK(cudaMemcpyAsync(pad.p, padded, npack, cudaMemcpyHostToDevice, ctx.stream));
-    k_gen_masks<<<dim3(N / 256, npack), 256, 0, ctx.stream>>>(values.p, masks_.p, blocks.p, pad.p, ctx.slot_map.p, seed, ctx.t, ctx.params.felts_per_item, ipb, (int)N);
+    aux_idx_.upload(seq, ctx.stream);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(aux_bytes_.p, padded, npack, cudaMemcpyHostToDevice, ctx.stream));
+    k_prng_mask_values<<<dim3(N / 1024, npack), 64, 0, ctx.stream>>>(values.p, aux_idx_.p, seed, ctx.t, (int)N);
+    APSU_LAUNCH_CHECK();
+    k_masks_scatter_blocks<<<dim3(N / 256, npack), 256, 0, ctx.stream>>>(values.p, masks_.p, blocks.p, aux_bytes_.p, ctx.slot_map.p, ctx.t,
+                                                                          ctx.params.felts_per_item, ipb, (int)N);
     APSU_LAUNCH_CHECK();
     ctx.ntt(masks_.p, masks_.p, npack, { ctx.idx_t }, true);
     npack_ = npack;
-    if (blocks_out) APSU_CUDA_CHECK(cudaMemcpyAsync(blocks_out, blocks.p, blocks.n * 8, cudaMemcpyDeviceToHost, ctx.stream));
-    if (values_out) APSU_CUDA_CHECK(cudaMemcpyAsync(values_out, values.p, values.n * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    if (blocks_out) APSU_CUDA_CHECK(cudaMemcpyAsync(blocks_out, blocks.p, (size_t)npack * ipb * 2 * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    if (values_out) APSU_CUDA_CHECK(cudaMemcpyAsync(values_out, values.p, (size_t)npack * N * 8, cudaMemcpyDeviceToHost, ctx.stream));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+
+// sample_poly_uniform for `n` seeded polynomials of L primes each into arena blocks dst[k] ([L][N]); seeds on the host
+void Engine::expand_seeds(uint32_t L, const std::vector<uint32_t> &dst, const uint8_t *seeds64, u64 *base, const uint64_t *moduli)
+{
+    const uint32_t n = (uint32_t)dst.size(), N = ctx.N;
+    if (!n) return;
+    UniformMods um;
+    std::memset(&um, 0, sizeof(um));
+    um.L = (int)L;
+    for (uint32_t j = 0; j < L; j++) {
+        const uint64_t q = moduli[j];
+        for (size_t m = 0; m < ctx.mod_values.size(); m++)
+            if (ctx.mod_values[m] == q) um.q[j] = ctx.mod_host[m];
+        um.max_multiple[j] = ~0ull - (~0ull % q) - 1;
+    }
+    seed_buf_.ensure((size_t)n * sizeof(PrngSeed));
+    rej_.ensure((size_t)n * (kMaxRej + 1));
+    APSU_CUDA_CHECK(cudaMemcpyAsync(seed_buf_.p, seeds64, (size_t)n * sizeof(PrngSeed), cudaMemcpyHostToDevice, ctx.stream));
+    APSU_CUDA_CHECK(cudaMemsetAsync(rej_.p, 0, (size_t)n * sizeof(uint32_t), ctx.stream));
+    seed_dst_.upload(dst, ctx.stream);
+    const PrngSeed *sd = reinterpret_cast<const PrngSeed *>(seed_buf_.p);
+    uint32_t *rej_count = rej_.p, *rej_pos = rej_.p + n;
+    k_prng_sample_uniform<<<dim3(L * N / 512, n), 64, 0, ctx.stream>>>(base, seed_dst_.p, sd, um, (int)N, rej_count, rej_pos);
+    APSU_LAUNCH_CHECK();
+    k_prng_fix_rejects<<<(n + 63) / 64, 64, 0, ctx.stream>>>(base, seed_dst_.p, sd, um, (int)N, rej_count, rej_pos, n, query_bad_.p + 1);
+    query_checked_ = true;
+    APSU_LAUNCH_CHECK();
 }
 
 // ResultPackage::extract for a batch of result ciphertexts (result_package.cpp:175-213, sender_ddh.cpp:580-605):
@@ -545,21 +607,21 @@ void Engine::decrypt_results(const uint64_t *secret_ntt_q0, const uint64_t *cts,
     if (!secret_ntt_q0 || !cts || !n || !values_out) throw std::invalid_argument("decrypt_results: bad arguments");
     const uint32_t N = ctx.N, ipb = ctx.params.items_per_bundle;
     const DMod q0 = ctx.mod_host[0];
-    DBuf<u64> d_ct, d_s, tmp, plain, values, blocks;
-    DBuf<int> budget;
-    DBuf<uint32_t> src_idx;
-    d_ct.alloc((size_t)n * 2 * N);
-    d_s.alloc(N);
-    tmp.alloc((size_t)n * N);
-    plain.alloc((size_t)n * N);
-    values.alloc((size_t)n * N);
-    blocks.alloc((size_t)n * ipb * 2);
-    budget.alloc(n);
+    DBuf<u64> &d_ct = aux_[0], &d_s = aux_[1], &tmp = aux_[2], &plain = aux_[3], &values = aux_[4], &blocks = aux_[5]; // kept between calls
+    DBuf<int> &budget = aux_int_;
+    DBuf<uint32_t> &src_idx = aux_idx_;
+    d_ct.ensure((size_t)n * 2 * N);
+    d_s.ensure(N);
+    tmp.ensure((size_t)n * N);
+    plain.ensure((size_t)n * N);
+    values.ensure((size_t)n * N);
+    blocks.ensure((size_t)n * ipb * 2);
+    budget.ensure(n);
     std::vector<uint32_t> idx(n);
     for (uint32_t k = 0; k < n; k++) idx[k] = 2 * k + 1; // the c1 polynomials
     src_idx.upload(idx, ctx.stream);
     std::vector<int> big(n, 1 << 20);
-    APSU_CUDA_CHECK(cudaMemcpyAsync(d_ct.p, cts, d_ct.n * 8, cudaMemcpyHostToDevice, ctx.stream));
+    APSU_CUDA_CHECK(cudaMemcpyAsync(d_ct.p, cts, (size_t)n * 2 * N * 8, cudaMemcpyHostToDevice, ctx.stream));
     APSU_CUDA_CHECK(cudaMemcpyAsync(d_s.p, secret_ntt_q0, (size_t)N * 8, cudaMemcpyHostToDevice, ctx.stream));
     APSU_CUDA_CHECK(cudaMemcpyAsync(budget.p, big.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
     ctx.ntt(d_ct.p, tmp.p, n, { 0 }, false, src_idx.p, nullptr);
@@ -571,30 +633,113 @@ void Engine::decrypt_results(const uint64_t *secret_ntt_q0, const uint64_t *cts,
     ctx.ntt(plain.p, plain.p, n, { ctx.idx_t }, false);
     k_decode_gather<<<dim3(N / 256, n), 256, 0, ctx.stream>>>(plain.p, values.p, blocks_out ? blocks.p : nullptr, ctx.slot_map.p, ctx.t, ctx.params.felts_per_item, ipb, (int)N);
     APSU_LAUNCH_CHECK();
-    APSU_CUDA_CHECK(cudaMemcpyAsync(values_out, values.p, values.n * 8, cudaMemcpyDeviceToHost, ctx.stream));
-    if (blocks_out) APSU_CUDA_CHECK(cudaMemcpyAsync(blocks_out, blocks.p, blocks.n * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    APSU_CUDA_CHECK(cudaMemcpyAsync(values_out, values.p, (size_t)n * N * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    if (blocks_out) APSU_CUDA_CHECK(cudaMemcpyAsync(blocks_out, blocks.p, (size_t)n * ipb * 2 * 8, cudaMemcpyDeviceToHost, ctx.stream));
     if (budget_out) APSU_CUDA_CHECK(cudaMemcpyAsync(budget_out, budget.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+
+// Query validation (receiver/apsu/query.cpp:68-111): the source powers must be exactly the parameter set's
+std::vector<uint32_t> Engine::check_query_powers(const uint32_t *src_powers, uint32_t nsrc)
+{
+    const apsu_b200_params &p = ctx.params;
+    if (!src_powers) throw std::invalid_argument("query is invalid");
+    std::set<uint32_t> given(src_powers, src_powers + nsrc), want(p.query_powers, p.query_powers + p.query_power_count);
+    if (given.size() != nsrc || given != want) throw std::invalid_argument("query powers do not match the query_powers of the parameters");
+    if (!plan_valid_) build_plan();
+    std::vector<uint32_t> sorted(want.begin(), want.end()), rank(nsrc);
+    for (uint32_t k = 0; k < nsrc; k++) rank[k] = (uint32_t)(std::lower_bound(sorted.begin(), sorted.end(), src_powers[k]) - sorted.begin());
+    return rank; // the plan addresses sources by sorted rank; the caller's block keeps its own order
+}
+
+// is_valid_for of the loaded query ciphertexts / keys (query.cpp:45-66): residues below their moduli, checked on
+// the device; the flag is read back by the next synchronising call (throw_if_query_invalid)
+void Engine::check_range(const u64 *base, uint32_t n_polys, const uint64_t *moduli, uint32_t nmods)
+{
+    if (!n_polys) return;
+    RangeMods rm;
+    std::memset(&rm, 0, sizeof(rm));
+    rm.n = (int)nmods;
+    for (uint32_t j = 0; j < nmods; j++) rm.q[j] = moduli[j];
+    k_check_range<<<dim3(ctx.N / kEwThreads, n_polys), kEwThreads, 0, ctx.stream>>>(base, rm, (int)ctx.N, query_bad_.p);
+    APSU_LAUNCH_CHECK();
+    query_checked_ = true;
+}
+void Engine::throw_if_query_invalid()
+{
+    if (!query_checked_) return;
+    int bad[2] = { 0, 0 }; // [0] residue out of range, [1] rejection list overflow of a seed expansion
+    APSU_CUDA_CHECK(cudaMemcpyAsync(bad, query_bad_.p, sizeof(bad), cudaMemcpyDeviceToHost, ctx.stream));
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    if (bad[0] | bad[1]) APSU_CUDA_CHECK(cudaMemsetAsync(query_bad_.p, 0, sizeof(bad), ctx.stream));
+    query_checked_ = false;
+    if (bad[0]) {
+        query_loaded_ = false;
+        throw std::invalid_argument("query ciphertexts or keys are not valid for the encryption parameters (residue >= modulus)");
+    }
+    if (bad[1]) {
+        query_loaded_ = false;
+        throw std::runtime_error("seed expansion: more rejected samples than the device list holds");
+    }
 }
 
 void Engine::query_begin(const uint32_t *src_powers, uint32_t nsrc, const void *cts, bool on_device)
 {
     const apsu_b200_params &p = ctx.params;
-    if (!src_powers || !cts) throw std::invalid_argument("query is invalid");
-    std::set<uint32_t> given(src_powers, src_powers + nsrc), want(p.query_powers, p.query_powers + p.query_power_count);
-    if (given.size() != nsrc || given != want) throw std::invalid_argument("query powers do not match the query_powers of the parameters");
-    if (!plan_valid_) build_plan();
-    // the uploaded block keeps the caller's order [k][bundle_idx]; the plan addresses sources by sorted rank
-    std::vector<uint32_t> sorted(want.begin(), want.end());
+    if (!cts) throw std::invalid_argument("query is invalid");
+    const std::vector<uint32_t> rank = check_query_powers(src_powers, nsrc);
     const size_t ct_words = (size_t)2 * ctx.first_L * ctx.N, row = (size_t)p.bundle_idx_count * ct_words;
+    u64 *region = arena_.buf.p + (size_t)query_region_ * ctx.N;
     for (uint32_t k = 0; k < nsrc; k++) {
-        uint32_t rank = (uint32_t)(std::lower_bound(sorted.begin(), sorted.end(), src_powers[k]) - sorted.begin());
         const u64 *src = (const u64 *)cts + (size_t)k * row;
-        u64 *dst = arena_.buf.p + (size_t)query_region_ * ctx.N + (size_t)rank * row;
-        APSU_CUDA_CHECK(cudaMemcpyAsync(dst, src, row * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
+        APSU_CUDA_CHECK(cudaMemcpyAsync(region + (size_t)rank[k] * row, src, row * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
     }
+    check_range(region, nsrc * p.bundle_idx_count * 2 * ctx.first_L, p.coeff_modulus, ctx.first_L);
     query_loaded_ = true;
     powers_done_ = eval_done_ = false;
+}
+
+// Row f2: the query as it arrives on the wire (seal::Serializable<Ciphertext>, common/apsu/seal_object.h:161-219,
+// sender/apsu/plaintext_powers.cpp:45): c1 of every ciphertext is a 64-byte PRNG seed, expanded here on the device
+// (sample_poly_uniform) instead of on the host: half the upload.  c0: [nsrc][bundle_idx_count][L][N].
+void Engine::query_begin_seeded(const uint32_t *src_powers, uint32_t nsrc, const uint64_t *c0, const uint8_t *seeds64)
+{
+    const apsu_b200_params &p = ctx.params;
+    if (!c0 || !seeds64) throw std::invalid_argument("query is invalid");
+    const std::vector<uint32_t> rank = check_query_powers(src_powers, nsrc);
+    const uint32_t bic = p.bundle_idx_count, Lf = ctx.first_L;
+    const size_t poly_bytes = (size_t)Lf * ctx.N * 8;
+    u64 *region = arena_.buf.p + (size_t)query_region_ * ctx.N;
+    std::vector<uint32_t> dst;
+    for (uint32_t k = 0; k < nsrc; k++) {
+        u64 *row = region + (size_t)rank[k] * bic * 2 * Lf * ctx.N;
+        APSU_CUDA_CHECK(cudaMemcpy2DAsync(row, 2 * poly_bytes, c0 + (size_t)k * bic * Lf * ctx.N, poly_bytes, poly_bytes, bic, cudaMemcpyHostToDevice, ctx.stream));
+        for (uint32_t b = 0; b < bic; b++) dst.push_back(query_region_ + ((rank[k] * bic + b) * 2 + 1) * Lf);
+    }
+    expand_seeds(Lf, dst, seeds64, arena_.buf.p, p.coeff_modulus);
+    check_range(region, nsrc * bic * 2 * Lf, p.coeff_modulus, Lf);
+    query_loaded_ = true;
+    powers_done_ = eval_done_ = false;
+}
+
+// Serializable<RelinKeys> (KeyGenerator::create_relin_keys): the second polynomial of every key is a seed, sampled in
+// NTT form at the key level.  c0: [K-1][K][N], seeds: [K-1][64].
+void Engine::set_relin_keys_seeded(const uint64_t *c0, const uint8_t *seeds64)
+{
+    if (!ctx.using_keyswitching()) {
+        have_keys_ = false;
+        return;
+    }
+    if (!c0 || !seeds64) throw std::invalid_argument("relinearization keys are required for this parameter set");
+    const uint32_t K = ctx.K, N = ctx.N;
+    relin_keys_.ensure((size_t)(K - 1) * 2 * K * N);
+    const size_t poly_bytes = (size_t)K * N * 8;
+    APSU_CUDA_CHECK(cudaMemcpy2DAsync(relin_keys_.p, 2 * poly_bytes, c0, poly_bytes, poly_bytes, K - 1, cudaMemcpyHostToDevice, ctx.stream));
+    std::vector<uint32_t> dst;
+    for (uint32_t J = 0; J + 1 < K; J++) dst.push_back((J * 2 + 1) * K);
+    expand_seeds(K, dst, seeds64, relin_keys_.p, ctx.params.coeff_modulus);
+    check_range(relin_keys_.p, (K - 1) * 2 * K, ctx.params.coeff_modulus, K);
+    have_keys_ = true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1065,7 +1210,7 @@ void Engine::drop_graphs()
 // given has moved), replayed afterwards
 void Engine::run_steps(std::vector<Step> &prog, size_t lo, size_t hi, ProgGraph &g)
 {
-    if (!use_graphs_) {
+    if (!use_graphs_ || !ctx.stream) { // the legacy default stream (NULL) cannot be captured: run eagerly on it
         for (size_t k = lo; k < hi; k++) prog[k].run();
         return;
     }
@@ -1166,17 +1311,11 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<KtGroup> &grou
             APSU_CUDA_CHECK(record_event(a, ctx.stream));
         }
         const KtGroup *gd = reinterpret_cast<const KtGroup *>(desc_dev_.p + off);
-        // one persistent launch over all groups
+        // one persistent launch over all groups (shared-memory opt-in and occupancy: Engine ctor, per device)
         auto kern = k_db_mac_kt<kKtStages, kKtCtasPerSm>;
         constexpr size_t smem = kt_smem_bytes(kKtStages);
-        APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        APSU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kKtThreads, smem));
-        per_sm = std::max(1, std::min(per_sm, kKtCtasPerSm));
-        int sms = 0;
-        APSU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device));
         const uint32_t items = n * (L * ctx.N / kKtCols);
-        const uint32_t grid = std::min<uint32_t>(items, (uint32_t)(sms * per_sm));
+        const uint32_t grid = std::min<uint32_t>(items, kt_grid_cap_);
         kern<<<grid, kKtThreads, smem, ctx.stream>>>(arena_.buf.p, gd, n, ctx.level[L], (int)ctx.N, split_, fold_stages_, 0u);
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;
@@ -1330,6 +1469,7 @@ void Engine::collect_timings()
 void Engine::fetch_results(uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx)
 {
     if (!eval_done_) throw std::logic_error("fetch_results called before eval_all");
+    throw_if_query_invalid();
     size_t n = result_order_.size();
     if (out && n) APSU_CUDA_CHECK(cudaMemcpyAsync(out, results_.p, n * 2 * ctx.N * 8, cudaMemcpyDeviceToHost, ctx.stream));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
@@ -1393,6 +1533,32 @@ void Engine::run_scratch_program(Build &&build)
     }
     arena_ = std::move(saved_arena);
     idx_ = std::move(saved_idx);
+}
+
+// SEAL's blake2xb generator as a raw stream (refills counter0, counter0+1, ...) and sample_poly_uniform (tests)
+void Engine::op_prng_stream(const uint8_t *seed64, uint64_t counter0, uint64_t *out, size_t n_words)
+{
+    if (!seed64 || !out || !n_words) throw std::invalid_argument("op_prng_stream: bad arguments");
+    PrngSeed seed;
+    std::memcpy(seed.w, seed64, sizeof(seed.w));
+    DBuf<u64> &buf = aux_[0];
+    buf.ensure(n_words);
+    k_prng_stream<<<(unsigned)((n_words + 511) / 512), 64, 0, ctx.stream>>>(buf.p, seed, counter0, n_words);
+    APSU_LAUNCH_CHECK();
+    APSU_CUDA_CHECK(cudaMemcpyAsync(out, buf.p, n_words * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+void Engine::op_expand_seeds(uint32_t L, const uint8_t *seeds64, uint32_t n, uint64_t *out)
+{
+    if (L < 1 || L > ctx.K || L > (uint32_t)kMaxQ) throw std::invalid_argument("op_expand_seeds: level is out of range");
+    if (!seeds64 || !out || !n) throw std::invalid_argument("op_expand_seeds: bad arguments");
+    DBuf<u64> &buf = aux_[0];
+    buf.ensure((size_t)n * L * ctx.N);
+    std::vector<uint32_t> dst(n);
+    for (uint32_t k = 0; k < n; k++) dst[k] = k * L;
+    expand_seeds(L, dst, seeds64, buf.p, ctx.params.coeff_modulus);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(out, buf.p, (size_t)n * L * ctx.N * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    throw_if_query_invalid();
 }
 
 void Engine::op_multiply(uint32_t L, const uint64_t *a, const uint64_t *b, uint64_t *out, uint32_t n_ops)

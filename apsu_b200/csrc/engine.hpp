@@ -84,9 +84,12 @@ public:
     // ---- query ----
     void set_relin_keys(const void *keys, bool on_device);
     void query_begin(const uint32_t *src_powers, uint32_t nsrc, const void *cts, bool on_device);
+    void query_begin_seeded(const uint32_t *src_powers, uint32_t nsrc, const uint64_t *c0, const uint8_t *seeds64);
+    void set_relin_keys_seeded(const uint64_t *c0, const uint8_t *seeds64);
+    void throw_if_query_invalid(); // reads back the is_valid_for flag of the loaded query / keys (synchronises)
     void set_masks(const void *masks, uint32_t npack, bool on_device);
     void encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t *out);
-    void generate_masks(uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out);
+    void generate_masks(const uint8_t *seed64, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out);
     void decrypt_results(const uint64_t *secret_ntt_q0, const uint64_t *cts, uint32_t n, uint64_t *values_out, uint64_t *blocks_out, int32_t *budget_out);
     void compute_powers();
     // PowersDag split over the ranks that share a bundle index (collective C2)
@@ -105,6 +108,8 @@ public:
     void op_multiply(uint32_t L, const uint64_t *a, const uint64_t *b, uint64_t *out, uint32_t n_ops);
     void op_relinearize(uint32_t L, const uint64_t *in, uint64_t *out, uint32_t n_ops);
     void op_mod_switch_next(uint32_t L, const uint64_t *in, uint64_t *out, uint32_t n_polys);
+    void op_prng_stream(const uint8_t *seed64, uint64_t counter0, uint64_t *out, size_t n_words);
+    void op_expand_seeds(uint32_t L, const uint8_t *seeds64, uint32_t n, uint64_t *out);
 
     apsu_b200_timings timings{};
     bool profiling = false;
@@ -181,8 +186,21 @@ private:
     DBuf<uint32_t> build_first_, build_size_, build_rows_; // scratch of add_binbundle_from_bins, kept between calls
     DBuf<u64> build_roots_, build_M_, build_enc_;
     DBuf<int> build_bad_;
+    DBuf<u64> aux_[6];        // scratch of the mask / decrypt entry points, kept between calls
+    DBuf<int> aux_int_;
+    DBuf<uint32_t> aux_idx_;
+    DBuf<unsigned char> aux_bytes_;
+    // seed expansion (blake2.cuh) and query validation
+    DBuf<unsigned char> seed_buf_;
+    DBuf<uint32_t> seed_dst_, rej_; // rej_: [count per polynomial][positions]
+    DBuf<int> query_bad_;           // [0] residue out of range, [1] rejection-list overflow
+    bool query_checked_ = false;
+    std::vector<uint32_t> check_query_powers(const uint32_t *src_powers, uint32_t nsrc);
+    void check_range(const u64 *base, uint32_t n_polys, const uint64_t *moduli, uint32_t nmods);
+    void expand_seeds(uint32_t L, const std::vector<uint32_t> &dst, const uint8_t *seeds64, u64 *base, const uint64_t *moduli);
     int split_ = 30;          // bit position the DB-stream operands are split at
     uint32_t fold_stages_ = 1; // ring stages between lane folds in the DB-stream kernel
+    uint32_t kt_grid_cap_ = 1; // resident CTAs of the DB-stream kernel on this device (persistent grid)
     size_t add_desc(const void *data, size_t bytes);
     void emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<KtGroup> &groups, uint64_t bytes);
     void emit_mul_terms(ProgramBuilder &pb, uint32_t L, std::vector<MulTermsJob> &jobs, uint32_t nterms);

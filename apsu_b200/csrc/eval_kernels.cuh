@@ -380,30 +380,27 @@ __device__ __forceinline__ void vec_to_std_block(F val, u32 felts_per_item, u64 
     }
 }
 
-// Mask generation of RunQuery (receiver/apsu/receiver_ddh.cpp:241-283): for every (cache_idx, bundle_idx) pair
-// p = pack index, one value r = prng32 % plain_modulus per slot (generate() yields 32-bit words, :258), scattered to
-// its BatchEncoder position (encode = this scatter + the inverse NTT mod t done by the caller), and the items'
-// 128-bit blocks of the PEQT hand-off (vec_to_std_block, :70-92); padded pairs (:247-252) get all-one blocks and no
-// mask.  The reference seeds SEAL's blake2xb PRNG from random_bytes, so its masks are not reproducible; here
-// word (p, i) of the stream is the low half of splitmix64_at(seed, p*N + i).
+// Mask generation of RunQuery (receiver/apsu/receiver_ddh.cpp:241-283), second half: the values r = prng32 % t were
+// drawn by k_prng_mask_values (blake2.cuh: SEAL's blake2xb generator, as the reference uses); here every value is
+// scattered to its BatchEncoder position (encode = this scatter + the inverse NTT mod t done by the caller) and the
+// items' 128-bit blocks of the PEQT hand-off are packed (vec_to_std_block, :70-92); padded pairs (:247-252) get
+// all-one blocks and no mask.
 // grid (N/256, npack).  values/scattered: [npack][N]; blocks: [npack][items_per_bundle][2] = (low, high) words.
 __global__ void __launch_bounds__(256)
-k_gen_masks(u64 *__restrict__ values, u64 *__restrict__ scattered, u64 *__restrict__ blocks, const unsigned char *__restrict__ padded, const u32 *__restrict__ map,
-            u64 seed, u64 t, u32 felts_per_item, u32 items_per_bundle, int N)
+k_masks_scatter_blocks(const u64 *__restrict__ values, u64 *__restrict__ scattered, u64 *__restrict__ blocks, const unsigned char *__restrict__ padded,
+                       const u32 *__restrict__ map, u64 t, u32 felts_per_item, u32 items_per_bundle, int N)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t p = blockIdx.y;
     const bool pad = padded[p] != 0;
-    const u64 r = pad ? 0 : (u64)(u32)splitmix64_at(seed, p * (size_t)N + i) % t;
-    values[p * N + i] = r;
-    scattered[p * N + map[i]] = r;
+    scattered[p * N + map[i]] = values[p * N + i];
     if (i < items_per_bundle) {
         u64 lower = 0, higher = 0;
         if (pad) {
             lower = higher = ~0ull; // Block::all_one_block
         } else {
             const size_t base = p * (size_t)N + (size_t)i * felts_per_item;
-            vec_to_std_block([&](u32 j) { return (u64)(u32)splitmix64_at(seed, base + j) % t; }, felts_per_item, t, lower, higher);
+            vec_to_std_block([&](u32 j) { return values[base + j]; }, felts_per_item, t, lower, higher);
         }
         blocks[(p * items_per_bundle + i) * 2] = lower;
         blocks[(p * items_per_bundle + i) * 2 + 1] = higher;

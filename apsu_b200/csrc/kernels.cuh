@@ -230,4 +230,17 @@ k_sum_polys(u64 *A, const u32 *__restrict__ terms, const u32 *__restrict__ first
     A[((size_t)dst[rp] + j) * N + n] = s;
 }
 
+// ---- Query validation: seal::is_valid_for -> is_data_valid_for (receiver/apsu/query.cpp:45-66) ----
+// every residue of polynomial p must be below modulus p % nmods.  grid (N/256, n_polys); *bad is set on a violation.
+struct RangeMods {
+    u64 q[8];
+    int n;
+};
+__global__ void __launch_bounds__(kEwThreads) k_check_range(const u64 *__restrict__ base, RangeMods mods, int N, int *__restrict__ bad)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 p = blockIdx.y;
+    if (base[(size_t)p * N + n] >= mods.q[p % mods.n]) atomicExch(bad, 1);
+}
+
 } // namespace apsu_b200

@@ -144,7 +144,7 @@ constexpr int ntt_min_blocks(int logn, int div)
     return by_smem < by_threads ? by_smem : by_threads;
 }
 template <int LOGN, bool FWD, int DIV>
-__global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) ntt_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, NttArgs a, NttSrc src)
+__global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) ntt_kernel(const u64 *in, u64 *out, NttArgs a, NttSrc src)
 {
     constexpr int N = 1 << LOGN;
     constexpr int RF = (LOGN % 3 == 0) ? 3 : (LOGN % 3 == 1 ? 4 : 2); // 13 = 4+3+3+3: one shared-memory round trip less than 1+3+3+3+3

@@ -209,9 +209,11 @@ public:
         detail::check(apsu_b200_db_add_binbundle_synthetic(ctx_, bundle_idx, ncoeffs, seed, &ci));
         return ci;
     }
-    // RunQuery's mask loop on the device (receiver_ddh.cpp:241-283): returns random_matrix as (low, high) words per
-    // item, [alpha_max*bundle_idx_count][items_per_bundle][2]; the masks stay device-resident for the next query
-    std::vector<std::uint64_t> generate_masks(std::uint64_t seed)
+    // RunQuery's mask loop on the device (receiver_ddh.cpp:218-283): SEAL's blake2xb generator keyed with 64 bytes of
+    // OS randomness (seed == nullptr, the reference's random_bytes) or with a caller-chosen 64-byte seed (reproducible
+    // runs); returns random_matrix as (low, high) words per item, [alpha_max*bundle_idx_count][items_per_bundle][2];
+    // the masks stay device-resident for the next query
+    std::vector<std::uint64_t> generate_masks(const std::uint8_t *seed = nullptr)
     {
         std::unique_lock<std::shared_mutex> lock(db_lock_);
         const std::uint32_t bic = params_.bundle_idx_count();

@@ -198,14 +198,29 @@ class Receiver:
         if query.relin_keys is not None:
             capi.check(self._L.apsu_b200_set_relin_keys(h, capi.ptr(query.relin_keys)))
 
+    def load_query_seeded(self, src_powers, c0: np.ndarray, seeds: np.ndarray, relin_c0: np.ndarray | None = None, relin_seeds: np.ndarray | None = None):
+        """Row f2: the query as on the wire (seal::Serializable): c0 [nsrc][bundle_idx_count][L][N] + one 64-byte seed per
+        ciphertext [nsrc][bundle_idx_count][64]; relinearisation keys c0 [K-1][K][N] + seeds [K-1][64]; the second
+        polynomials are sampled on the device (sample_poly_uniform)."""
+        sp = np.ascontiguousarray(list(src_powers), dtype=np.uint32)
+        c0 = np.ascontiguousarray(c0, dtype=np.uint64)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8)
+        capi.check(self._L.apsu_b200_query_begin_seeded(self.db._h, sp, len(sp), capi.ptr(c0), capi.ptr(seeds)))
+        if relin_c0 is not None:
+            rc0 = np.ascontiguousarray(relin_c0, dtype=np.uint64)
+            rs = np.ascontiguousarray(relin_seeds, dtype=np.uint8)
+            capi.check(self._L.apsu_b200_set_relin_keys_seeded(self.db._h, capi.ptr(rc0), capi.ptr(rs)))
+
     def set_masks(self, masks: np.ndarray):
         masks = np.ascontiguousarray(masks, dtype=np.uint64)
         capi.check(self._L.apsu_b200_set_masks(self.db._h, masks, masks.shape[0]))
 
-    def generate_masks(self, seed: int, cache_counts=None, want_values: bool = False):
-        """receiver_ddh.cpp:241-283 on the device: draws the masks of every (cache_idx, bundle_idx) pair, keeps their
-        encodings resident for the next evaluation and returns random_matrix [npack][items_per_bundle][2] (low, high
-        words of the PEQT blocks; all ones for padded pairs).  cache_counts[bundle_idx] defaults to the DB's."""
+    def generate_masks(self, seed: bytes | None = None, cache_counts=None, want_values: bool = False):
+        """receiver_ddh.cpp:218-283 on the device: draws the masks of every (cache_idx, bundle_idx) pair from SEAL's
+        blake2xb generator keyed with the 64-byte `seed` (None: 64 bytes of OS randomness, as the reference does),
+        keeps their encodings resident for the next evaluation and returns random_matrix
+        [npack][items_per_bundle][2] (low, high words of the PEQT blocks; all ones for padded pairs).
+        cache_counts[bundle_idx] defaults to the DB's."""
         bic = self.db.params.bundle_idx_count()
         if cache_counts is None:
             cache_counts = [self.db.get_bin_bundle_count(b) for b in range(bic)]
@@ -214,7 +229,12 @@ class Receiver:
         npack = alpha * bic
         blocks = np.zeros((npack, self.db.params.items_per_bundle(), 2), dtype=np.uint64)
         values = np.zeros((npack, self.db.params.poly_modulus_degree()), dtype=np.uint64) if want_values else None
-        capi.check(self._L.apsu_b200_generate_masks(self.db._h, seed, capi.ptr(padded), npack, capi.ptr(blocks), capi.ptr(values)))
+        sd = None
+        if seed is not None:
+            if len(seed) != 64:
+                raise ValueError("the mask seed is 64 bytes (seal::prng_seed_type)")
+            sd = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+        capi.check(self._L.apsu_b200_generate_masks(self.db._h, capi.ptr(sd), capi.ptr(padded), npack, capi.ptr(blocks), capi.ptr(values)))
         return (blocks, values) if want_values else blocks
 
     def decrypt_results(self, secret_key_ntt_q0: np.ndarray, cts: np.ndarray, want_blocks: bool = True):
@@ -318,6 +338,18 @@ class Receiver:
         out = np.ascontiguousarray(polys, dtype=np.uint64).copy()
         pat = np.ascontiguousarray(list(pattern), dtype=np.uint32)
         capi.check(self._L.apsu_b200_op_ntt(self.db._h, out.reshape(-1), out.size // N, pat, len(pat), int(inverse)))
+        return out
+
+    def op_prng_stream(self, seed: bytes, first_refill: int, n_words: int) -> np.ndarray:
+        sd = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+        out = np.zeros(n_words, dtype=np.uint64)
+        capi.check(self._L.apsu_b200_op_prng_stream(self.db._h, capi.ptr(sd), first_refill, capi.ptr(out), n_words))
+        return out
+
+    def op_expand_seeds(self, num_primes: int, seeds: np.ndarray) -> np.ndarray:
+        sd = np.ascontiguousarray(seeds, dtype=np.uint8).reshape(-1, 64)
+        out = np.zeros((sd.shape[0], num_primes, self.db.params.poly_modulus_degree()), dtype=np.uint64)
+        capi.check(self._L.apsu_b200_op_expand_seeds(self.db._h, num_primes, capi.ptr(sd), sd.shape[0], capi.ptr(out)))
         return out
 
     def op_multiply(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:

@@ -95,7 +95,8 @@ int apsu_b200_powers_dag(
  * BEHZ constants on `device` (a CUDA ordinal). */
 int apsu_b200_ctx_create(const apsu_b200_params *params, int device, apsu_b200_ctx **out);
 void apsu_b200_ctx_destroy(apsu_b200_ctx *ctx);
-/* Run all work of this context on an existing cudaStream_t (e.g. torch's current stream). */
+/* Run all work of this context on an existing cudaStream_t (e.g. torch's current stream).  NULL (the legacy default
+ * stream) is accepted but cannot be captured into CUDA graphs: the context then launches its kernels one by one. */
 int apsu_b200_ctx_set_stream(apsu_b200_ctx *ctx, void *cuda_stream);
 int apsu_b200_ctx_synchronize(apsu_b200_ctx *ctx);
 /* number of RNS primes of: 0 = first data level, 1 = DB plaintexts / low powers, 2 = high powers,
@@ -174,16 +175,28 @@ int apsu_b200_powers_stage_count(apsu_b200_ctx *ctx, uint32_t *count);
 int apsu_b200_compute_powers_stage(apsu_b200_ctx *ctx, uint32_t stage);
 int apsu_b200_powers_exchange_regions(
     apsu_b200_ctx *ctx, uint32_t level, void **device_ptrs, uint64_t *chunk_bytes, uint32_t capacity, uint32_t *count);
-/* "next" row f3 — the mask generation of RunQuery on the device (receiver_ddh.cpp:241-283): for every pack index
- * p = bundle_idx + cache_idx*bundle_idx_count with padded[p] == 0, r = prng32 % plain_modulus per slot (:258),
- * BatchEncoder::encode of it (:275; kept device-resident as the masks of the next evaluation, like
- * apsu_b200_set_masks) and the 128-bit blocks of the PEQT hand-off, random_matrix[p][item] = vec_to_std_block of the
- * item's felts (:70-92, :263-270) as (low, high) words; padded pairs (:247-252) get Block::all_one_block.  The
- * reference draws from SEAL's blake2xb PRNG seeded by random_bytes (:223) and is not reproducible; here word (p, i) is
- * the low half of splitmix64 at counter p*N + i of `seed`, so that fixed seeds give identical ciphertexts.
- * random_matrix: [npack][items_per_bundle][2]; slot_values (optional, tests): [npack][N]. */
+/* Row f3 — the mask generation of RunQuery on the device (receiver/apsu/receiver_ddh.cpp:218-283): SEAL's default
+ * generator (Blake2xbPRNG) keyed with the 64 bytes of `seed`; seed == NULL draws them from the OS (getrandom) exactly
+ * as the reference does with random_bytes (:221-225) — that is the production setting; a caller-supplied seed makes
+ * masks (and with them result ciphertexts) reproducible for tests.  The pairs are visited in (cache_idx, bundle_idx)
+ * order, i.e. ascending pack index p = bundle_idx + cache_idx*bundle_idx_count, padded pairs (padded[p] != 0) draw
+ * nothing and get Block::all_one_block (:247-252); every other pair draws N 32-bit words, r = word % plain_modulus per
+ * slot (:256-262), BatchEncoder::encode of it (:275; kept device-resident as the masks of the next evaluation, like
+ * apsu_b200_set_masks) and random_matrix[p][item] = vec_to_std_block of the item's felts (:70-92, :263-270) as
+ * (low, high) words.  random_matrix: [npack][items_per_bundle][2]; slot_values (optional, tests): [npack][N].
+ * [SEAL-RECALL] Blake2xbPRNG: 4096-byte refills blake2xb(key = seed, input = 64-bit refill counter). */
 int apsu_b200_generate_masks(
-    apsu_b200_ctx *ctx, uint64_t seed, const uint8_t *padded, uint32_t npack, uint64_t *random_matrix, uint64_t *slot_values);
+    apsu_b200_ctx *ctx, const uint8_t *seed /*[64] or NULL*/, const uint8_t *padded, uint32_t npack, uint64_t *random_matrix, uint64_t *slot_values);
+/* Row f2 — the query as it is on the wire (seal::Serializable<Ciphertext>: sender/apsu/plaintext_powers.cpp:45,
+ * common/apsu/seal_object.h:161-219, common/apsu/network/receiver_operation.cpp:187-345): the second polynomial of a
+ * symmetric-key ciphertext is replaced by the 64-byte seed of the generator that sampled it, and
+ * Ciphertext::unsafe_load re-samples it (expand_seed -> sample_poly_uniform).  The expansion runs on the device, so
+ * only c0 and the seeds are uploaded (half the bytes).  c0: uint64_t[nsrc][bundle_idx_count][L_first][N];
+ * seeds: uint8_t[nsrc][bundle_idx_count][64].  Relinearisation keys likewise (KeyGenerator::create_relin_keys returns
+ * Serializable<RelinKeys>): c0 uint64_t[K-1][K][N], seeds uint8_t[K-1][64].  Host-side parsing of the SEAL byte
+ * layout: apsu_b200/host/seal_wire.hpp. */
+int apsu_b200_query_begin_seeded(apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *c0, const uint8_t *seeds);
+int apsu_b200_set_relin_keys_seeded(apsu_b200_ctx *ctx, const uint64_t *c0, const uint8_t *seeds);
 /* Receiver::ProcessBinBundleCache for every BinBundle — receiver_ddh.cpp:340-369, 485-535 →
  * BatchedPlaintextPolyn::eval / eval_patstock (bin_bundle.cpp:106-174, 192-360).  Results stay on the
  * device until fetched.  Order of results: bundle_idx major, cache_idx minor. */
@@ -197,7 +210,11 @@ int apsu_b200_fetch_results(apsu_b200_ctx *ctx, uint64_t *out, uint32_t *bundle_
 int apsu_b200_run_query(
     apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys,
     const uint64_t *masks, uint32_t npack, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
-/* Device-resident variant used for sharded runs: cts/keys/masks already on this context's GPU. */
+/* Device-resident variant used for sharded runs: cts/keys/masks already on this context's GPU.  These calls are
+ * ASYNCHRONOUS: they queue device-to-device copies on the context stream and return; the source buffers must stay
+ * valid (and unmodified) until apsu_b200_ctx_synchronize or a fetch of the results.  The residue-range check of the
+ * query (seal::is_valid_for, receiver/apsu/query.cpp:45-66) runs on the device with every load and is reported by the
+ * next synchronising call (the host-buffer variants report it themselves). */
 int apsu_b200_query_begin_device(apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const void *cts_device);
 int apsu_b200_set_relin_keys_device(apsu_b200_ctx *ctx, const void *keys_device);
 int apsu_b200_set_masks_device(apsu_b200_ctx *ctx, const void *masks_device, uint32_t npack);
@@ -220,6 +237,11 @@ int apsu_b200_op_multiply(apsu_b200_ctx *ctx, uint32_t num_primes, const uint64_
 int apsu_b200_op_relinearize(apsu_b200_ctx *ctx, uint32_t num_primes, const uint64_t *in, uint64_t *out, uint32_t n_ops);
 /* Evaluator::mod_switch_to_next_inplace on n_polys polynomials uint64_t[n_polys][L][N] -> [n_polys][L-1][N]. */
 int apsu_b200_op_mod_switch_next(apsu_b200_ctx *ctx, uint32_t num_primes, const uint64_t *in, uint64_t *out, uint32_t n_polys);
+
+/* SEAL's Blake2xbPRNG as a raw stream: n_words 64-bit words starting at refill `first_refill` (4096 bytes each), and
+ * sample_poly_uniform for n seeded polynomials over coeff_modulus[0..num_primes-1]: out uint64_t[n][num_primes][N]. */
+int apsu_b200_op_prng_stream(apsu_b200_ctx *ctx, const uint8_t *seed /*[64]*/, uint64_t first_refill, uint64_t *out, uint64_t n_words);
+int apsu_b200_op_expand_seeds(apsu_b200_ctx *ctx, uint32_t num_primes, const uint8_t *seeds /*[n][64]*/, uint32_t n, uint64_t *out);
 
 /* ---- measurement ----------------------------------------------------------------------------- */
 typedef struct apsu_b200_timings {

@@ -23,7 +23,7 @@ u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
 
 def build(force: bool = False) -> pathlib.Path:
     so = _HERE / "liborc.so"
-    srcs = [_HERE / n for n in ("oracle_capi.cpp", "apsu_restate.hpp", "seal_restate.hpp")]
+    srcs = [_HERE / n for n in ("oracle_capi.cpp", "apsu_restate.hpp", "seal_restate.hpp", "prng_restate.hpp")]
     if force or not so.exists() or any(s.exists() and s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.check_call(["make", "-C", str(_HERE), "-s"])
     return so
@@ -101,6 +101,12 @@ def lib():
         L.orc_session_power.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int), C.c_void_p]
         L.orc_session_eval_subset.restype = C.c_double
         L.orc_session_eval_subset.argtypes = [C.c_void_p, C.c_void_p, u32p, u32p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
+        u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+        for f in ("orc_blake2b", "orc_blake2xb"):
+            getattr(L, f).argtypes = [u8p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.orc_prng_bytes.argtypes = [u8p, C.c_size_t, u8p]
+        L.orc_sample_poly_uniform.argtypes = [u8p, u64p, C.c_size_t, C.c_size_t, u64p]
+        L.orc_mask_values.argtypes = [u8p, u8p, C.c_size_t, C.c_size_t, C.c_uint64, u64p]
         _LIB = L
     return _LIB
 
@@ -141,6 +147,53 @@ def minimal_primitive_root(degree: int, modulus: int) -> int:
 def ntt_mod(N: int, modulus: int, data: np.ndarray, inverse: bool = False) -> np.ndarray:
     out = np.ascontiguousarray(data, dtype=np.uint64).copy()
     _check(lib().orc_ntt_mod(N, modulus, out, int(inverse)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# SEAL's default random generator (prng_restate.hpp)
+# ---------------------------------------------------------------------------------------------
+def _bytes_arg(b):
+    a = np.frombuffer(bytes(b), dtype=np.uint8) if len(b) else np.zeros(0, dtype=np.uint8)
+    return a, (a.ctypes.data_as(C.c_void_p) if len(b) else None)
+
+
+def blake2b(data: bytes, outlen: int = 64, key: bytes = b"") -> bytes:
+    out = np.zeros(outlen, dtype=np.uint8)
+    d, dp = _bytes_arg(data)
+    k, kp = _bytes_arg(key)
+    _check(lib().orc_blake2b(out, outlen, dp, len(data), kp, len(key)))
+    return out.tobytes()
+
+
+def blake2xb(data: bytes, outlen: int, key: bytes = b"") -> bytes:
+    out = np.zeros(outlen, dtype=np.uint8)
+    d, dp = _bytes_arg(data)
+    k, kp = _bytes_arg(key)
+    _check(lib().orc_blake2xb(out, outlen, dp, len(data), kp, len(key)))
+    return out.tobytes()
+
+
+def prng_bytes(seed: bytes, nbytes: int) -> bytes:
+    """first nbytes of the Blake2xbPRNG stream keyed with the 64-byte seed"""
+    out = np.zeros(nbytes, dtype=np.uint8)
+    _check(lib().orc_prng_bytes(np.frombuffer(bytes(seed), dtype=np.uint8).copy(), nbytes, out))
+    return out.tobytes()
+
+
+def sample_poly_uniform(seed: bytes, moduli, N: int) -> np.ndarray:
+    """seal::util::sample_poly_uniform with a fresh generator: [L][N]"""
+    m = np.array([int(x) for x in moduli], dtype=np.uint64)
+    out = np.zeros((len(m), N), dtype=np.uint64)
+    _check(lib().orc_sample_poly_uniform(np.frombuffer(bytes(seed), dtype=np.uint8).copy(), m, len(m), N, out))
+    return out
+
+
+def mask_values(seed: bytes, padded, N: int, t: int) -> np.ndarray:
+    """receiver_ddh.cpp:241-262: slot values of every pack index (zero rows for padded pairs)"""
+    pad = np.ascontiguousarray(padded, dtype=np.uint8)
+    out = np.zeros((len(pad), N), dtype=np.uint64)
+    _check(lib().orc_mask_values(np.frombuffer(bytes(seed), dtype=np.uint8).copy(), pad, len(pad), N, t, out))
     return out
 
 

@@ -2,6 +2,7 @@
 // ctypes (oracle/oracle.py).  Used by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
 // legs only; the product library (libapsu_b200.so) never links or loads this.
 #include "apsu_restate.hpp"
+#include "prng_restate.hpp"
 #include <chrono>
 #include <memory>
 #include <string>
@@ -447,6 +448,48 @@ double orc_session_eval_subset(
         ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     });
     return ms;
+}
+
+// ---- SEAL's default random generator and seed expansion (prng_restate.hpp) ----
+int orc_blake2b(uint8_t *out, size_t outlen, const uint8_t *in, size_t inlen, const uint8_t *key, size_t keylen)
+{
+    return guard([&] { orc_prng::blake2b(out, outlen, in, inlen, key, keylen); });
+}
+int orc_blake2xb(uint8_t *out, size_t outlen, const uint8_t *in, size_t inlen, const uint8_t *key, size_t keylen)
+{
+    return guard([&] { orc_prng::blake2xb(out, outlen, in, inlen, key, keylen); });
+}
+// first nbytes of the Blake2xbPRNG stream of `seed` (64 bytes)
+int orc_prng_bytes(const uint8_t *seed, size_t nbytes, uint8_t *out)
+{
+    return guard([&] {
+        std::array<uint64_t, 8> sd;
+        for (int i = 0; i < 8; i++) sd[i] = orc_prng::load64(seed + 8 * i);
+        orc_prng::Blake2xbPRNG prng(sd);
+        prng.generate(nbytes, out);
+    });
+}
+// sample_poly_uniform with a fresh generator seeded by `seed`: out [L][N]
+int orc_sample_poly_uniform(const uint8_t *seed, const u64 *moduli, size_t L, size_t N, u64 *out)
+{
+    return guard([&] {
+        std::array<uint64_t, 8> sd;
+        for (int i = 0; i < 8; i++) sd[i] = orc_prng::load64(seed + 8 * i);
+        orc_prng::Blake2xbPRNG prng(sd);
+        orc_prng::sample_poly_uniform(prng, reinterpret_cast<const uint64_t *>(moduli), L, N, reinterpret_cast<uint64_t *>(out));
+    });
+}
+// mask values of RunQuery (receiver_ddh.cpp:241-262): for every non-padded pack index in ascending order, N draws of
+// prng->generate() % t; padded ones are left zero.  values [npack][N]
+int orc_mask_values(const uint8_t *seed, const uint8_t *padded, size_t npack, size_t N, u64 t, u64 *values)
+{
+    return guard([&] {
+        std::array<uint64_t, 8> sd;
+        for (int i = 0; i < 8; i++) sd[i] = orc_prng::load64(seed + 8 * i);
+        orc_prng::Blake2xbPRNG prng(sd);
+        for (size_t p = 0; p < npack; p++)
+            for (size_t i = 0; i < N; i++) values[p * N + i] = padded[p] ? 0 : (u64)prng.generate() % t;
+    });
 }
 
 } // extern "C"

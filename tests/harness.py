@@ -141,27 +141,23 @@ def ref_vec_to_std_block(vals, felts_per_item: int, plain_modulus: int):
     return lower & ((1 << 64) - 1), higher & ((1 << 64) - 1)
 
 
-def ref_generate_masks(p, seed: int, cache_counts):
+def ref_generate_masks(p, seed: bytes, cache_counts):
     """-> (values [npack][N], blocks [npack][items_per_bundle][2], padded [npack]) in pack order
-    p = bundle_idx + cache_idx * bundle_idx_count (receiver_ddh.cpp:243-246, 346)."""
+    p = bundle_idx + cache_idx * bundle_idx_count (receiver_ddh.cpp:243-246, 346); the values are the oracle's
+    restatement of SEAL's blake2xb generator keyed with the 64-byte seed (oracle/prng_restate.hpp), one 32-bit draw
+    per slot of every non-padded pair in (cache_idx, bundle_idx) order (receiver_ddh.cpp:241-262)."""
     bic, N = p.bundle_idx_count, p.N
     alpha = max(max(cache_counts), 1)
     npack = alpha * bic
-    with np.errstate(over="ignore"):
-        words = splitmix64_at(seed, np.arange(npack * N, dtype=np.uint64)) & np.uint64(0xFFFFFFFF)
-    values = (words % np.uint64(p.t)).reshape(npack, N)
+    padded = np.array([c >= cache_counts[b] for c in range(alpha) for b in range(bic)], dtype=bool)
+    values = O.mask_values(seed, padded.astype(np.uint8), N, p.t)
     ipb = p.N // p.felts_per_item
     blocks = np.zeros((npack, ipb, 2), dtype=np.uint64)
-    padded = np.zeros(npack, dtype=bool)
-    for c in range(alpha):
-        for b in range(bic):
-            k = b + c * bic
-            if c >= cache_counts[b]:
-                padded[k] = True
-                values[k] = 0
-                blocks[k] = np.uint64((1 << 64) - 1)
-                continue
-            for i in range(ipb):
-                lo, hi = ref_vec_to_std_block([int(v) for v in values[k, i * p.felts_per_item:(i + 1) * p.felts_per_item]], p.felts_per_item, p.t)
-                blocks[k, i] = (lo, hi)
+    for k in range(npack):
+        if padded[k]:
+            blocks[k] = np.uint64((1 << 64) - 1)
+            continue
+        for i in range(ipb):
+            lo, hi = ref_vec_to_std_block([int(v) for v in values[k, i * p.felts_per_item:(i + 1) * p.felts_per_item]], p.felts_per_item, p.t)
+            blocks[k, i] = (lo, hi)
     return values, blocks, padded

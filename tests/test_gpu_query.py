@@ -217,8 +217,9 @@ def test_mask_generation_on_device(name, degrees):
         _upload(sc, db)
         rx = apsu_b200.Receiver(db)
         counts = [len(d) for d in degrees]
-        blocks, values = rx.generate_masks(0x4D4D, want_values=True)
-        rvalues, rblocks, padded = ref_generate_masks(sc.p, 0x4D4D, counts)
+        seed = bytes((7 * i + 3) & 0xFF for i in range(64))
+        blocks, values = rx.generate_masks(seed, want_values=True)
+        rvalues, rblocks, padded = ref_generate_masks(sc.p, seed, counts)
         assert np.array_equal(values, rvalues)
         assert np.array_equal(blocks, rblocks)
         # evaluate with the resident masks, then with the same masks passed in

@@ -174,3 +174,63 @@ def test_query_semantics_and_golden_results(name):
         assert ok and budget > 0
         r = sc.mask_values[sc.pack_idx(b, c)]
         assert all(got[s] == r[s] for s in sc.planted[(b, c)])
+
+
+# ---- SEAL's default generator restated (oracle/prng_restate.hpp): rows f2/f3 --------------------------------------
+def test_blake2b_rfc7693_vector_and_hashlib():
+    """BLAKE2b core of the oracle: the RFC 7693 appendix A vector, and hashlib for keyed / truncated digests."""
+    import hashlib
+    rfc = ("ba80a53f981c4d0d6a2797b69f12f6e94c212f14685ac4b74b12bb6fdbffa2d1"
+           "7d87c5392aab792dc252d5de4533cc9518d38aa8dbf1925ab92386edd4009923")
+    assert O.blake2b(b"abc").hex() == rfc
+    rng = np.random.default_rng(7693)
+    for n in (0, 1, 64, 127, 128, 129, 255, 256, 1000):
+        d = rng.bytes(n)
+        for kl in (0, 16, 64):
+            k = rng.bytes(kl)
+            for ol in (20, 32, 64):
+                assert O.blake2b(d, ol, k) == hashlib.blake2b(d, digest_size=ol, key=k).digest(), (n, kl, ol)
+
+
+def test_blake2xb_against_independent_model():
+    """BLAKE2Xb: hashlib cannot express the expansion nodes (fanout = depth = 0), so the pin is a pure-Python model
+    of the compression function with an explicit parameter block (tests/blake2_model.py), itself checked against
+    hashlib on every parameter block hashlib accepts (tree parameters, node_offset carrying xof_length)."""
+    import hashlib
+    import blake2_model as M
+    rng = np.random.default_rng(2)
+    for n in (0, 3, 128, 129, 300):
+        d = rng.bytes(n)
+        for k in (b"", rng.bytes(64)):
+            assert M.blake2b_param(d, M.param_block(64, len(k)), k) == hashlib.blake2b(d, key=k).digest()
+            assert M.blake2b_param(d, M.param_block(48, len(k), 2, 3, 64, 7, 4096, 1, 64), k) == hashlib.blake2b(
+                d, digest_size=48, key=k, fanout=2, depth=3, leaf_size=64, node_offset=7 | (4096 << 32), node_depth=1, inner_size=64).digest()
+            for ol in (1, 64, 65, 200, 4096):
+                assert O.blake2xb(d, ol, k) == M.blake2xb(d, ol, k), (n, ol)
+
+
+def test_prng_stream_and_sample_poly_uniform():
+    """Blake2xbPRNG = concatenated 4096-byte refills blake2xb(key = seed, input = refill counter); sample_poly_uniform =
+    bulk fill + sequential redraws of rejected words, against a Python model of the same rule on the model's stream.
+    The second modulus sits far below a power of two, so that rejections actually happen."""
+    import blake2_model as M
+    seed = bytes(range(64))
+    s = O.prng_bytes(seed, 9000)
+    assert s[:4096] == M.blake2xb((0).to_bytes(8, "little"), 4096, seed)
+    assert s[4096:8192] == M.blake2xb((1).to_bytes(8, "little"), 4096, seed)
+    assert s[8192:] == M.blake2xb((2).to_bytes(8, "little"), 4096, seed)[:808]
+    N, moduli = 256, [0xFFFFFFFFFFC0001, 0xB000000000000001 >> 4]
+    got = O.sample_poly_uniform(seed, moduli, N)
+    stream = b"".join(M.blake2xb(c.to_bytes(8, "little"), 4096, seed) for c in range(4))
+    words = np.frombuffer(stream, dtype="<u8")
+    nxt, rejected = len(moduli) * N, 0
+    for j, q in enumerate(moduli):
+        mm = (2 ** 64 - 1) - ((2 ** 64 - 1) % q) - 1
+        for i in range(N):
+            r = int(words[j * N + i])
+            while r >= mm:
+                r = int(words[nxt])
+                nxt += 1
+                rejected += 1
+            assert int(got[j, i]) == r % q, (j, i)
+    assert rejected > 0
