@@ -74,7 +74,17 @@ SIGNATURES = {
     "apsu_b200_powers_dag": (C.c_int, [C.POINTER(CParams), C.c_uint32, u32p, u32p, u32p, u32p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "apsu_b200_ctx_create": (C.c_int, [C.POINTER(CParams), C.c_int, C.POINTER(vp)]),
     "apsu_b200_ctx_destroy": (None, [vp]),
+    "apsu_b200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+    "apsu_b200_host_free": (None, [vp]),
+    "apsu_b200_mgpu_unique_id": (C.c_int, [vp]),
+    "apsu_b200_mgpu_create": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "apsu_b200_mgpu_destroy": (None, [vp]),
+    "apsu_b200_mgpu_commit": (C.c_int, [vp, vp, C.c_int]),
+    "apsu_b200_mgpu_info": (C.c_int, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]),
+    "apsu_b200_mgpu_run_query": (C.c_int, [vp, u32p, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp]),
+    "apsu_b200_mgpu_compute_powers": (C.c_int, [vp]),
     "apsu_b200_ctx_set_stream": (C.c_int, [vp, vp]),
+    "apsu_b200_ctx_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
     "apsu_b200_ctx_synchronize": (C.c_int, [vp]),
     "apsu_b200_ctx_level": (C.c_int, [vp, C.c_int, C.POINTER(C.c_uint32)]),
     "apsu_b200_db_add_binbundle": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), C.c_uint32, C.POINTER(C.c_uint32)]),

@@ -55,6 +55,12 @@ T *need(T *p, const char *what)
 }
 } // namespace
 
+namespace apsu_b200 {
+// for the other translation units of the C ABI (mgpu.cu)
+Engine &engine_of(apsu_b200_ctx *ctx) { return E(ctx); }
+int guarded_call(const std::function<void()> &f) { return guarded(f); }
+} // namespace apsu_b200
+
 extern "C" {
 
 const char *apsu_b200_last_error(void) { return g_last_error.c_str(); }
@@ -124,6 +130,16 @@ void apsu_b200_ctx_destroy(apsu_b200_ctx *ctx)
     }
     delete ctx;
 }
+/* pinned host memory for query / result buffers (cudaHostAlloc): host<->device copies from pageable memory are staged
+ * and run at a fraction of the PCIe rate */
+int apsu_b200_host_alloc(size_t bytes, void **out)
+{
+    return guarded([&] { APSU_CUDA_CHECK(cudaHostAlloc(need(out, "out"), bytes ? bytes : 1, cudaHostAllocDefault)); });
+}
+void apsu_b200_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
 int apsu_b200_ctx_set_stream(apsu_b200_ctx *ctx, void *cuda_stream)
 {
     return guarded([&] {
@@ -133,6 +149,10 @@ int apsu_b200_ctx_set_stream(apsu_b200_ctx *ctx, void *cuda_stream)
         e.ctx.stream = (cudaStream_t)cuda_stream;
         e.ctx.owns_stream = false;
     });
+}
+int apsu_b200_ctx_get_stream(apsu_b200_ctx *ctx, void **cuda_stream)
+{
+    return guarded([&] { *need(cuda_stream, "cuda_stream") = (void *)E(ctx).ctx.stream; });
 }
 int apsu_b200_ctx_synchronize(apsu_b200_ctx *ctx)
 {

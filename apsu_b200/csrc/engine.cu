@@ -699,6 +699,30 @@ void Engine::query_begin(const uint32_t *src_powers, uint32_t nsrc, const void *
     powers_done_ = eval_done_ = false;
 }
 
+// Multi-GPU loading (mgpu.cu): the ranks of a sharded DB receive only the ciphertexts of the bundle indices they own.
+// query_begin_partial validates the source powers and opens the query; query_load_index places the ciphertexts of
+// ONE bundle index, device buffer [nsrc][2][L_first][N] in the caller's source order (asynchronous, context stream).
+void Engine::query_begin_partial(const uint32_t *src_powers, uint32_t nsrc)
+{
+    partial_rank_ = check_query_powers(src_powers, nsrc);
+    query_loaded_ = true;
+    powers_done_ = eval_done_ = false;
+}
+void Engine::query_load_index(uint32_t bundle_idx, const void *cts_device)
+{
+    const apsu_b200_params &p = ctx.params;
+    if (!query_loaded_ || partial_rank_.empty()) throw std::logic_error("query_load_index called before query_begin_partial");
+    if (bundle_idx >= p.bundle_idx_count || !cts_device) throw std::invalid_argument("query_load_index: bad arguments");
+    const size_t ct_words = (size_t)2 * ctx.first_L * ctx.N;
+    u64 *region = arena_.buf.p + (size_t)query_region_ * ctx.N;
+    const uint32_t nsrc = (uint32_t)partial_rank_.size();
+    for (uint32_t k = 0; k < nsrc; k++) {
+        u64 *dst = region + ((size_t)partial_rank_[k] * p.bundle_idx_count + bundle_idx) * ct_words;
+        APSU_CUDA_CHECK(cudaMemcpyAsync(dst, (const u64 *)cts_device + (size_t)k * ct_words, ct_words * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+    }
+    check_range((const u64 *)cts_device, nsrc * 2 * ctx.first_L, p.coeff_modulus, ctx.first_L);
+}
+
 // Row f2: the query as it arrives on the wire (seal::Serializable<Ciphertext>, common/apsu/seal_object.h:161-219,
 // sender/apsu/plaintext_powers.cpp:45): c1 of every ciphertext is a 64-byte PRNG seed, expanded here on the device
 // (sample_poly_uniform) instead of on the host: half the upload.  c0: [nsrc][bundle_idx_count][L][N].

@@ -86,6 +86,22 @@ public:
     void query_begin(const uint32_t *src_powers, uint32_t nsrc, const void *cts, bool on_device);
     void query_begin_seeded(const uint32_t *src_powers, uint32_t nsrc, const uint64_t *c0, const uint8_t *seeds64);
     void set_relin_keys_seeded(const uint64_t *c0, const uint8_t *seeds64);
+    // relinearisation keys filled in place by the caller (multi-GPU broadcast): reserve, write/receive on the context
+    // stream, then relin_keys_loaded() (runs the residue check)
+    void reserve_relin_keys() { relin_keys_.ensure((size_t)(ctx.K - 1) * 2 * ctx.K * ctx.N); }
+    u64 *relin_keys_device() { return relin_keys_.p; }
+    void relin_keys_loaded()
+    {
+        check_range(relin_keys_.p, (ctx.K - 1) * 2 * ctx.K, ctx.params.coeff_modulus, ctx.K);
+        have_keys_ = true;
+    }
+    void query_begin_partial(const uint32_t *src_powers, uint32_t nsrc);
+    void query_load_index(uint32_t bundle_idx, const void *cts_device);
+    const std::vector<std::pair<uint32_t, uint32_t>> &result_order()
+    {
+        if (!plan_valid_) build_plan();
+        return result_order_;
+    }
     void throw_if_query_invalid(); // reads back the is_valid_for flag of the loaded query / keys (synchronises)
     void set_masks(const void *masks, uint32_t npack, bool on_device);
     void encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t *out);
@@ -195,6 +211,7 @@ private:
     DBuf<uint32_t> seed_dst_, rej_; // rej_: [count per polynomial][positions]
     DBuf<int> query_bad_;           // [0] residue out of range, [1] rejection-list overflow
     bool query_checked_ = false;
+    std::vector<uint32_t> partial_rank_; // sorted rank of every source power of a partially loaded query
     std::vector<uint32_t> check_query_powers(const uint32_t *src_powers, uint32_t nsrc);
     void check_range(const u64 *base, uint32_t n_polys, const uint64_t *moduli, uint32_t nmods);
     void expand_seeds(uint32_t L, const std::vector<uint32_t> &dst, const uint8_t *seeds64, u64 *base, const uint64_t *moduli);

@@ -258,7 +258,8 @@ class Receiver:
     def ComputePowers(self, exchange=None):
         """Receiver::ComputePowers for every bundle index.  With a split PowersDag (set_powers_partition) `exchange`
         is called after every DAG level as exchange(level, regions) with regions = [(device_ptr, chunk_bytes), ...]
-        and must all-gather them between the ranks of the partition (apsu_b200/sharding.py::exchange_powers)."""
+        and must all-gather them between the ranks of the partition (apsu_b200/sharding.py::exchange_powers, which
+        needs engine_stream=self.stream() to order its collective with the context's stream)."""
         if self._part_size == 1:
             capi.check(self._L.apsu_b200_compute_powers(self.db._h))
             return
@@ -273,6 +274,12 @@ class Receiver:
             capi.check(self._L.apsu_b200_compute_powers_stage(self.db._h, s))
             if regions is not None:
                 exchange(s + 1, regions)
+
+    def stream(self) -> int:
+        """cudaStream_t the context runs on (apsu_b200_ctx_get_stream), as an integer"""
+        v = C.c_void_p()
+        capi.check(self._L.apsu_b200_ctx_get_stream(self.db._h, C.byref(v)))
+        return int(v.value or 0)
 
     def set_powers_partition(self, rank: int, size: int):
         """collective C2: this receiver computes chunk `rank` of `size` of every PowersDag level."""

@@ -24,6 +24,67 @@ def shard_bundles(degrees, world: int):
     return parts
 
 
+class MultiGpu:
+    """One rank of the C++ multi-GPU path (include/apsu_b200.h, apsu_b200_mgpu_*; csrc/mgpu.cu): query scatter, optional
+    PowersDag split and result gather all run inside the library over NCCL.  This class only forwards — ranks are
+    processes (torchrun) or threads, each with its own ReceiverDB on its own GPU."""
+
+    def __init__(self, db, unique_id: bytes, rank: int, world: int):
+        import ctypes as C
+        import numpy as np
+        from . import capi
+        self._C, self._np, self._capi, self._L = C, np, capi, capi.lib()
+        self.db, self.rank, self.world = db, rank, world
+        idb = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        h = C.c_void_p()
+        capi.check(self._L.apsu_b200_mgpu_create(db._h, capi.ptr(idb), rank, world, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import numpy as np
+        from . import capi
+        idb = np.zeros(128, dtype=np.uint8)
+        capi.check(capi.lib().apsu_b200_mgpu_unique_id(capi.ptr(idb)))
+        return idb.tobytes()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.apsu_b200_mgpu_destroy(self._h)
+            self._h = None
+
+    def commit(self, global_cache_idx=None, dag_split: int = -1):
+        g = None if global_cache_idx is None else self._np.ascontiguousarray(global_cache_idx, dtype=self._np.uint32)
+        self._capi.check(self._L.apsu_b200_mgpu_commit(self._h, self._capi.ptr(g), dag_split))
+        return self.info()
+
+    def info(self) -> dict:
+        C = self._C
+        total, group, ver = C.c_uint32(), C.c_uint32(), C.c_int()
+        self._capi.check(self._L.apsu_b200_mgpu_info(self._h, C.byref(total), C.byref(group), C.byref(ver)))
+        return {"total_bin_bundles": total.value, "dag_group_size": group.value, "nccl_version": ver.value}
+
+    def compute_powers(self):
+        self._capi.check(self._L.apsu_b200_mgpu_compute_powers(self._h))
+
+    def run_query(self, src_powers, cts, relin_keys, masks_local, out=None, bundle_idx=None, cache_idx=None):
+        """root (rank 0): cts / relin_keys host arrays and `out` [total][2][N] (allocated when None); other ranks pass
+        None.  Returns (out, bundle_idx, cache_idx) on root, None elsewhere."""
+        np, ptr = self._np, self._capi.ptr
+        sp = np.ascontiguousarray(list(src_powers), dtype=np.uint32)
+        root = self.rank == 0
+        if root and out is None:
+            total = self.info()["total_bin_bundles"]
+            out = np.zeros((max(total, 1), 2, self.db.params.poly_modulus_degree()), dtype=np.uint64)
+        if root and bundle_idx is None:
+            bundle_idx, cache_idx = np.zeros(out.shape[0], dtype=np.uint32), np.zeros(out.shape[0], dtype=np.uint32)
+        npack = 0 if masks_local is None else masks_local.shape[0]
+        self._capi.check(self._L.apsu_b200_mgpu_run_query(
+            self._h, sp, len(sp), ptr(cts) if root else None, ptr(relin_keys) if root else None, ptr(masks_local), npack,
+            ptr(out) if root else None, ptr(bundle_idx) if root else None, ptr(cache_idx) if root else None))
+        return (out, bundle_idx, cache_idx) if root else None
+
+
 def broadcast_query(tensors, src: int = 0):
     """query ciphertexts + relinearisation keys from the rank that received them (C1 of SURVEY.md §2.2)."""
     import torch.distributed as dist
@@ -129,11 +190,29 @@ def allgather_region(full, index: int, size: int, group=None):
 _REGION_VIEWS = {}
 
 
-def exchange_powers(regions, index: int, size: int, group=None):
+def exchange_powers(regions, index: int, size: int, group=None, engine_stream: int | None = None):
     """all-gather of one DAG level between the `size` ranks of a group: every region is a device buffer of `size`
     chunks, this rank's products in chunk `index` (apsu_b200_powers_exchange_regions).  In place (NCCL's in-place
     all-gather: the send buffer is this rank's chunk of the receive buffer); the tensor views of a region are built
     once, the call is on the per-query path of every rank."""
+    import torch
+    import torch.distributed as dist
+    # The collective is issued on torch's CURRENT stream while the products were written (and will be read) on the
+    # engine's stream (apsu_b200_ctx_get_stream): order the two in both directions unless they are the same stream.
+    # The C++ path (MultiGpu / apsu_b200_mgpu_*) issues the all-gather on the engine's stream itself.
+    cur = torch.cuda.current_stream()
+    ext = None
+    if engine_stream is not None and engine_stream != cur.cuda_stream:
+        ext = torch.cuda.ExternalStream(engine_stream)
+        cur.wait_stream(ext)
+    try:
+        _exchange_regions(regions, index, size, group)
+    finally:
+        if ext is not None:
+            ext.wait_stream(cur)
+
+
+def _exchange_regions(regions, index: int, size: int, group=None):
     import torch
     import torch.distributed as dist
     for ptr, chunk_bytes in regions:

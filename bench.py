@@ -198,57 +198,80 @@ def db_build_measure(pj, name, params, device, with_cpu):
     return out
 
 
-def cpu_baseline(pj, name, degrees, cts, relin, masks, sample_pairs, threads):
-    """Times the oracle (CPU restatement of the reference's SEAL path, oracle/) with all host threads busy on a
-    bounded sample of the workload: ComputePowers for ONE bundle index (the reference runs bundle indices
-    serially with -t workers over the DAG, receiver_ddh.cpp:325-333) + the evaluation of `threads` full
-    BinBundles in parallel, one per worker as in receiver_ddh.cpp:340-364.  The whole query is extrapolated
-    linearly in bundle indices and plaintext count.  `sample_pairs` (same seeds as the GPU DB) are also
-    evaluated so their result ciphertexts can be compared bit for bit.  Returns (dict, {pair: ndarray})."""
+def oracle_results(pj, name, degrees, cts, relin, masks, pairs, threads):
+    """Result ciphertexts of the BinBundles `pairs` = [(bundle_idx, cache_idx), ...] of the synthetic DB, computed by
+    the CPU oracle (same seeds as the GPU DB): the checker of `parity_sample`.  -> {pair: ndarray [2][N]}"""
     from oracle import oracle as O
     p = O.Params(pj, name + ".json")
     ctx = O.Context.from_params(p)
     bic = p.bundle_idx_count
     db = O.ReceiverDB(ctx, p)
-    b0 = sample_pairs[0][0]
-    # the oracle DB holds bundles at index b0 only (other indices empty => ComputePowers skipped there)
     local = {}
-    for (b, c) in sample_pairs:
-        assert b == b0
+    for (b, c) in pairs:
         local[(b, c)] = db.add_bundle_synthetic(b, degrees[b][c] + 1, SEEDS["db"] * 1000 + b * 64 + c)
-    full = p.max_items_per_bin
-    timed = [lc for (b, c), lc in local.items() if degrees[b][c] + 1 == full][:threads]
-    while len(timed) < max(threads, 1):  # timing-only full-size bundles so that every worker has one
-        timed.append(db.add_bundle_synthetic(b0, full, 999000 + len(timed)))
-    ses = db.run_query(p.query_powers, cts, relin, None, threads=threads, powers_only=True)
-    powers_ms_one = ses.powers_ms
-    alpha = db.bundle_count(b0)
+    alpha = max(db.bundle_count(b) for b in range(bic))
     m = np.zeros((alpha * bic, p.N), dtype=np.uint64)
-    m[:] = masks[b0]
     for (b, c), lc in local.items():
         m[b + lc * bic] = masks[b + c * bic]
-    eval_ms = ses.eval_subset([(b0, lc) for lc in timed], relin, m, threads=threads)
-    rest = [(b0, lc) for lc in local.values() if lc not in timed]
-    if rest:
-        ses.eval_subset(rest, relin, m, threads=threads)
-    res = {}
-    for (bb, lc, ct) in ses.results():
-        for (b, c), l2 in local.items():
-            if (bb, lc) == (b, l2):
-                res[(b, c)] = ct
-    timed_coeffs = len(timed) * full
+    ses = db.run_query(p.query_powers, cts, relin, m, threads=threads)
+    inv = {(b, lc): (b, c) for (b, c), lc in local.items()}
+    return {inv[(bb, lc)]: ct for (bb, lc, ct) in ses.results()}
+
+
+def cpu_baseline(pj, name, degrees, cts, relin, masks, threads):
+    """Times the oracle (CPU restatement of the reference's SEAL path, oracle/) on a bounded sample of the workload,
+    once with -t 1 and once with -t `threads` (all host threads), like the reference's thread pool: ComputePowers for
+    ONE bundle index (the reference runs bundle indices serially with -t workers over the DAG,
+    receiver_ddh.cpp:325-333) + the evaluation of t full BinBundles in parallel, one per worker as in
+    receiver_ddh.cpp:340-364.  The whole query is extrapolated linearly in bundle indices and plaintext count
+    (a non-extrapolated full query is recorded once in profiles/, tools/cpu_full_query.py)."""
+    from oracle import oracle as O
+    p = O.Params(pj, name + ".json")
+    ctx = O.Context.from_params(p)
+    bic = p.bundle_idx_count
+    full = p.max_items_per_bin
+    b0 = max(range(bic), key=lambda b: len(degrees[b]))
     total_coeffs = sum(d + 1 for row in degrees for d in row)
     n_active = sum(1 for row in degrees if row)
-    est_ms = powers_ms_one * n_active + eval_ms * total_coeffs / timed_coeffs
     n_bundles = sum(len(r) for r in degrees)
-    info = {
-        "value": n_bundles / (est_ms / 1e3), "unit": "BinBundles/s", "cores": threads, "kind": "port",
-        "sample": f"oracle (SEAL-algorithm restatement, not SEAL), -t {threads}: ComputePowers for 1 of {n_active} bundle indices "
-                  f"({powers_ms_one:.0f} ms) + eval_patstock of {len(timed)} full BinBundles in parallel = {timed_coeffs} of {total_coeffs} "
-                  f"plaintexts ({eval_ms:.0f} ms); extrapolated linearly to the whole query = {est_ms:.0f} ms",
-        "query_eval_ms_est": est_ms, "host_cores": os.cpu_count(),
+    runs = {}
+    for t in sorted({1, max(threads, 1)}):
+        db = O.ReceiverDB(ctx, p)
+        timed = [db.add_bundle_synthetic(b0, full, 999000 + k) for k in range(t)]
+        ses = db.run_query(p.query_powers, cts, relin, None, threads=t, powers_only=True)
+        m = np.zeros((len(timed) * bic, p.N), dtype=np.uint64)
+        m[:] = masks[b0]
+        eval_ms = ses.eval_subset([(b0, lc) for lc in timed], relin, m, threads=t)
+        est_ms = ses.powers_ms * n_active + eval_ms * total_coeffs / (len(timed) * full)
+        runs[t] = {"threads": t, "compute_powers_one_index_ms": ses.powers_ms, "eval_ms": eval_ms, "bundles_evaluated": len(timed),
+                   "query_eval_ms_est": est_ms, "value": n_bundles / (est_ms / 1e3)}
+        del ses, db
+    best = runs[max(runs)]
+    cpu_model = ""
+    try:
+        cpu_model = next(l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name"))
+    except Exception:  # noqa: BLE001
+        pass
+    return {
+        "value": best["value"], "unit": "BinBundles/s", "cores": best["threads"], "kind": "port",
+        "sample": f"oracle (SEAL-algorithm restatement, not SEAL; built on this host with -O3 -march=native), -t {best['threads']}: ComputePowers "
+                  f"for 1 of {n_active} bundle indices ({best['compute_powers_one_index_ms']:.0f} ms) + eval_patstock of {best['bundles_evaluated']} full "
+                  f"BinBundles in parallel ({best['eval_ms']:.0f} ms); extrapolated linearly to the whole query = {best['query_eval_ms_est']:.0f} ms",
+        "query_eval_ms_est": best["query_eval_ms_est"], "host_cores": os.cpu_count(), "cpu_model": cpu_model,
+        "t1": runs[1], "t_all": best,
     }
-    return info, res
+
+
+def results_digest(out, bidx, cidx, n):
+    """sha256 over every result ciphertext in (bundle_idx, cache_idx) order: the same synthetic DB, query and masks give
+    the same digest at every GPU count (profiles/results_sha256_*.json holds the N=1 record)."""
+    import hashlib
+    order = sorted(range(n), key=lambda k: (int(bidx[k]), int(cidx[k])))
+    h = hashlib.sha256()
+    for k in order:
+        h.update(np.array([bidx[k], cidx[k]], dtype=np.uint32).tobytes())
+        h.update(np.ascontiguousarray(out[k]).tobytes())
+    return h.hexdigest()
 
 
 def main():
@@ -260,10 +283,12 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--db-log2", type=int, default=DB_LOG2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the bit-exact comparison of sampled BinBundles with the oracle")
     ap.add_argument("--no-db-build", action="store_true", help="skip the device DB-build measurement (row f1)")
     ap.add_argument("--no-dag-split", action="store_true", help="ranks sharing a bundle index recompute its powers instead of splitting the PowersDag")
     ap.add_argument("--dag-split", action="store_true", help="split the PowersDag whenever ranks share a bundle index (default: only for large DAGs)")
     ap.add_argument("--chunk", type=int, default=None, help="BinBundles per evaluation chunk (APSU_B200_CHUNK)")
+    ap.add_argument("--write-digest", action="store_true", help="record the result digest of this run under profiles/")
     args = ap.parse_args()
     if args.chunk:
         os.environ["APSU_B200_CHUNK"] = str(args.chunk)
@@ -287,18 +312,14 @@ def main():
         if rank != 0:
             return
         from oracle import oracle as O
+        O.build()  # compiled on THIS host (-march=native)
         p = O.Params(pj, name + ".json")
         threads = os.cpu_count() or 1
         cts, relin, masks = synth_query(p.primes, p.t, p.N, p.first_L, p.K, len(p.query_powers), p.bundle_idx_count,
                                         max(len(r) for r in degrees) * p.bundle_idx_count, SEEDS["query"])
-        b0 = 0
-        full = [(b0, c) for c, d in enumerate(degrees[b0]) if d + 1 == p.max_items_per_bin][:1]
-        small = [(b0, len(degrees[b0]) - 1)]
-        sample = full + [s for s in small if s not in full]
         vals = []
         for _ in range(args.warmup + args.steps):
-            info, _ = cpu_baseline(pj, name, degrees, cts, relin, masks, sample, threads)
-            vals.append(info)
+            vals.append(cpu_baseline(pj, name, degrees, cts, relin, masks, threads))
         vals = vals[args.warmup:] or vals
         ms = float(np.mean([v["query_eval_ms_est"] for v in vals]))
         info = vals[-1]
@@ -316,7 +337,7 @@ def main():
     import torch
     import ctypes as C
     import apsu_b200
-    from apsu_b200 import capi
+    from apsu_b200 import capi, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: apsu_b200 has no CPU fallback")
@@ -333,37 +354,30 @@ def main():
     db = apsu_b200.ReceiverDB(params, local_rank)
     rx = apsu_b200.Receiver(db)
     first_L, low_L = db.level(0), db.level(1)
-    stream = torch.cuda.Stream()
-    capi.check(capi.lib().apsu_b200_ctx_set_stream(db._h, C.c_void_p(stream.cuda_stream)))
+    lib = capi.lib()
+    h = db._h
 
     # this rank's shard; local cache indices are dense per bundle index
     parts = shard(degrees, world)
     mine = parts[rank]
-    # more ranks than bundle indices: the ranks sharing an index split its PowersDag and all-gather the powers
-    # level by level (collective C2) instead of each recomputing them
-    part_group, part_index, part_pg = [rank], 0, None
-    if world > 1:
-        from apsu_b200 import sharding
-        part_group, part_index, all_groups = sharding.powers_partition(parts, rank)
-        dagp = apsu_b200.PowersDag(params)
-        n_products = len(dagp.nodes) - dagp.source_count()
-        if args.no_dag_split or not (args.dag_split or sharding.worth_splitting(n_products, len(part_group))):
-            part_group, part_index, all_groups = [rank], 0, []
-        if any(len(g) > 1 for g in all_groups):
-            for g in all_groups:  # every rank creates every group
-                pg = dist.new_group(g)
-                if g == part_group:
-                    part_pg = pg
-        if len(part_group) > 1:
-            rx.set_powers_partition(part_index, len(part_group))
-        if len(part_group) > 1:
-            config["parallelism"] = (f"BinBundles sharded over {world} GPU(s); PowersDag of a bundle index split over the "
-                                     f"{len(part_group)} rank(s) that share it, powers all-gathered per DAG level (NCCL)")
     local_of = {}
     for (b, c, d) in mine:
         local_of[(b, c)] = db.add_bin_bundle_synthetic(b, d + 1, SEEDS["db"] * 1000 + b * 64 + c)
     my_bytes = db.stream_bytes()
     total_bytes = sum(bundle_bytes(pj, d + 1, low_L) for row in degrees for d in row)
+
+    # multi-GPU: the C++ path (csrc/mgpu.cu) over its own NCCL communicator; torch.distributed only carries the
+    # communicator id, the barriers and the max-over-ranks of the timings
+    mg, mg_info = None, {"dag_group_size": 1}
+    if world > 1:
+        box = [sharding.MultiGpu.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        mg = sharding.MultiGpu(db, box[0], rank, world)
+        mg_info = mg.commit([c for (_, c, _) in mine], 0 if args.no_dag_split else (1 if args.dag_split else -1))
+        if mg_info["dag_group_size"] > 1:
+            config["parallelism"] = (f"BinBundles sharded over {world} GPU(s); PowersDag of a bundle index split over the "
+                                     f"{mg_info['dag_group_size']} rank(s) that share it, powers all-gathered per DAG level (ncclAllGather)")
+        config["multi_gpu"] = f"C++ host path apsu_b200_mgpu_* over NCCL {mg_info['nccl_version']}: query scattered by bundle index, results gathered unpadded"
 
     nsrc = len(params.query_powers())
     src_powers = np.array(params.query_powers(), dtype=np.uint32)
@@ -381,12 +395,14 @@ def main():
     cts_t, cts_p = pinned(cts)
     relin_t, relin_p = pinned(relin)
     masks_t, masks_p = pinned(masks_local)
-    n_local = len(mine)
-    out_t = torch.empty((max(n_local, 1), 2, N), dtype=torch.int64).pin_memory()
+    n_out = n_bundles if (rank == 0 or world == 1) else 1
+    out_t = torch.empty((max(n_out, 1), 2, N), dtype=torch.int64).pin_memory()
     out_p = out_t.numpy().view(np.uint64)
+    bidx = np.zeros(max(n_out, 1), dtype=np.uint32)
+    cidx = np.zeros(max(n_out, 1), dtype=np.uint32)
 
-    lib = capi.lib()
-    h = db._h
+    stream_ptr = rx.stream()
+    stream = torch.cuda.ExternalStream(stream_ptr)  # the context's own stream: timing events are recorded on it
 
     def barrier():
         if dist is not None:
@@ -394,84 +410,51 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident path: inputs in HBM before the timed region ----
-    with torch.cuda.stream(stream):
-        capi.check(lib.apsu_b200_query_begin(h, src_powers, nsrc, cts_p.reshape(-1)))
-        capi.check(lib.apsu_b200_set_relin_keys(h, capi.ptr(relin_p)))
-        capi.check(lib.apsu_b200_set_masks(h, masks_p.reshape(-1), masks_p.shape[0]))
-        rx.set_profiling(True)
+    capi.check(lib.apsu_b200_query_begin(h, src_powers, nsrc, cts_p.reshape(-1)))
+    capi.check(lib.apsu_b200_set_relin_keys(h, capi.ptr(relin_p)))
+    capi.check(lib.apsu_b200_set_masks(h, masks_p.reshape(-1), masks_p.shape[0]))
+    rx.set_profiling(True)
 
-        def compute_powers():
-            if len(part_group) > 1:
-                rx.ComputePowers(exchange=lambda level, regs: sharding.exchange_powers(regs, part_index, len(part_group), part_pg))
-            else:
-                capi.check(lib.apsu_b200_compute_powers(h))
+    def step_resident():
+        if mg is not None:
+            mg.compute_powers()
+        else:
+            capi.check(lib.apsu_b200_compute_powers(h))
+        capi.check(lib.apsu_b200_eval_all(h))
 
-        def step_resident():
-            compute_powers()
-            capi.check(lib.apsu_b200_eval_all(h))
-
+    if mine:
         for _ in range(args.warmup):
             step_resident()
-        barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        per_step = []
-        e0.record(stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    if mine:
         for _ in range(args.steps):
             step_resident()
-        e1.record(stream)
-        barrier()
-        clocks = sampler.stop()
-        ms_total = e0.elapsed_time(e1)
-        tm = rx.timings()  # last step: scopes + DB-stream kernel launches timed live with CUDA events
-        ms_step_local = ms_total / args.steps
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_step_local = e0.elapsed_time(e1) / args.steps
+    tm = rx.timings()  # last step: scopes + DB-stream kernel launches timed live with CUDA events
 
-        # ---- e2e path: host buffers through the C ABI (+ NCCL broadcast / gather for N>1) ----
-        bidx = np.zeros(max(n_local, 1), dtype=np.uint32)
-        cidx = np.zeros(max(n_local, 1), dtype=np.uint32)
-        if dist is not None:
-            # one pinned host block and one device block for the whole query (ciphertexts + relinearisation keys):
-            # one H2D copy on the rank that received it, one NCCL broadcast
-            q_host = torch.empty(cts_t.numel() + relin_t.numel(), dtype=torch.int64).pin_memory()
-            q_host[:cts_t.numel()] = cts_t.reshape(-1)
-            q_host[cts_t.numel():] = relin_t.reshape(-1)
-            d_query = torch.empty(q_host.shape, dtype=torch.int64, device="cuda")
-            d_cts, d_relin = d_query[:cts_t.numel()], d_query[cts_t.numel():]
-            counts = [len(x) for x in parts]
-            gatherer = sharding.ResultGatherer(counts, N, torch.device("cuda", local_rank), dst=0)
+    # ---- e2e path: host buffers through the C ABI; N>1: the C++ multi-GPU path (scatter / gather over NCCL inside) ----
+    def step_e2e():
+        if mg is None:
+            capi.check(lib.apsu_b200_run_query(h, src_powers, nsrc, capi.ptr(cts_p), capi.ptr(relin_p), capi.ptr(masks_p),
+                                               masks_p.shape[0], capi.ptr(out_p), capi.ptr(bidx), capi.ptr(cidx)))
+        else:
+            mg.run_query(src_powers, cts_p if rank == 0 else None, relin_p if rank == 0 else None, masks_p, out_p, bidx, cidx)
 
-        def step_e2e():
-            if dist is None:
-                capi.check(lib.apsu_b200_run_query(h, src_powers, nsrc, capi.ptr(cts_p), capi.ptr(relin_p), capi.ptr(masks_p),
-                                                   masks_p.shape[0], capi.ptr(out_p), capi.ptr(bidx), capi.ptr(cidx)))
-            else:
-                # rank 0 holds the query on the host: H2D once, NCCL broadcast over NVLink, evaluate, gather, D2H
-                if rank == 0:
-                    d_query.copy_(q_host, non_blocking=True)
-                sharding.broadcast_query([d_query], src=0)
-                capi.check(lib.apsu_b200_query_begin_device(h, src_powers, nsrc, C.c_void_p(d_cts.data_ptr())))
-                capi.check(lib.apsu_b200_set_relin_keys_device(h, C.c_void_p(d_relin.data_ptr())))
-                capi.check(lib.apsu_b200_set_masks(h, masks_p.reshape(-1), masks_p.shape[0]))
-                compute_powers()
-                capi.check(lib.apsu_b200_eval_all(h))
-                if n_local:
-                    capi.check(lib.apsu_b200_copy_results_device(h, C.c_void_p(gatherer.local_buffer().data_ptr())))
-                gatherer.gather()
-                if rank == 0:
-                    stream.synchronize()  # the results are on the host
-
-        for _ in range(args.warmup):
-            step_e2e()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        f1.record(stream)
-        barrier()
-        e2e_ms_local = max(f0.elapsed_time(f1), (time.perf_counter() - w0) * 1e3) / args.steps
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()  # returns with the results on the (root's) host
+    e2e_ms_local = (time.perf_counter() - w0) * 1e3 / args.steps
+    barrier()
 
     # max over ranks
     if dist is not None:
@@ -482,6 +465,7 @@ def main():
         ms_step, e2e_ms = ms_step_local, e2e_ms_local
 
     if rank == 0:
+        # N=1: local cache indices are the global ones (one rank holds everything, in order)
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
@@ -512,30 +496,54 @@ def main():
             },
             "clocks": clocks,
             "e2e": {"value": n_bundles / (e2e_ms / 1e3), "unit": "BinBundles/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(cts.nbytes + relin.nbytes + masks_local.nbytes),
-                    "d2h_bytes_per_step": int(n_bundles * 2 * N * 8)},
+                    "h2d_bytes_per_step": int(cts.nbytes + relin.nbytes + masks.nbytes),
+                    "d2h_bytes_per_step": int(n_bundles * 2 * N * 8),
+                    "what": "apsu_b200_run_query" if world == 1 else "apsu_b200_mgpu_run_query (root uploads the query, NCCL scatter / gather inside the call; "
+                                                                      "every rank uploads its own masks)"},
             "gpu_launches": int(tm["kernel_launches"]) * args.steps,
             "launch_mode": "eager" if os.environ.get("APSU_B200_NO_GRAPH", "0") not in ("", "0") else
-                           f"CUDA graphs replayed per query ({int(tm['kernel_launches'])} kernel nodes of this repo's kernels per query)",
+                           f"CUDA graphs replayed per query ({int(tm['kernel_launches'])} kernel nodes of this repo's kernels per query on rank 0)",
         }
-        if not args.no_cpu_baseline and world == 1:
-            # bounded CPU sample of the same workload + bit-exact spot check of those BinBundles
-            b0 = mine[0][0]
-            full = [(b, c) for (b, c, d) in mine if b == b0 and d + 1 == pj["table_params"]["max_items_per_bin"]][:1]
-            small = [(b, c) for (b, c, d) in mine if b == b0][-1:]
-            sample = full + [s for s in small if s not in full]
-            info, ref = cpu_baseline(pj, name, degrees, cts, relin, masks, sample, os.cpu_count() or 1)
-            out["cpu_baseline"] = info
-            got = {(r.bundle_idx, r.cache_idx): r.psu_result.reshape(2, -1) for r in rx.results()}
-            ok = all(np.array_equal(got[(b, local_of[(b, c)])], ref[(b, c)]) for (b, c) in sample)
-            out["parity_sample"] = {"bundles": sample, "bit_exact_vs_oracle": bool(ok)}
+        # ---- parity at every N: the gathered results of the last e2e step against the oracle (one BinBundle per rank,
+        # the fullest and the smallest at N=1) and their digest against the N=1 record ----
+        got = {(int(bidx[k]), int(cidx[k])): out_p[k] for k in range(n_bundles)}
+        digest = results_digest(out_p, bidx, cidx, n_bundles)
+        out["results_sha256"] = digest
+        rec = ROOT / "profiles" / f"results_sha256_{name}_2p{args.db_log2}.json"
+        if args.write_digest and world == 1:
+            rec.write_text(json.dumps({"workload": config["workload"], "seeds": SEEDS, "n_gpus": 1, "results_sha256": digest}, indent=1) + "\n")
+        if rec.exists():
+            want = json.loads(rec.read_text())["results_sha256"]
+            out["results_sha256_matches_n1_record"] = bool(want == digest)
+            if want != digest:
+                out["INVALID"] = "result digest differs from the recorded N=1 run (profiles/" + rec.name + ")"
+        if not args.no_parity:
+            sample = []
+            for part in parts:
+                if part:
+                    sample.append((part[0][0], part[0][1]))
+            if world == 1:
+                b0 = mine[0][0]
+                small = [(b, c) for (b, c, d) in mine if b == b0][-1:]
+                sample += [s_ for s_ in small if s_ not in sample]
+            ref = oracle_results(pj, name, degrees, cts, relin, masks, sample, os.cpu_count() or 1)
+            ok = all(np.array_equal(got[k].reshape(2, -1), ref[k]) for k in sample)
+            out["parity_sample"] = {"bundles": sample, "bit_exact_vs_oracle": bool(ok),
+                                    "what": "result ciphertexts gathered on rank 0 by the last end-to-end step vs the CPU oracle, one BinBundle per rank"}
             if not ok:
                 out["INVALID"] = "GPU results differ from the oracle on the sampled BinBundles"
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import oracle as O
+            O.build()  # on this host
+            out["cpu_baseline"] = cpu_baseline(pj, name, degrees, cts, relin, masks, os.cpu_count() or 1)
         if not args.no_db_build and world == 1:
             out["db_build"] = db_build_measure(pj, name, params, local_rank, not args.no_cpu_baseline)
         print(json.dumps(out))
+    if mg is not None:
+        mg.close()
     db.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -95,9 +95,17 @@ int apsu_b200_powers_dag(
  * BEHZ constants on `device` (a CUDA ordinal). */
 int apsu_b200_ctx_create(const apsu_b200_params *params, int device, apsu_b200_ctx **out);
 void apsu_b200_ctx_destroy(apsu_b200_ctx *ctx);
+/* Pinned host memory for query / result buffers (host<->device copies from pageable memory run at a fraction of the
+ * PCIe rate). */
+int apsu_b200_host_alloc(size_t bytes, void **out);
+void apsu_b200_host_free(void *p);
 /* Run all work of this context on an existing cudaStream_t (e.g. torch's current stream).  NULL (the legacy default
  * stream) is accepted but cannot be captured into CUDA graphs: the context then launches its kernels one by one. */
 int apsu_b200_ctx_set_stream(apsu_b200_ctx *ctx, void *cuda_stream);
+/* The cudaStream_t the context runs on (its own non-blocking stream unless one was set): anything that touches the
+ * context's device buffers from another stream (e.g. an external collective on apsu_b200_powers_exchange_regions)
+ * must order itself with this stream in both directions. */
+int apsu_b200_ctx_get_stream(apsu_b200_ctx *ctx, void **cuda_stream);
 int apsu_b200_ctx_synchronize(apsu_b200_ctx *ctx);
 /* number of RNS primes of: 0 = first data level, 1 = DB plaintexts / low powers, 2 = high powers,
  * 3 = key level (get_parms_id_for_chain_idx, common/apsu/util/utils.cpp:179-189). */
@@ -223,6 +231,41 @@ int apsu_b200_results_device(apsu_b200_ctx *ctx, void **ptr, uint64_t *bytes);
 /* asynchronous device-to-device copy of the results into a caller-owned device buffer (e.g. a torch tensor
  * that is then gathered with NCCL); ordered on the context stream. */
 int apsu_b200_copy_results_device(apsu_b200_ctx *ctx, void *dst_device);
+
+/* ---- multi-GPU: one rank per B200, BinBundles sharded ------------------------------------------ */
+/* The reference fans ProcessBinBundleCache out over a thread pool (receiver/apsu/receiver_ddh.cpp:340-364); the unit
+ * of that fan-out, the BinBundle, is what shards across GPUs: every rank holds the BinBundles it was given in its own
+ * context (apsu_b200_db_add_*), recomputes the query powers of the bundle indices it owns (ComputePowers,
+ * receiver_ddh.cpp:325-333) and evaluates its BinBundles.  All exchanges run inside the library, in C++, over NCCL
+ * (bound at run time with dlopen("libnccl.so.2"); no link-time dependency): the query goes from the root rank (0) to
+ * the ranks that need it (only the ciphertexts of the bundle indices a rank owns; relinearisation keys to all), the
+ * result ciphertexts come back to the root unpadded.  When several ranks hold BinBundles of ONE bundle index only,
+ * they may split its PowersDag and all-gather every DAG level in place (collective C2).
+ * One apsu_b200_mgpu per rank; ranks may be processes (one per GPU) or threads of one process (each with its own
+ * context); every function below is COLLECTIVE: all ranks call it, in the same order. */
+typedef struct apsu_b200_mgpu apsu_b200_mgpu;
+#define APSU_B200_MGPU_ID_BYTES 128
+/* ncclGetUniqueId on one rank; hand the 128 bytes to every rank (any transport). */
+int apsu_b200_mgpu_unique_id(uint8_t *id /*[128]*/);
+int apsu_b200_mgpu_create(apsu_b200_ctx *ctx, const uint8_t *id, uint32_t rank, uint32_t world, apsu_b200_mgpu **out);
+void apsu_b200_mgpu_destroy(apsu_b200_mgpu *m);
+/* After the rank's BinBundles are loaded (and after every DB change): publishes which BinBundles each rank holds.
+ * global_cache_idx[k] = cache index, in the whole DB, of this rank's k-th BinBundle in result order (bundle_idx major,
+ * local cache index minor); NULL = the local indices.  dag_split: 1 = ranks sharing one bundle index split its
+ * PowersDag, 0 = every rank recomputes it, -1 = split only large DAGs (>= 128 products: below that a level's all-gather
+ * costs more than the products it saves, profiles/README.md). */
+int apsu_b200_mgpu_commit(apsu_b200_mgpu *m, const uint32_t *global_cache_idx, int dag_split);
+int apsu_b200_mgpu_info(const apsu_b200_mgpu *m, uint32_t *total_bin_bundles, uint32_t *dag_group_size, int *nccl_version);
+/* The HE part of Receiver::RunQuery (receiver_ddh.cpp:295-369) over all ranks, host buffers in and out.  Root passes
+ * cts / relin_keys (layouts of apsu_b200_run_query) and receives out = uint64_t[total][2][N] with the ResultPackage
+ * indices of every result (rank-major, each rank's results in its result order); the other ranks pass NULL for them.
+ * masks_local: this rank's dense mask table for its local cache indices (NULL keeps the resident masks, e.g. after
+ * apsu_b200_generate_masks). */
+int apsu_b200_mgpu_run_query(
+    apsu_b200_mgpu *m, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys, const uint64_t *masks_local,
+    uint32_t npack_local, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
+/* ComputePowers of this rank with the per-level exchange of a split PowersDag (query already loaded). */
+int apsu_b200_mgpu_compute_powers(apsu_b200_mgpu *m);
 
 /* ---- SEAL Evaluator calls on the path, as stand-alone batched device operations (K2–K8) ----- */
 /* modulus selector for apsu_b200_op_ntt: index into [coeff_modulus[0..K-1], m_sk, B_0.., plain_modulus] */

@@ -21,11 +21,31 @@ u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
 
 
+def _host_tag() -> str:
+    """CPU model + ISA flags of this host: liborc.so is compiled with -march=native, so a binary built elsewhere (the
+    build container) is rebuilt on the box that runs it (GPU box host cores for the CPU baseline)."""
+    import hashlib
+    model, flags = "", ""
+    try:
+        for line in pathlib.Path("/proc/cpuinfo").read_text().splitlines():
+            if line.startswith("model name") and not model:
+                model = line.split(":", 1)[1].strip()
+            if line.startswith("flags") and not flags:
+                flags = line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return model + " " + hashlib.sha256(flags.encode()).hexdigest()[:16]
+
+
 def build(force: bool = False) -> pathlib.Path:
-    so = _HERE / "liborc.so"
+    so, tag_file = _HERE / "liborc.so", _HERE / "liborc.so.host"
     srcs = [_HERE / n for n in ("oracle_capi.cpp", "apsu_restate.hpp", "seal_restate.hpp", "prng_restate.hpp")]
-    if force or not so.exists() or any(s.exists() and s.stat().st_mtime > so.stat().st_mtime for s in srcs):
-        subprocess.check_call(["make", "-C", str(_HERE), "-s"])
+    tag = _host_tag()
+    stale = not so.exists() or any(s.exists() and s.stat().st_mtime > so.stat().st_mtime for s in srcs)
+    other_host = not tag_file.exists() or tag_file.read_text() != tag
+    if force or stale or other_host:
+        subprocess.check_call(["make", "-C", str(_HERE), "-s", "-B"])
+        tag_file.write_text(tag)
     return so
 
 

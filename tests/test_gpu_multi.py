@@ -1,0 +1,76 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the C++ multi-GPU path (apsu_b200_mgpu_*, csrc/mgpu.cu) with
+REAL NCCL between two B200s — query scatter (ncclSend/ncclRecv per bundle index + ncclBroadcast of the keys), the
+PowersDag split with its per-level in-place ncclAllGather (collective C2) and the unpadded result gather — compared
+bit for bit with the CPU oracle.  The two ranks are two threads of this process, each with its own context on its own
+GPU (ctypes releases the GIL, so both block inside NCCL concurrently); bench.py runs the same calls with one process
+per GPU under torchrun."""
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from harness import Scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _run_ranks(world, fn):
+    with ThreadPoolExecutor(world) as ex:
+        futs = [ex.submit(fn, r) for r in range(world)]
+        return [f.result(timeout=600) for f in futs]
+
+
+@pytest.mark.parametrize("name,degrees,dag_split,expect_group", [
+    ("1M-4096-com", [[30, 9], [20], [], [12], [18]], -1, 1),   # ranks own different bundle indices: scatter by index
+    ("16M-4096", [[140, 45]], 1, 2),                            # both ranks on ONE bundle index: PowersDag split (C2)
+    ("256K-512", [[63, 20, 5]], 1, 2),                          # direct evaluation, depth-1 DAG, split
+    ("16M-4096", [[50], [], [46, 3], []], 0, 1),                # empty bundle indices, no split
+])
+def test_two_gpu_query_matches_oracle(name, degrees, dag_split, expect_group):
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    import apsu_b200
+    from apsu_b200.sharding import MultiGpu, shard_bundles
+    world = 2
+    sc = Scenario(name, degrees, planted=4)
+    bic = sc.p.bundle_idx_count
+    exp = {(b, c): ct for b, c, ct in sc.db.run_query(sc.src_powers, sc.cts, sc.relin, sc.masks, threads=4).results()}
+    parts = shard_bundles(degrees, world)
+    uid = MultiGpu.unique_id()
+
+    def rank_main(r):
+        db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), r)
+        mg = None
+        try:
+            local, gidx = {}, []
+            for (b, c, _) in parts[r]:
+                local[(b, c)] = db.add_bin_bundle(b, [a for (_, a) in sc.db.bundle_coeffs(b, c)])
+                gidx.append(c)
+            alpha = (max(local.values()) + 1) if local else 1
+            masks = np.zeros((alpha * bic, sc.p.N), dtype=np.uint64)
+            for (b, c), lc in local.items():
+                masks[b + lc * bic] = sc.masks[b + c * bic]
+            mg = MultiGpu(db, uid, r, world)
+            info = mg.commit(gidx, dag_split)
+            out = None
+            for _ in range(2):  # twice: the second query replays the captured graphs and reuses the staging buffers
+                out = mg.run_query(sc.src_powers, sc.cts if r == 0 else None, sc.relin if r == 0 else None, masks)
+            return info, out
+        finally:
+            if mg is not None:
+                mg.close()
+            db.close()
+
+    res = _run_ranks(world, rank_main)
+    info0, (out, bidx, cidx) = res[0]
+    assert info0["total_bin_bundles"] == len(exp)
+    assert info0["dag_group_size"] == expect_group and res[1][0]["dag_group_size"] == expect_group
+    got = {(int(bidx[k]), int(cidx[k])): out[k] for k in range(len(exp))}
+    assert set(got) == set(exp)
+    for key in exp:
+        assert np.array_equal(got[key], exp[key]), key

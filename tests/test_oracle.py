@@ -234,3 +234,16 @@ def test_prng_stream_and_sample_poly_uniform():
                 rejected += 1
             assert int(got[j, i]) == r % q, (j, i)
     assert rejected > 0
+
+
+def test_seal_kat_expected_is_current():
+    """tests/golden/seal_kat_expected.json (what tools/seal_kat/seal_kat.cpp must print when run against real SEAL 3.7)
+    is what the oracle computes today — one configuration here, all four in tools/seal_kat/make_kat_expected.py."""
+    import json
+    import pathlib
+    import sys
+    root = pathlib.Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root / "tools" / "seal_kat"))
+    import make_kat_expected as MK
+    exp = json.loads((root / "tests" / "golden" / "seal_kat_expected.json").read_text())
+    assert MK.config_vectors("256K-512") == exp["configs"]["256K-512"]
