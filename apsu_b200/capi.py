@@ -114,6 +114,8 @@ SIGNATURES = {
     "apsu_b200_powers_exchange_regions": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint32)]),
     "apsu_b200_eval_all": (C.c_int, [vp]),
     "apsu_b200_fetch_results": (C.c_int, [vp, vp, vp, vp]),
+    "apsu_b200_eval_all_stream": (C.c_int, [vp, vp, vp, vp]),
+    "apsu_b200_ctx_set_eval_chunk": (C.c_int, [vp, C.c_uint32]),
     "apsu_b200_run_query": (C.c_int, [vp, u32p, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp]),
     "apsu_b200_query_begin_device": (C.c_int, [vp, u32p, C.c_uint32, vp]),
     "apsu_b200_set_relin_keys_device": (C.c_int, [vp, vp]),

@@ -344,6 +344,14 @@ int apsu_b200_eval_all(apsu_b200_ctx *ctx)
 {
     return guarded([&] { E(ctx).eval_all(); });
 }
+int apsu_b200_eval_all_stream(apsu_b200_ctx *ctx, uint64_t *out, apsu_b200_result_fn fn, void *user)
+{
+    return guarded([&] { E(ctx).eval_all_stream(out, fn, user); });
+}
+int apsu_b200_ctx_set_eval_chunk(apsu_b200_ctx *ctx, uint32_t bin_bundles)
+{
+    return guarded([&] { E(ctx).set_eval_chunk(bin_bundles); });
+}
 int apsu_b200_fetch_results(apsu_b200_ctx *ctx, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx)
 {
     return guarded([&] { E(ctx).fetch_results(out, bundle_idx, cache_idx); });

@@ -255,26 +255,30 @@ NttArgs DeviceContext::make_args(const std::vector<uint32_t> &pattern) const
     return a;
 }
 
-template <int LOGN, int DIV>
-static void launch_ntt_shape(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, bool inverse, cudaStream_t st)
+template <int LOGN, int DIV, int MODE>
+static void launch_ntt_shape(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, const NttFuse &f, bool inverse, cudaStream_t st)
 {
     constexpr int threads = (1 << LOGN) / DIV;
     constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4)); // + one pad word per 16
-    if (inverse)
-        ntt_kernel<LOGN, false, DIV><<<count, threads, smem, st>>>(in, out, a, s);
-    else
-        ntt_kernel<LOGN, true, DIV><<<count, threads, smem, st>>>(in, out, a, s);
+    // the forward transform fuses kNttExtend, the inverse one kNttTensor / kNttKsMac (ntt.cuh)
+    if (inverse) {
+        if constexpr (MODE != kNttExtend) ntt_kernel<LOGN, false, DIV, MODE><<<count, threads, smem, st>>>(in, out, a, s, f);
+    } else {
+        if constexpr (MODE == kNttPlain || MODE == kNttExtend) ntt_kernel<LOGN, true, DIV, MODE><<<count, threads, smem, st>>>(in, out, a, s, f);
+    }
 }
 
-// picks the launch shape by batch size (ntt.cuh): more threads per polynomial while the batch leaves SMs idle
 // Function attributes are per device: every DeviceContext opts its device's kernel instances into the large
 // dynamic shared-memory size once, in its constructor (two contexts on different GPUs of one process both work).
 template <int LOGN, int DIV>
 static void configure_ntt_shape()
 {
     constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4));
-    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true, DIV, kNttPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true, DIV, kNttExtend>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV, kNttPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV, kNttTensor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV, kNttKsMac>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
 template <int LOGN>
 static void configure_ntt()
@@ -284,16 +288,30 @@ static void configure_ntt()
     configure_ntt_shape<LOGN, 32>();
 }
 
-template <int LOGN>
-static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, bool inverse, cudaStream_t st, int sms)
+// picks the launch shape by batch size (ntt.cuh): more threads per polynomial while the batch leaves SMs idle
+template <int LOGN, int MODE>
+static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, const NttFuse &f, bool inverse, cudaStream_t st, int sms)
 {
     // measured (N = 8192, one bundle index): 24..112 polynomials take 16 us with N/8 threads and 20-22 us with N/32;
     // N/16 threads for 150..300 polynomials made no difference
     constexpr int kLatDiv = (LOGN == 12 || LOGN == 13) ? 8 : 16; // at most 1024 threads per CTA
     if (count <= (uint32_t)sms * ntt_min_blocks(LOGN, kLatDiv))
-        launch_ntt_shape<LOGN, kLatDiv>(in, out, count, a, s, inverse, st);
+        launch_ntt_shape<LOGN, kLatDiv, MODE>(in, out, count, a, s, f, inverse, st);
     else
-        launch_ntt_shape<LOGN, 32>(in, out, count, a, s, inverse, st);
+        launch_ntt_shape<LOGN, 32, MODE>(in, out, count, a, s, f, inverse, st);
+}
+
+template <int MODE>
+static void launch_ntt_logn(uint32_t logN, const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, const NttFuse &f, bool inverse, cudaStream_t st,
+                            int sms)
+{
+    switch (logN) {
+    case 11: launch_ntt<11, MODE>(in, out, count, a, s, f, inverse, st, sms); break;
+    case 12: launch_ntt<12, MODE>(in, out, count, a, s, f, inverse, st, sms); break;
+    case 13: launch_ntt<13, MODE>(in, out, count, a, s, f, inverse, st, sms); break;
+    case 14: launch_ntt<14, MODE>(in, out, count, a, s, f, inverse, st, sms); break;
+    default: throw std::invalid_argument("unsupported poly_modulus_degree");
+    }
 }
 
 void DeviceContext::ntt(const u64 *in, u64 *out, uint32_t count, const std::vector<uint32_t> &pattern, bool inverse,
@@ -302,12 +320,24 @@ void DeviceContext::ntt(const u64 *in, u64 *out, uint32_t count, const std::vect
     if (!count) return;
     NttArgs a = make_args(pattern);
     NttSrc s{ src_idx, dst_idx, reduce_input ? 1 : 0 };
-    switch (logN) {
-    case 11: launch_ntt<11>(in, out, count, a, s, inverse, stream, sms); break;
-    case 12: launch_ntt<12>(in, out, count, a, s, inverse, stream, sms); break;
-    case 13: launch_ntt<13>(in, out, count, a, s, inverse, stream, sms); break;
-    case 14: launch_ntt<14>(in, out, count, a, s, inverse, stream, sms); break;
-    default: throw std::invalid_argument("unsupported poly_modulus_degree");
+    launch_ntt_logn<kNttPlain>(logN, in, out, count, a, s, NttFuse(), inverse, stream, sms);
+    APSU_CUDA_CHECK(cudaGetLastError());
+    launches++;
+}
+
+// transforms with a fused element-wise prologue (ntt.cuh: NttFuse); `arena` is both the source of the fused inputs and
+// the destination
+void DeviceContext::ntt_fused(int mode, u64 *arena, uint32_t count, const std::vector<uint32_t> &pattern, const uint32_t *src_idx, const uint32_t *dst_idx,
+                              u64 *out_base, const NttFuse &f)
+{
+    if (!count) return;
+    NttArgs a = make_args(pattern);
+    NttSrc s{ src_idx, dst_idx, 0 };
+    switch (mode) {
+    case kNttExtend: launch_ntt_logn<kNttExtend>(logN, arena, out_base, count, a, s, f, false, stream, sms); break;
+    case kNttTensor: launch_ntt_logn<kNttTensor>(logN, arena, out_base, count, a, s, f, true, stream, sms); break;
+    case kNttKsMac: launch_ntt_logn<kNttKsMac>(logN, arena, out_base, count, a, s, f, true, stream, sms); break;
+    default: throw std::invalid_argument("unknown fused transform");
     }
     APSU_CUDA_CHECK(cudaGetLastError());
     launches++;

@@ -98,6 +98,10 @@ public:
     // word modulo the target modulus first.
     void ntt(const u64 *in, u64 *out, uint32_t count, const std::vector<uint32_t> &pattern, bool inverse,
              const uint32_t *src_idx = nullptr, const uint32_t *dst_idx = nullptr, bool reduce_input = false);
+    // transform with a fused element-wise prologue (ntt.cuh: kNttExtend / kNttTensor / kNttKsMac); fused inputs are read
+    // from `arena`, polynomial p is written to out_base + (dst_idx ? dst_idx[p] : p) * N
+    void ntt_fused(int mode, u64 *arena, uint32_t count, const std::vector<uint32_t> &pattern, const uint32_t *src_idx, const uint32_t *dst_idx, u64 *out_base,
+                   const NttFuse &f);
     std::vector<uint32_t> pattern_q(uint32_t L) const;   // q_0..q_{L-1}
     std::vector<uint32_t> pattern_bsk(uint32_t L) const; // B_0..B_{|B|-1}, m_sk for level L
     std::vector<uint32_t> pattern_ks(uint32_t L) const;  // q_0..q_{L-1}, P

@@ -69,4 +69,15 @@ struct KeySwitchConsts {
     u64 half_P_mod[kMaxQ];  // (P>>1) mod q_i
 };
 
+// fused prologues of the transforms (ntt.cuh)
+enum { kNttPlain = 0, kNttExtend = 1, kNttTensor = 2, kNttKsMac = 3 };
+struct NttFuse {
+    const LevelConsts *lc; // kNttExtend: constants of the level (device copy)
+    const unsigned *a_idx; // kNttTensor: operand a per op;  kNttKsMac: digit block per op ([L][R] polynomials)
+    const unsigned *b_idx; // kNttTensor: operand b per op
+    const u64 *keys;       // kNttKsMac: relinearisation keys [K-1][2][K][N]
+    int L, S, K;           // |q|, |Bsk| (kNttExtend / kNttTensor); |q|, -, key primes (kNttKsMac)
+};
+
+
 } // namespace apsu_b200

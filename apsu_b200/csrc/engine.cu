@@ -119,9 +119,20 @@ struct ProgramBuilder {
                     ndst.push_back(exts[k] + c * LS + j);
                 }
             }
+        Engine *en = &e;
+        if (e.fuse_) {
+            // one launch: the transform of polynomial (rp, j) computes its own input (ntt.cuh: kNttExtend)
+            size_t so = idx.add(esrc), dn = idx.add(ndst);
+            const uint32_t count = (uint32_t)ndst.size();
+            const std::vector<uint32_t> pat = ctx.pattern_ext(L);
+            step([=] {
+                NttFuse f{ en->levels_dev_.p + L, nullptr, nullptr, nullptr, (int)L, (int)S, 0 };
+                en->ctx.ntt_fused(kNttExtend, en->arena_.buf.p, count, pat, en->idx_.at(so), en->idx_.at(dn), en->arena_.buf.p, f);
+            });
+            return;
+        }
         size_t so = idx.add(esrc), dn = idx.add(edst);
         uint32_t n = (uint32_t)esrc.size();
-        Engine *en = &e;
         step([=] { en->run_extend(L, n, en->idx_.at(so), en->idx_.at(dn)); });
         ntt(nsrc, ndst, ctx.pattern_ext(L), false);
     }
@@ -142,8 +153,17 @@ struct ProgramBuilder {
         }
         size_t ao = idx.add(a), bo = idx.add(b), dof = idx.add(d), so = idx.add(ssrc), sd = idx.add(sdst);
         Engine *en = &e;
-        step([=] { en->run_tensor(L, n_ops, en->idx_.at(ao), en->idx_.at(bo), en->idx_.at(dof)); });
-        ntt_run(scratch, n_ops * 3 * LS, ctx.pattern_ext(L), true);
+        if (e.fuse_) {
+            // tensor product computed on the way into the inverse transform (ntt.cuh: kNttTensor)
+            const std::vector<uint32_t> pat = ctx.pattern_ext(L);
+            step([=] {
+                NttFuse f{ nullptr, en->idx_.at(ao), en->idx_.at(bo), nullptr, (int)L, (int)S, 0 };
+                en->ctx.ntt_fused(kNttTensor, en->arena_.buf.p, n_ops * 3 * LS, pat, nullptr, nullptr, en->arena_.buf.p + (size_t)scratch * en->ctx.N, f);
+            });
+        } else {
+            step([=] { en->run_tensor(L, n_ops, en->idx_.at(ao), en->idx_.at(bo), en->idx_.at(dof)); });
+            ntt_run(scratch, n_ops * 3 * LS, ctx.pattern_ext(L), true);
+        }
         step([=] { en->run_scale_down(L, n_ops * 3, en->idx_.at(so), en->idx_.at(sd)); });
     }
     static uint32_t multiply_scratch(const DeviceContext &c, uint32_t L, uint32_t n_ops) { return n_ops * 3 * (L + (uint32_t)c.level[L].S); }
@@ -168,8 +188,17 @@ struct ProgramBuilder {
         ntt(nsrc, ndst, ctx.pattern_ks(L), false, /*reduce=*/true);
         size_t dg = idx.add(dig), ac = idx.add(acc), ct = idx.add(ct3), ds = idx.add(dst);
         Engine *en = &e;
-        step([=] { en->run_ks_mac(L, n_ops, en->idx_.at(dg), en->idx_.at(ac)); });
-        ntt_run(acc0, n_ops * 2 * R, ctx.pattern_ks(L), true);
+        if (e.fuse_) {
+            // inner product with the keys computed on the way into the inverse transform (ntt.cuh: kNttKsMac)
+            const std::vector<uint32_t> pat = ctx.pattern_ks(L);
+            step([=] {
+                NttFuse f{ nullptr, en->idx_.at(dg), nullptr, en->relin_keys_.p, (int)L, 0, (int)en->ctx.K };
+                en->ctx.ntt_fused(kNttKsMac, en->arena_.buf.p, n_ops * 2 * R, pat, nullptr, nullptr, en->arena_.buf.p + (size_t)acc0 * en->ctx.N, f);
+            });
+        } else {
+            step([=] { en->run_ks_mac(L, n_ops, en->idx_.at(dg), en->idx_.at(ac)); });
+            ntt_run(acc0, n_ops * 2 * R, ctx.pattern_ks(L), true);
+        }
         step([=] { en->run_ks_moddown(L, n_ops, en->idx_.at(ac), en->idx_.at(ct), en->idx_.at(ds)); });
     }
     static uint32_t relin_scratch(uint32_t L, uint32_t n_ops) { return n_ops * (L + 2) * (L + 1); }
@@ -262,6 +291,8 @@ Engine::Engine(const apsu_b200_params &p, int device) : ctx(p, device)
         kt_grid_cap_ = (uint32_t)(ctx.sms * per_sm);
     }
     if (const char *ev = std::getenv("APSU_B200_NO_GRAPH")) use_graphs_ = atoi(ev) == 0;
+    if (const char *ev = std::getenv("APSU_B200_CHUNK")) eval_chunk_ = (uint32_t)std::max(1, atoi(ev));
+    if (const char *ev = std::getenv("APSU_B200_NO_FUSE")) fuse_ = atoi(ev) == 0; // A/B: element-wise kernels unfused
     for (auto &ev : ev_) APSU_CUDA_CHECK(cudaEventCreate(&ev));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
 }
@@ -269,6 +300,11 @@ Engine::Engine(const apsu_b200_params &p, int device) : ctx(p, device)
 Engine::~Engine()
 {
     drop_graphs();
+    for (auto &g : fin_groups_) {
+        if (g.done) cudaEventDestroy(g.done);
+        if (g.copied) cudaEventDestroy(g.copied);
+    }
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
     for (auto &e : ev_)
         if (e) cudaEventDestroy(e);
     for (auto &pr : mac_events_) {
@@ -785,6 +821,11 @@ void Engine::build_plan()
     powers_prog_.clear();
     eval_prog_.clear();
     mac_step_bytes_.clear();
+    for (auto &g : fin_groups_) {
+        if (g.done) cudaEventDestroy(g.done);
+        if (g.copied) cudaEventDestroy(g.copied);
+    }
+    fin_groups_.clear();
 
     const std::set<uint32_t> &targets = dag.target_powers();
     std::vector<uint32_t> sources(p.query_powers, p.query_powers + p.query_power_count);
@@ -990,8 +1031,7 @@ void Engine::build_plan()
         for (auto &v : db) alpha_max = std::max<uint32_t>(alpha_max, (uint32_t)v.size());
         npack_needed_ = alpha_max * bic;
 
-        uint32_t chunk = 32; // measured on B200: larger batches win over L2 locality (launch tails dominate)
-        if (const char *ev = std::getenv("APSU_B200_CHUNK")) chunk = (uint32_t)std::max(1, atoi(ev));
+        const uint32_t chunk = eval_chunk_; // measured on B200: larger batches win over L2 locality (launch tails dominate)
         const uint32_t drops = Ll - Lh;
         if (drops > 1) throw std::logic_error("unexpected level gap between low and high powers");
 
@@ -1196,6 +1236,10 @@ void Engine::build_plan()
         }
     }
 
+    for (auto &g : fin_groups_) {
+        APSU_CUDA_CHECK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+        APSU_CUDA_CHECK(cudaEventCreateWithFlags(&g.copied, cudaEventDisableTiming));
+    }
     arena_.buf.ensure(arena_.high_water * (size_t)N);
     idx_.upload(ctx.stream);
     desc_dev_.upload(desc_host_, ctx.stream);
@@ -1370,6 +1414,11 @@ void Engine::emit_finalize(ProgramBuilder &pb, uint32_t Ls, std::vector<Finalize
     const apsu_b200_params &p = ctx.params;
     size_t off = add_desc(jobs.data(), jobs.size() * sizeof(FinalizeJob));
     uint32_t n = (uint32_t)jobs.size();
+    // the result slots this launch completes: apsu_b200_eval_all_stream delivers them as soon as its event fires
+    const size_t group = fin_groups_.size();
+    fin_groups_.emplace_back();
+    for (auto &j : jobs) fin_groups_.back().slots.push_back(j.slot);
+    std::sort(fin_groups_.back().slots.begin(), fin_groups_.back().slots.end());
     jobs.clear();
     // try_clear_irrelevant_bits (bin_bundle.cpp:67-97): the last level always has exactly one prime
     int keep = hm::bit_length(ctx.t) + ((int)ctx.logN + 1) - 1;
@@ -1381,6 +1430,7 @@ void Engine::emit_finalize(ProgramBuilder &pb, uint32_t Ls, std::vector<Finalize
             clear_mask, (int)ctx.N);
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;
+        if (fin_groups_[group].done) APSU_CUDA_CHECK(record_event(fin_groups_[group].done, ctx.stream));
     });
 }
 
@@ -1501,6 +1551,34 @@ void Engine::fetch_results(uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_
         if (bundle_idx) bundle_idx[k] = result_order_[k].first;
         if (cache_idx) cache_idx[k] = result_order_[k].second;
     }
+}
+
+// ProcessBinBundleCache for every BinBundle with delivery per BinBundle, as the reference hands every ResultPackage to
+// the channel the moment its BinBundle is done (receiver_ddh.cpp:527-534): each finalize launch of the evaluation
+// records an event; a second stream waits for it and copies that launch's result ciphertexts to the host; the calling
+// thread invokes `fn` for them as soon as the copy lands, while the device is still evaluating later chunks.
+void Engine::eval_all_stream(uint64_t *out, void (*fn)(void *, uint32_t, uint32_t, const uint64_t *), void *user)
+{
+    if (!out) throw std::invalid_argument("eval_all_stream: out is null");
+    if (!copy_stream_) APSU_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    eval_all();
+    const size_t per = (size_t)2 * ctx.N;
+    for (auto &g : fin_groups_) {
+        APSU_CUDA_CHECK(cudaStreamWaitEvent(copy_stream_, g.done, 0));
+        for (size_t a = 0; a < g.slots.size();) { // consecutive slots in one copy
+            size_t b = a + 1;
+            while (b < g.slots.size() && g.slots[b] == g.slots[b - 1] + 1) b++;
+            APSU_CUDA_CHECK(cudaMemcpyAsync(out + g.slots[a] * per, results_.p + g.slots[a] * per, (b - a) * per * 8, cudaMemcpyDeviceToHost, copy_stream_));
+            a = b;
+        }
+        APSU_CUDA_CHECK(cudaEventRecord(g.copied, copy_stream_));
+    }
+    for (auto &g : fin_groups_) {
+        APSU_CUDA_CHECK(cudaEventSynchronize(g.copied));
+        if (fn)
+            for (uint32_t slot : g.slots) fn(user, result_order_[slot].first, result_order_[slot].second, out + slot * per);
+    }
+    throw_if_query_invalid();
 }
 
 void Engine::results_device(void **ptr, uint64_t *bytes)

@@ -115,6 +115,12 @@ public:
     uint32_t powers_exchange_regions(uint32_t level, void **ptrs, uint64_t *chunk_bytes, uint32_t capacity);
     void eval_all();
     void fetch_results(uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
+    void eval_all_stream(uint64_t *out, void (*fn)(void *, uint32_t, uint32_t, const uint64_t *), void *user);
+    void set_eval_chunk(uint32_t n)
+    {
+        eval_chunk_ = n ? n : 32;
+        invalidate_plan();
+    }
     void get_power(uint32_t bundle_idx, uint32_t power, uint64_t *out, uint32_t *L, int *is_ntt);
     void results_device(void **ptr, uint64_t *bytes);
     void collect_timings();
@@ -188,6 +194,14 @@ private:
     std::vector<ProgGraph> powers_graphs_;
     ProgGraph eval_graph_;
     bool use_graphs_ = true;
+    uint32_t eval_chunk_ = 32; // BinBundles per Paterson-Stockmeyer chunk (= per result delivery of eval_all_stream)
+    struct FinGroup { // one finalize launch: the result slots it completes
+        std::vector<uint32_t> slots;
+        cudaEvent_t done = nullptr, copied = nullptr;
+    };
+    std::vector<FinGroup> fin_groups_;
+    cudaStream_t copy_stream_ = nullptr;
+    bool fuse_ = true; // element-wise producers fused into the transforms that consume them (ntt.cuh: NttFuse)
     void run_steps(std::vector<Step> &prog, size_t lo, size_t hi, ProgGraph &g);
     void drop_graphs();
     void invalidate_plan()

@@ -19,6 +19,72 @@ struct NttSrc {
     int reduce_input;        // reduce every input word modulo the target modulus first
 };
 
+// Fused prologues: the element-wise kernel that used to produce a transform's input runs inside the transform, on
+// the way into shared memory, so its output never makes the round trip through the arena and one launch of the
+// (launch-latency-bound) ComputePowers chain disappears per fusion:
+//   kNttExtend (forward):  polynomial p = (rp, j), j < L+S.  j < L: plain transform of source polynomial src_idx[rp]+j;
+//                          j >= L: BEHZ steps (1)-(2) for auxiliary prime j-L computed from the L source residues
+//                          (k_behz_extend, kernels.cuh), then transformed.
+//   kNttTensor (inverse):  polynomial p = (o, c, j), c < 3: component c of the tensor product of the extended
+//                          operands a_idx[o], b_idx[o] at modulus slot j (k_tensor), then inverse transform.
+//   kNttKsMac (inverse):   polynomial p = (o, comp, I): key-switch inner product over the L digits at modulus slot I
+//                          (k_ks_mac), then inverse transform.
+// value n of the fused input of polynomial p (see NttFuse); A = arena base
+template <int MODE>
+__device__ __forceinline__ u64 fused_input(const u64 *A, const NttSrc &src, const NttFuse &f, unsigned p, unsigned n, int N, const DMod &m)
+{
+    if (MODE == kNttExtend) {
+        const int L = f.L, LS = f.L + f.S;
+        const unsigned rp = p / LS, jb = p % LS - L;
+        const LevelConsts &c = *f.lc;
+        const u64 *x = A + (size_t)src.src_idx[rp] * N + n;
+        u64 tmp[kMaxQ];
+        u32 ymt = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxQ; i++) {
+            if (i < L) {
+                tmp[i] = mul_shoup(x[(size_t)i * N], c.mtilde_inv_punct_q[i], c.q[i].q);
+                ymt += (u32)tmp[i] * c.q_punct_mod_mtilde[i];
+            }
+        }
+        const u32 r = ymt * c.neg_inv_q_mod_mtilde; // arithmetic mod m_tilde = 2^32
+        u64 s = 0;
+        int pending = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxQ; i++) {
+            if (i < L) {
+                s += mul_shoup_lazy3(tmp[i], c.ext_punct_bsk[jb][i].op, c.ext_punct_bsk[jb][i].quot, 0 - m.q);
+                if (++pending == 2) s = reduce_8q(s, m.q), pending = 0;
+            }
+        }
+        u64 rr = r;
+        if (r >= 0x80000000u) rr += m.q - 0x100000000ull; // centred lift of r
+        s += mul_shoup_lazy3(rr, c.ext_q_bsk[jb].op, c.ext_q_bsk[jb].quot, 0 - m.q);
+        return reduce_8q(s, m.q);
+    } else if (MODE == kNttTensor) {
+        const int LS = f.L + f.S;
+        const unsigned j = p % LS, oc = p / LS, o = oc / 3, cc = oc % 3;
+        const size_t cs = (size_t)LS * N;
+        const u64 *a = A + ((size_t)f.a_idx[o] + j) * N + n;
+        const u64 *b = A + ((size_t)f.b_idx[o] + j) * N + n;
+        if (cc == 0) return mul_mod(a[0], b[0], m);
+        if (cc == 2) return mul_mod(a[cs], b[cs], m);
+        const u64 a0 = a[0], a1 = a[cs], b0 = b[0], b1 = b[cs];
+        Acc128 acc{ 0, 0 };
+        mac128(acc, a0, b1);
+        mac128(acc, a1, b0);
+        return barrett_prod(acc.lo, acc.hi, m); // 2 q^2 < 2^(64+sh)
+    } else {
+        const int L = f.L, R = f.L + 1;
+        const unsigned I = p % R, oc = p / R, o = oc >> 1, comp = oc & 1;
+        const unsigned key_index = I == (unsigned)L ? f.K - 1 : I;
+        const u64 *dg = A + ((size_t)f.a_idx[o] + I) * N + n;
+        Acc128 acc{ 0, 0 };
+        for (int J = 0; J < L; J++) mac128(acc, dg[(size_t)J * R * N], f.keys[(((size_t)J * 2 + comp) * f.K + key_index) * N + n]);
+        return barrett_prod(acc.lo, acc.hi, m); // <= 5 products of reduced operands
+    }
+}
+
 // Butterflies with the 3q-lazy Shoup product (modarith.cuh: mul_shoup_lazy3): forward values live in [0, 6q),
 // inverse values in [0, 3q); nq = 2^64 - q, q3 = 3q (q < 2^61.4, so 6q fits a word).
 template <int R>
@@ -143,8 +209,10 @@ constexpr int ntt_min_blocks(int logn, int div)
     const int threads = (1 << logn) / div, by_threads = threads >= 1024 ? 1 : 1024 / threads;
     return by_smem < by_threads ? by_smem : by_threads;
 }
-template <int LOGN, bool FWD, int DIV>
-__global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) ntt_kernel(const u64 *in, u64 *out, NttArgs a, NttSrc src)
+// in and out may alias (in-place transforms, gather/scatter inside one arena): each CTA reads its whole polynomial
+// before its first store and no CTA's destination is another CTA's source, so neither pointer is __restrict__.
+template <int LOGN, bool FWD, int DIV, int MODE = kNttPlain>
+__global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) ntt_kernel(const u64 *in, u64 *out, NttArgs a, NttSrc src, NttFuse fuse = NttFuse())
 {
     constexpr int N = 1 << LOGN;
     constexpr int RF = (LOGN % 3 == 0) ? 3 : (LOGN % 3 == 1 ? 4 : 2); // 13 = 4+3+3+3: one shared-memory round trip less than 1+3+3+3+3
@@ -155,15 +223,32 @@ __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) 
     const DMod m = a.mod[slot];
     const u64 q = m.q, nq = 0 - m.q, q3 = 3 * m.q;
     const ulonglong2 *tw = a.tw + ((size_t)a.table[slot] * 2 + (FWD ? 0 : 1)) * N;
-    const u64 *ip = in + (size_t)(src.src_idx ? src.src_idx[p] : p) * N;
     u64 *op = out + (size_t)(src.dst_idx ? src.dst_idx[p] : p) * N;
     const bool reduce = src.reduce_input != 0;
+    // fused prologue: the input is computed element by element into shared memory and the first pass runs from there
+    // (CTA-uniform choice: in kNttExtend the polynomials of the q primes take the plain path from their source)
+    bool from_smem = false;
+    const u64 *ip;
+    if (MODE == kNttExtend) {
+        const unsigned LS = fuse.L + fuse.S, rp = p / LS, j = p % LS;
+        ip = in + ((size_t)src.src_idx[rp] + j) * N; // only used when j < L
+        from_smem = j >= (unsigned)fuse.L;
+    } else {
+        ip = in + (size_t)((MODE == kNttPlain && src.src_idx) ? src.src_idx[p] : p) * N;
+        from_smem = MODE != kNttPlain;
+    }
+    if (MODE != kNttPlain && from_smem) {
+        for (unsigned n = threadIdx.x; n < (unsigned)N; n += blockDim.x) sm[pad_idx(n)] = fused_input<MODE>(in, src, fuse, p, n, N, m);
+        __syncthreads();
+    }
 
     if (FWD) {
         // stages [0, RF): global -> registers -> shared.  The trip count is a compile-time constant and the loads of
         // kBatch iterations are issued together: with a run-time loop every iteration waited a full memory latency
         // on its own two loads (long-scoreboard was the top stall of the forward transform)
-        {
+        if (MODE != kNttPlain && from_smem) {
+            smem_pass<LOGN, RF, true>(sm, tw, 0, nq, q3);
+        } else {
             constexpr unsigned stride = N >> RF;
             constexpr unsigned kThreads = N / DIV, kIters = (stride + kThreads - 1) / kThreads, kBatch = (RF == 1 && kIters % 4 == 0) ? 4 : 1;
             static_assert(kIters % kBatch == 0, "first-pass batching");
@@ -205,8 +290,9 @@ __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) 
             for (int k = 0; k < 4; k++) o2[k] = make_ulonglong2(x[2 * k], x[2 * k + 1]);
         }
     } else {
-        // stages [LOGN-3, LOGN) first: global -> registers -> shared
-        for (unsigned g = threadIdx.x; g < (N >> 3); g += blockDim.x) {
+        // stages [LOGN-3, LOGN) first: global -> registers -> shared (fused prologue: shared -> shared)
+        if (MODE != kNttPlain) smem_pass<LOGN, 3, false>(sm, tw, LOGN - 3, nq, q3);
+        for (unsigned g = threadIdx.x; MODE == kNttPlain && g < (N >> 3); g += blockDim.x) {
             u64 x[8];
             const ulonglong2 *i2 = reinterpret_cast<const ulonglong2 *>(ip + 8 * g);
 #pragma unroll

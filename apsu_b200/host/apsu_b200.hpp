@@ -15,13 +15,17 @@
 #pragma once
 #include "../../include/apsu_b200.h"
 #include <cstdint>
+#include <algorithm>
+#include <exception>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <set>
 #include <shared_mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -187,7 +191,11 @@ public:
     {
         detail::check(apsu_b200_ctx_create(&params_.c_params(), device, &ctx_));
     }
-    ~ReceiverDB() { apsu_b200_ctx_destroy(ctx_); }
+    ~ReceiverDB()
+    {
+        apsu_b200_ctx_destroy(ctx_);
+        for (auto &b : pinned_) apsu_b200_host_free(b.p);
+    }
     ReceiverDB(const ReceiverDB &) = delete;
     ReceiverDB &operator=(const ReceiverDB &) = delete;
 
@@ -265,11 +273,34 @@ public:
     }
     std::shared_lock<std::shared_mutex> get_reader_lock() const { return std::shared_lock<std::shared_mutex>(db_lock_); }
     apsu_b200_ctx *handle() const { return ctx_; }
+    // a context is thread-compatible, not thread-safe: callers of the query path serialise on THIS context's mutex
+    std::mutex &context_mutex() const { return ctx_mutex_; }
+    // pinned host staging owned by the DB and reused between queries (slot 0: query ciphertexts, slot 1: results)
+    std::uint64_t *pinned(int slot, std::size_t words) const
+    {
+        Pinned &b = pinned_[slot];
+        if (words > b.words) {
+            apsu_b200_host_free(b.p);
+            b.p = nullptr;
+            b.words = 0;
+            void *q = nullptr;
+            detail::check(apsu_b200_host_alloc(words * sizeof(std::uint64_t), &q));
+            b.p = static_cast<std::uint64_t *>(q);
+            b.words = words;
+        }
+        return b.p;
+    }
 
 private:
+    struct Pinned {
+        std::uint64_t *p = nullptr;
+        std::size_t words = 0;
+    };
     PSUParams params_;
     apsu_b200_ctx *ctx_ = nullptr;
     mutable std::shared_mutex db_lock_;
+    mutable std::mutex ctx_mutex_;
+    mutable Pinned pinned_[2];
 };
 
 // the already-extracted query: source power -> one ciphertext per bundle index (uint64_t[2][L][N]), relin keys
@@ -310,46 +341,173 @@ class Receiver {
 public:
     // The HE part of Receiver::RunQuery (receiver_ddh.cpp:139-369): `masks` is the dense
     // [alpha_max_cache_count][bundle_idx_count][N] table of coefficient-form random plaintexts
-    // (random_plain_list, indexed by pack_idx); send_rp_fun receives one ResultPackage per BinBundle.
+    // (random_plain_list, indexed by pack_idx), or empty to keep the masks ReceiverDB::generate_masks left on the
+    // device; send_rp_fun receives one ResultPackage per BinBundle AS ITS BinBundle FINISHES (the reference sends from
+    // the pool thread that evaluated it, receiver_ddh.cpp:527-534): chunk by chunk, while later chunks are evaluated.
     static void RunQuery(const Query &query, const std::vector<std::uint64_t> &masks,
                          const std::function<void(ResultPart)> &send_rp_fun)
     {
         if (!query) throw std::invalid_argument("query is invalid");
         auto db = query.receiver_db();
         auto lock = db->get_reader_lock();
-        static std::mutex ctx_mutex; // a context is thread-compatible; serialise
-        std::lock_guard<std::mutex> guard(ctx_mutex);
+        std::lock_guard<std::mutex> guard(db->context_mutex()); // a context is thread-compatible: serialise per context
         const PSUParams &p = db->get_params();
         const std::size_t N = p.seal_params().poly_modulus_degree;
         std::uint32_t L = 0;
         detail::check(apsu_b200_ctx_level(db->handle(), 0, &L));
         const std::size_t ct_words = 2 * static_cast<std::size_t>(L) * N, bic = p.bundle_idx_count();
+        const std::size_t n = db->get_bin_bundle_count();
+        // one copy of the ciphertexts, straight into pinned staging kept by the DB (uploads from pageable memory are staged)
+        std::uint64_t *cts = db->pinned(0, query.data().size() * bic * ct_words);
         std::vector<std::uint32_t> src;
-        std::vector<std::uint64_t> cts;
+        std::size_t at = 0;
         for (auto &kv : query.data()) {
             src.push_back(kv.first);
             for (auto &ct : kv.second) {
                 if (ct.size() != ct_words) throw std::invalid_argument("query ciphertext has the wrong size");
-                cts.insert(cts.end(), ct.begin(), ct.end());
+                std::copy(ct.begin(), ct.end(), cts + at);
+                at += ct_words;
             }
         }
-        const std::size_t n = db->get_bin_bundle_count();
         if (masks.size() % N) throw std::invalid_argument("mask table is not a multiple of poly_modulus_degree");
-        std::vector<std::uint64_t> out(n * 2 * N);
-        std::vector<std::uint32_t> bidx(n), cidx(n);
-        detail::check(apsu_b200_run_query(
-            db->handle(), src.data(), static_cast<std::uint32_t>(src.size()), cts.data(),
-            query.relin_keys().empty() ? nullptr : query.relin_keys().data(), masks.data(), static_cast<std::uint32_t>(masks.size() / N),
-            out.data(), bidx.data(), cidx.data()));
-        (void)bic;
-        for (std::size_t k = 0; k < n; k++) {
+        detail::check(apsu_b200_query_begin(db->handle(), src.data(), static_cast<std::uint32_t>(src.size()), cts));
+        detail::check(apsu_b200_set_relin_keys(db->handle(), query.relin_keys().empty() ? nullptr : query.relin_keys().data()));
+        if (!masks.empty()) detail::check(apsu_b200_set_masks(db->handle(), masks.data(), static_cast<std::uint32_t>(masks.size() / N)));
+        detail::check(apsu_b200_compute_powers(db->handle()));
+        std::uint64_t *out = db->pinned(1, n * 2 * N);
+        struct Sink {
+            const std::function<void(ResultPart)> *send;
+            std::size_t words;
+        } sink{ &send_rp_fun, 2 * N };
+        detail::check(apsu_b200_eval_all_stream(
+            db->handle(), out,
+            [](void *user, std::uint32_t bundle_idx, std::uint32_t cache_idx, const std::uint64_t *ct) {
+                auto *sk = static_cast<Sink *>(user);
+                auto rp = std::make_unique<network::ResultPackage>();
+                rp->bundle_idx = bundle_idx;
+                rp->cache_idx = cache_idx;
+                rp->psu_result.assign(ct, ct + sk->words);
+                (*sk->send)(std::move(rp));
+            },
+            &sink));
+    }
+};
+
+// BinBundles sharded over the GPUs of one box: one ReceiverDB (context) per GPU, one host thread per
+// GPU inside the calls, all exchanges inside the library (apsu_b200_mgpu_*, NCCL).  The unit that is distributed is the
+// unit the reference hands to its thread pool: the BinBundle (receiver_ddh.cpp:340-364).
+class MultiGpuReceiver {
+public:
+    MultiGpuReceiver(const PSUParams &params, const std::vector<int> &devices)
+    {
+        if (devices.empty()) throw std::invalid_argument("no devices");
+        for (int d : devices) dbs_.push_back(std::make_shared<ReceiverDB>(params, d));
+        gidx_.resize(devices.size());
+        next_cache_.assign(params.bundle_idx_count(), 0);
+    }
+    ~MultiGpuReceiver()
+    {
+        for (auto m : mg_) apsu_b200_mgpu_destroy(m);
+    }
+    std::size_t world() const { return dbs_.size(); }
+    std::shared_ptr<ReceiverDB> db(std::size_t rank) const { return dbs_.at(rank); }
+    // appends a BinBundle to bundle index `bundle_idx` of the whole DB, stored on GPU `rank`; returns its cache index
+    std::uint32_t add_bin_bundle(std::size_t rank, std::uint32_t bundle_idx, const BinBundleCache &cache)
+    {
+        dbs_.at(rank)->add_bin_bundle(bundle_idx, cache);
+        return note(rank, bundle_idx);
+    }
+    std::uint32_t add_bin_bundle_synthetic(std::size_t rank, std::uint32_t bundle_idx, std::uint32_t ncoeffs, std::uint64_t seed)
+    {
+        dbs_.at(rank)->add_bin_bundle_synthetic(bundle_idx, ncoeffs, seed);
+        return note(rank, bundle_idx);
+    }
+    // collective set-up after the DB is loaded (and after every change): dag_split as in apsu_b200_mgpu_commit
+    void commit(int dag_split = -1)
+    {
+        if (mg_.empty()) {
+            std::uint8_t id[APSU_B200_MGPU_ID_BYTES];
+            detail::check(apsu_b200_mgpu_unique_id(id));
+            mg_.assign(world(), nullptr);
+            each_rank([&](std::size_t r) { detail::check(apsu_b200_mgpu_create(dbs_[r]->handle(), id, (std::uint32_t)r, (std::uint32_t)world(), &mg_[r])); });
+        }
+        each_rank([&](std::size_t r) {
+            std::vector<std::uint32_t> g;
+            for (auto &kv : gidx_[r]) g.insert(g.end(), kv.second.begin(), kv.second.end()); // bundle_idx major, insertion order
+            detail::check(apsu_b200_mgpu_commit(mg_[r], g.empty() ? nullptr : g.data(), dag_split));
+        });
+    }
+    // RunQuery over all GPUs: `query` was built against db(0); masks[r] = rank r's dense mask table for ITS local cache
+    // indices (empty: keep the masks generated on that GPU).  One ResultPackage per BinBundle of the whole DB.
+    void RunQuery(const Query &query, const std::vector<std::vector<std::uint64_t>> &masks, const std::function<void(ResultPart)> &send_rp_fun)
+    {
+        if (!query) throw std::invalid_argument("query is invalid");
+        if (mg_.empty()) throw std::logic_error("MultiGpuReceiver::commit has not been called");
+        const PSUParams &p = dbs_[0]->get_params();
+        const std::size_t N = p.seal_params().poly_modulus_degree, bic = p.bundle_idx_count();
+        std::uint32_t L = 0, total = 0;
+        detail::check(apsu_b200_ctx_level(dbs_[0]->handle(), 0, &L));
+        detail::check(apsu_b200_mgpu_info(mg_[0], &total, nullptr, nullptr));
+        const std::size_t ct_words = 2 * static_cast<std::size_t>(L) * N;
+        std::uint64_t *cts = dbs_[0]->pinned(0, query.data().size() * bic * ct_words);
+        std::vector<std::uint32_t> src;
+        std::size_t at = 0;
+        for (auto &kv : query.data()) {
+            src.push_back(kv.first);
+            for (auto &ct : kv.second) {
+                if (ct.size() != ct_words) throw std::invalid_argument("query ciphertext has the wrong size");
+                std::copy(ct.begin(), ct.end(), cts + at);
+                at += ct_words;
+            }
+        }
+        std::uint64_t *out = dbs_[0]->pinned(1, static_cast<std::size_t>(total) * 2 * N);
+        std::vector<std::uint32_t> bidx(total), cidx(total);
+        each_rank([&](std::size_t r) {
+            const bool root = r == 0;
+            const std::vector<std::uint64_t> *m = r < masks.size() && !masks[r].empty() ? &masks[r] : nullptr;
+            detail::check(apsu_b200_mgpu_run_query(
+                mg_[r], src.data(), static_cast<std::uint32_t>(src.size()), root ? cts : nullptr,
+                root && !query.relin_keys().empty() ? query.relin_keys().data() : nullptr, m ? m->data() : nullptr,
+                m ? static_cast<std::uint32_t>(m->size() / N) : 0, root ? out : nullptr, root ? bidx.data() : nullptr, root ? cidx.data() : nullptr));
+        });
+        for (std::uint32_t k = 0; k < total; k++) {
             auto rp = std::make_unique<network::ResultPackage>();
             rp->bundle_idx = bidx[k];
             rp->cache_idx = cidx[k];
-            rp->psu_result.assign(out.begin() + k * 2 * N, out.begin() + (k + 1) * 2 * N);
+            rp->psu_result.assign(out + static_cast<std::size_t>(k) * 2 * N, out + static_cast<std::size_t>(k + 1) * 2 * N);
             send_rp_fun(std::move(rp));
         }
     }
+
+private:
+    std::uint32_t note(std::size_t rank, std::uint32_t bundle_idx)
+    {
+        const std::uint32_t g = next_cache_.at(bundle_idx)++;
+        gidx_[rank][bundle_idx].push_back(g);
+        return g;
+    }
+    // the collective calls block until every rank has entered them: one host thread per GPU
+    template <typename F>
+    void each_rank(F &&f)
+    {
+        std::vector<std::thread> th;
+        std::vector<std::exception_ptr> err(world());
+        for (std::size_t r = 0; r < world(); r++)
+            th.emplace_back([&, r] {
+                try {
+                    f(r);
+                } catch (...) {
+                    err[r] = std::current_exception();
+                }
+            });
+        for (auto &t : th) t.join();
+        for (auto &e : err)
+            if (e) std::rethrow_exception(e);
+    }
+    std::vector<std::shared_ptr<ReceiverDB>> dbs_;
+    std::vector<apsu_b200_mgpu *> mg_;
+    std::vector<std::map<std::uint32_t, std::vector<std::uint32_t>>> gidx_; // [rank][bundle_idx] -> global cache indices
+    std::vector<std::uint32_t> next_cache_;
 };
 
 } // namespace receiver

@@ -296,6 +296,32 @@ class Receiver:
     def ProcessBinBundleCaches(self):
         capi.check(self._L.apsu_b200_eval_all(self.db._h))
 
+    def set_eval_chunk(self, bin_bundles: int):
+        """BinBundles per Paterson-Stockmeyer chunk = per delivery of ProcessBinBundleCachesStreamed (rebuilds the plan:
+        call it before loading a query)."""
+        capi.check(self._L.apsu_b200_ctx_set_eval_chunk(self.db._h, bin_bundles))
+
+    def ProcessBinBundleCachesStreamed(self, on_result=None):
+        """ProcessBinBundleCache for every BinBundle with per-BinBundle delivery (send_rp_fun, receiver_ddh.cpp:527-534):
+        on_result(ResultPackage) is called as each BinBundle's ciphertext reaches the host, while later chunks are still
+        evaluated.  Returns the ResultPackages in delivery order."""
+        n = self.db.get_bin_bundle_count()
+        N = self.db.params.poly_modulus_degree()
+        out = np.zeros((max(n, 1), 2, N), dtype=np.uint64)
+        delivered = []
+        FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64))
+
+        def cb(_user, b, c, ct):
+            arr = np.ctypeslib.as_array(ct, shape=(2, 1, N)).copy()
+            rp = ResultPackage(int(b), int(c), arr)
+            delivered.append(rp)
+            if on_result is not None:
+                on_result(rp)
+
+        fn = FN(cb)
+        capi.check(self._L.apsu_b200_eval_all_stream(self.db._h, capi.ptr(out), C.cast(fn, C.c_void_p), None))
+        return delivered
+
     def get_power(self, bundle_idx: int, power: int):
         L, ntt = C.c_uint32(), C.c_int()
         capi.check(self._L.apsu_b200_get_power(self.db._h, bundle_idx, power, None, C.byref(L), C.byref(ntt)))

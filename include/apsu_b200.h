@@ -209,6 +209,16 @@ int apsu_b200_set_relin_keys_seeded(apsu_b200_ctx *ctx, const uint64_t *c0, cons
  * BatchedPlaintextPolyn::eval / eval_patstock (bin_bundle.cpp:106-174, 192-360).  Results stay on the
  * device until fetched.  Order of results: bundle_idx major, cache_idx minor. */
 int apsu_b200_eval_all(apsu_b200_ctx *ctx);
+/* The same with delivery PER BinBundle, as the reference hands each ResultPackage to the channel the moment its
+ * BinBundle is done (send_rp_fun, receiver_ddh.cpp:527-534): the result ciphertexts are copied to `out`
+ * (uint64_t[total_bin_bundle_count][2][N], result order; pinned memory recommended) chunk by chunk while later chunks
+ * are still being evaluated, and `fn(user, bundle_idx, cache_idx, ct)` is called on the calling thread for every
+ * BinBundle as soon as its ciphertext is on the host.  A chunk is what one finalize launch completes: all directly
+ * evaluated BinBundles first, then the Paterson-Stockmeyer ones apsu_b200_ctx_set_eval_chunk at a time (default 32:
+ * larger chunks are faster in total, smaller ones deliver earlier). */
+typedef void (*apsu_b200_result_fn)(void *user, uint32_t bundle_idx, uint32_t cache_idx, const uint64_t *ct);
+int apsu_b200_eval_all_stream(apsu_b200_ctx *ctx, uint64_t *out, apsu_b200_result_fn fn, void *user);
+int apsu_b200_ctx_set_eval_chunk(apsu_b200_ctx *ctx, uint32_t bin_bundles);
 /* rp->psu_result for every BinBundle: out = uint64_t[total_bin_bundle_count][2][N] (one prime), plus
  * the ResultPackage bundle_idx / cache_idx fields (network/result_package.h:44-62). Either index
  * array may be NULL. */

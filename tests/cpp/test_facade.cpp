@@ -1,6 +1,8 @@
 // C++ facade test.  `test_facade host <json>`: parameter loading, PowersDag, error mapping (no GPU needed).
 // `test_facade gpu <json> <ncoeffs> <seed>`: synthetic DB + synthetic query through Receiver::RunQuery; prints
 // an FNV-1a checksum per BinBundle result so that the Python test can compare it with the C-ABI path.
+// `test_facade mgpu <json> <ncoeffs> <seed> <world>`: the same DB spread over `world` GPUs (bundle index b on GPU
+// b % world) through MultiGpuReceiver (apsu_b200_mgpu_*, NCCL): must print the same lines.
 #include "../../apsu_b200/host/apsu_b200.hpp"
 #include <cstdio>
 #include <cstdlib>
@@ -66,11 +68,23 @@ int main(int argc, char **argv)
         std::printf("exceptions=%d\n", caught);
         return caught == 7 ? 0 : 1;
     }
-    // gpu mode
+    // gpu / mgpu mode
     uint32_t ncoeffs = (uint32_t)std::atoi(argv[3]);
     uint64_t seed = std::strtoull(argv[4], nullptr, 10);
-    auto db = std::make_shared<apsu::receiver::ReceiverDB>(params, 0);
-    for (uint32_t b = 0; b < params.bundle_idx_count(); b++) db->add_bin_bundle_synthetic(b, ncoeffs, seed + b);
+    const size_t world = mode == "mgpu" ? (size_t)std::atoi(argv[5]) : 1;
+    std::unique_ptr<apsu::receiver::MultiGpuReceiver> mg;
+    std::shared_ptr<apsu::receiver::ReceiverDB> db;
+    if (mode == "mgpu") {
+        std::vector<int> devices;
+        for (size_t r = 0; r < world; r++) devices.push_back((int)r);
+        mg = std::make_unique<apsu::receiver::MultiGpuReceiver>(params, devices);
+        for (uint32_t b = 0; b < params.bundle_idx_count(); b++) mg->add_bin_bundle_synthetic(b % world, b, ncoeffs, seed + b);
+        mg->commit();
+        db = mg->db(0);
+    } else {
+        db = std::make_shared<apsu::receiver::ReceiverDB>(params, 0);
+        for (uint32_t b = 0; b < params.bundle_idx_count(); b++) db->add_bin_bundle_synthetic(b, ncoeffs, seed + b);
+    }
     auto sp = params.seal_params();
     size_t N = sp.poly_modulus_degree, K = sp.coeff_modulus.size(), L = K > 1 ? K - 1 : 1;
     uint64_t s = seed;
@@ -94,9 +108,13 @@ int main(int argc, char **argv)
     for (auto &m : masks) m = splitmix(s) % sp.plain_modulus;
     apsu::receiver::Query query(db, std::move(data), std::move(relin));
     if (!query) return 1;
-    apsu::receiver::Receiver::RunQuery(query, masks, [&](apsu::receiver::ResultPart rp) {
+    auto print = [&](apsu::receiver::ResultPart rp) {
         std::printf("bundle_idx=%u cache_idx=%u fnv=%016llx\n", rp->bundle_idx, rp->cache_idx,
                     (unsigned long long)fnv(rp->psu_result.data(), rp->psu_result.size()));
-    });
+    };
+    if (mg)
+        mg->RunQuery(query, std::vector<std::vector<uint64_t>>(world, masks), print); // every bundle index has one BinBundle: local cache 0 everywhere
+    else
+        apsu::receiver::Receiver::RunQuery(query, masks, print);
     return 0;
 }

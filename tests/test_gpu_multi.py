@@ -74,3 +74,25 @@ def test_two_gpu_query_matches_oracle(name, degrees, dag_split, expect_group):
     assert set(got) == set(exp)
     for key in exp:
         assert np.array_equal(got[key], exp[key]), key
+
+
+def test_cpp_multi_gpu_facade_matches_single_gpu(tmp_path):
+    """apsu::receiver::MultiGpuReceiver (C++ facade, one host thread per GPU over apsu_b200_mgpu_*) returns the same
+    ResultPackages as apsu::receiver::Receiver on one GPU."""
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    import json
+    import pathlib
+    import subprocess
+    root = pathlib.Path(__file__).resolve().parent.parent
+    exe = tmp_path / "test_facade"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-o", str(exe), str(root / "tests" / "cpp" / "test_facade.cpp"),
+                           f"-L{root / 'apsu_b200'}", "-lapsu_b200", f"-Wl,-rpath,{root / 'apsu_b200'}"])
+    table = json.loads((root / "tests" / "golden" / "parameters.json").read_text())
+    pj = tmp_path / "p.json"
+    pj.write_text(json.dumps(table["1M-4096-com.json"]))
+    one = subprocess.check_output([str(exe), "gpu", str(pj), "40", "99"], text=True)
+    two = subprocess.check_output([str(exe), "mgpu", str(pj), "40", "99", "2"], text=True)
+    a = sorted(l for l in one.splitlines() if l.startswith("bundle_idx="))
+    b = sorted(l for l in two.splitlines() if l.startswith("bundle_idx="))
+    assert len(a) == 5 and a == b

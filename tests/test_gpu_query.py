@@ -418,7 +418,7 @@ def test_cpp_facade_on_gpu(tmp_path):
     import apsu_b200
     root = pathlib.Path(__file__).resolve().parent.parent
     exe = tmp_path / "test_facade"
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", str(exe), str(root / "tests" / "cpp" / "test_facade.cpp"),
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-o", str(exe), str(root / "tests" / "cpp" / "test_facade.cpp"),
                            f"-L{root / 'apsu_b200'}", "-lapsu_b200", f"-Wl,-rpath,{root / 'apsu_b200'}"])
     table = json.loads((root / "tests" / "golden" / "parameters.json").read_text())
     pj = tmp_path / "p.json"
@@ -461,5 +461,36 @@ def test_cpp_facade_on_gpu(tmp_path):
             return h
         exp = {f"bundle_idx={r.bundle_idx} cache_idx={r.cache_idx} fnv={fnv(r.psu_result):016x}" for r in res}
         assert set(lines) == exp
+    finally:
+        db.close()
+
+
+def test_results_are_delivered_per_binbundle():
+    """apsu_b200_eval_all_stream: one delivery per BinBundle, chunk by chunk (direct BinBundles first, then the
+    Paterson-Stockmeyer ones two at a time), every ciphertext identical to the batch call's."""
+    import apsu_b200
+    degrees = [[30, 9, 25, 7, 22], [20], [], [12, 15], [18]]  # 1M-4096-com: ps_low = 8, so degree <= 8 evaluates directly
+    sc = Scenario("1M-4096-com", degrees, planted=4)
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0)
+    try:
+        _upload(sc, db)
+        rx = apsu_b200.Receiver(db)
+        rx.load_query(apsu_b200.Query(sc.src_powers, sc.cts, sc.relin))
+        rx.set_masks(sc.masks)
+        rx.ComputePowers()
+        rx.ProcessBinBundleCaches()
+        want = {(r.bundle_idx, r.cache_idx): r.psu_result.copy() for r in rx.results()}
+        seen = []
+        rx.set_eval_chunk(2)
+        rx.load_query(apsu_b200.Query(sc.src_powers, sc.cts, sc.relin))
+        rx.ComputePowers()
+        got = rx.ProcessBinBundleCachesStreamed(on_result=lambda rp: seen.append((rp.bundle_idx, rp.cache_idx)))
+        assert len(got) == len(want) == 9 and len(set(seen)) == 9
+        assert seen[0] == (0, 3)  # the only directly evaluated BinBundle (degree 7) is delivered first
+        for rp in got:
+            assert np.array_equal(rp.psu_result, want[(rp.bundle_idx, rp.cache_idx)]), (rp.bundle_idx, rp.cache_idx)
+        exp = {(b, c): ct for b, c, ct in sc.db.run_query(sc.src_powers, sc.cts, sc.relin, sc.masks, threads=4).results()}
+        for rp in got:
+            assert np.array_equal(rp.psu_result.reshape(2, -1), exp[(rp.bundle_idx, rp.cache_idx)])
     finally:
         db.close()

@@ -129,7 +129,7 @@ def test_product_never_imports_the_oracle():
 
 def test_cpp_facade_host_side(tmp_path):
     exe = tmp_path / "test_facade"
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", str(exe), str(ROOT / "tests" / "cpp" / "test_facade.cpp"),
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-o", str(exe), str(ROOT / "tests" / "cpp" / "test_facade.cpp"),
                            f"-L{ROOT / 'apsu_b200'}", "-lapsu_b200", f"-Wl,-rpath,{ROOT / 'apsu_b200'}"])
     pj = tmp_path / "p.json"
     pj.write_text(json.dumps(TABLE["16M-4096.json"]))
