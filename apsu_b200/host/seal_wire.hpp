@@ -416,14 +416,19 @@ public:
         const std::uint32_t v = (std::uint32_t)(target - slot);
         for (int b = 0; b < 4; b++) o_[slot + (std::size_t)b] = (std::uint8_t)(v >> (8 * b));
     }
-    // table whose fields are all 4 bytes wide: values[i] is written verbatim; returns (table position, slot positions)
-    std::pair<std::size_t, std::vector<std::size_t>> table(const std::vector<std::uint32_t> &values)
+    // table whose fields are all 4 bytes wide: values[i] is written verbatim; fields listed in `absent` get a zero
+    // vtable entry (the reader then sees them as not present); returns (table position, slot positions)
+    std::pair<std::size_t, std::vector<std::size_t>> table(const std::vector<std::uint32_t> &values, const std::vector<int> &absent = {})
     {
         align4();
         const std::size_t vt = o_.size(), nf = values.size();
         put(o_, 4 + 2 * nf, 2);
         put(o_, 4 + 4 * nf, 2);
-        for (std::size_t i = 0; i < nf; i++) put(o_, 4 + 4 * i, 2);
+        for (std::size_t i = 0; i < nf; i++) {
+            bool gone = false;
+            for (int a : absent) gone |= (std::size_t)a == i;
+            put(o_, gone ? 0 : 4 + 4 * i, 2);
+        }
         align4();
         const std::size_t tab = o_.size();
         put(o_, (std::uint32_t)(tab - vt), 4);
@@ -445,12 +450,12 @@ public:
         for (std::size_t i = 0; i < n; i++) slots.push_back(u32(0));
         return at;
     }
-    bytes finish_size_prefixed(std::size_t root_slot_target)
+    bytes finish_size_prefixed(std::size_t root_table)
     {
-        // the first 8 bytes were reserved by begin(): size prefix + root offset
+        // the first 8 bytes were reserved by begin(): size prefix + root uoffset (relative to its own position, byte 4)
         const std::uint32_t total = (std::uint32_t)(o_.size() - 4);
         for (int b = 0; b < 4; b++) o_[(std::size_t)b] = (std::uint8_t)(total >> (8 * b));
-        patch_offset(4, root_slot_target);
+        patch_offset(4, root_table);
         return o_;
     }
     void begin()
@@ -479,7 +484,7 @@ inline bytes write_result_package(std::uint32_t bundle_idx, std::uint32_t cache_
     std::vector<std::size_t> none;
     const std::size_t labels = w.offset_vector(0, none);
     w.patch_offset(rp.second[5], labels);
-    return w.finish_size_prefixed(rp.first + 4); // root uoffset is relative to its own position (byte 4)
+    return w.finish_size_prefixed(rp.first);
 }
 struct ResultPackage {
     std::uint32_t bundle_idx = 0, cache_idx = 0, label_byte_count = 0, nonce_byte_count = 0;
@@ -506,7 +511,7 @@ inline bytes write_query_request(std::uint8_t compression_type, const bytes &rel
     FbWriter w;
     w.begin();
     auto rop = w.table({ 3 /*request_type = QueryRequest (ubyte in a 4-byte slot)*/, 0 /*request*/ });
-    auto req = w.table({ compression_type, 0 /*relin_keys*/, 0 /*query*/ });
+    auto req = w.table({ compression_type, 0 /*relin_keys*/, 0 /*query*/ }, relin_keys.empty() ? std::vector<int>{ 1 } : std::vector<int>{});
     w.patch_offset(rop.second[1], req.first);
     if (!relin_keys.empty()) w.patch_offset(req.second[1], w.byte_vector(relin_keys.data(), relin_keys.size()));
     std::vector<std::size_t> part_slots;
@@ -522,7 +527,7 @@ inline bytes write_query_request(std::uint8_t compression_type, const bytes &rel
             w.patch_offset(ct.second[0], w.byte_vector(parts[i].second[k].data(), parts[i].second[k].size()));
         }
     }
-    return w.finish_size_prefixed(rop.first + 4);
+    return w.finish_size_prefixed(rop.first);
 }
 
 } // namespace wire

@@ -204,3 +204,19 @@ def test_sharded_exchange_on_gloo(tmp_path):
                                    "--master-addr", "127.0.0.1", "--master-port", "29517", str(script), str(ROOT)],
                                   env=env, text=True, stderr=subprocess.STDOUT, timeout=300)
     assert "OK" in out and "OK2" in out
+
+
+def test_seal_wire_formats(tmp_path):
+    """Row f2 (apsu_b200/host/seal_wire.hpp): SEAL object framing (expanded and seeded ciphertexts), the FlatBuffers
+    envelopes of QueryRequest and ResultPackage round-tripped through reader and writer, error paths, and parms_id =
+    BLAKE2b-256 of the parameter words against hashlib.  The byte layouts are SEAL-3.7 recall (the header says so)."""
+    import hashlib
+    import struct
+    exe = tmp_path / "test_wire"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-o", str(exe), str(ROOT / "tests" / "cpp" / "test_wire.cpp")])
+    out = subprocess.check_output([str(exe)], text=True)
+    assert "ok=1" in out
+    words = [1, 8192, 0xfffffffff70001, 0xfffffffff78001, 0xfffffffffb4001, 0x3ffffffffc001, 4079617]
+    d = hashlib.blake2b(struct.pack("<7Q", *words), digest_size=32).digest()
+    assert "parms_id=" + ",".join("%016x" % x for x in struct.unpack("<4Q", d)) in out
+    assert f"ct_bytes={16 + 32 + 1 + 5 * 8 + 16 + 8 + 2 * 3 * 64 * 8}" in out
