@@ -90,6 +90,8 @@ SIGNATURES = {
     "apsu_b200_db_add_binbundle": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), C.c_uint32, C.POINTER(C.c_uint32)]),
     "apsu_b200_db_add_binbundle_synthetic": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32)]),
     "apsu_b200_db_add_binbundle_from_bins": (C.c_int, [vp, C.c_uint32, u32p, u64p, C.POINTER(C.c_uint32)]),
+    "apsu_b200_db_set_data": (C.c_int, [vp, vp, vp, C.c_uint64, vp]),
+    "apsu_b200_db_set_data_device": (C.c_int, [vp, vp, vp, C.c_uint64, vp]),
     "apsu_b200_db_bin_bundle_count": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
     "apsu_b200_db_total_bin_bundle_count": (C.c_int, [vp, C.POINTER(C.c_uint32)]),
     "apsu_b200_db_binbundle_ncoeffs": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),

@@ -194,6 +194,14 @@ int apsu_b200_db_add_binbundle_from_bins(apsu_b200_ctx *ctx, uint32_t bundle_idx
         if (cache_idx) *cache_idx = ci;
     });
 }
+int apsu_b200_db_set_data(apsu_b200_ctx *ctx, const uint64_t *felts, const uint64_t *cuckoo_idx, uint64_t n_items, uint32_t *bundle_counts)
+{
+    return guarded([&] { E(ctx).set_data(felts, cuckoo_idx, (size_t)n_items, false, bundle_counts); });
+}
+int apsu_b200_db_set_data_device(apsu_b200_ctx *ctx, const void *felts_device, const void *cuckoo_idx_device, uint64_t n_items, uint32_t *bundle_counts)
+{
+    return guarded([&] { E(ctx).set_data((const uint64_t *)felts_device, (const uint64_t *)cuckoo_idx_device, (size_t)n_items, true, bundle_counts); });
+}
 int apsu_b200_db_bin_bundle_count(const apsu_b200_ctx *ctx, uint32_t bundle_idx, uint32_t *count)
 {
     return guarded([&] {

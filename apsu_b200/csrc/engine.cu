@@ -343,8 +343,7 @@ void Engine::prepare_plain_high(BinBundleStore &s)
     if (!ctx.params.ps_low_degree || s.n_plain <= 1) return;
     uint32_t cnt = s.n_plain - 1;
     s.plain_high_ntt.alloc((size_t)cnt * Lh * N);
-    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream)); // the staging buffer may still feed an earlier pack
-    stage_.ensure((size_t)cnt * Lh * N);
+    stage_.ensure((size_t)cnt * Lh * N); // reuse is ordered by the stream; a reallocation (cudaFree) synchronises by itself
     k_plain_lift<<<dim3(N / kEwThreads, Lh, cnt), kEwThreads, 0, ctx.stream>>>(s.plain_coeffs.p + N, stage_.p, ctx.level[Lh], ctx.t, (int)N);
     APSU_LAUNCH_CHECK();
     ctx.ntt(stage_.p, stage_.p, cnt * Lh, ctx.pattern_q(Lh), false);
@@ -432,7 +431,7 @@ uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bi
 {
     if (bundle_idx >= db.size()) throw std::invalid_argument("bundle_idx is out of range");
     const apsu_b200_params &p = ctx.params;
-    const uint32_t N = ctx.N, Ll = ctx.low_L, nbins = p.bins_per_bundle;
+    const uint32_t nbins = p.bins_per_bundle;
     std::vector<uint32_t> first(nbins);
     uint32_t max_deg = 0;
     size_t total = 0;
@@ -444,6 +443,38 @@ uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bi
         if (bin_sizes[b] >= p.max_items_per_bin) throw std::invalid_argument("a bin holds max_items_per_bin or more items");
     }
     if (total >= (1ull << 32)) throw std::invalid_argument("too many items in one BinBundle");
+    // scratch of the build is kept between calls (a DB build is dozens of BinBundles of the same shape)
+    build_first_.upload(first, ctx.stream);
+    build_size_.ensure(nbins);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(build_size_.p, bin_sizes, nbins * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx.stream));
+    build_roots_.ensure(std::max<size_t>(total, 1));
+    if (total) APSU_CUDA_CHECK(cudaMemcpyAsync(build_roots_.p, roots, total * 8, cudaMemcpyHostToDevice, ctx.stream));
+    const uint32_t ci = add_binbundle_from_bins_device(bundle_idx, build_first_.p, build_size_.p, build_roots_.p, max_deg);
+    throw_if_build_invalid(); // synchronises
+    return ci;
+}
+
+void Engine::throw_if_build_invalid()
+{
+    int bad = 0;
+    build_bad_.ensure(1);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(&bad, build_bad_.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    if (bad) {
+        APSU_CUDA_CHECK(cudaMemsetAsync(build_bad_.p, 0, sizeof(int), ctx.stream));
+        throw std::invalid_argument("bin item is not a field element (>= plain_modulus)");
+    }
+}
+
+// The device part of the build: bins already on the device (first / size per bin, roots concatenated), max_deg =
+// the largest bin.  Asynchronous on the context stream: no host synchronisation (a non-field-element root is
+// recorded in build_bad_ and reported by throw_if_build_invalid).
+uint32_t Engine::add_binbundle_from_bins_device(uint32_t bundle_idx, const uint32_t *d_first, const uint32_t *d_size, const u64 *d_roots, uint32_t max_deg)
+{
+    if (bundle_idx >= db.size()) throw std::invalid_argument("bundle_idx is out of range");
+    const apsu_b200_params &p = ctx.params;
+    const uint32_t N = ctx.N, Ll = ctx.low_L, nbins = p.bins_per_bundle;
+    if (max_deg >= p.max_items_per_bin) throw std::invalid_argument("a bin holds max_items_per_bin or more items");
     const uint32_t ncoeffs = max_deg + 1;
 
     auto s = std::make_unique<BinBundleStore>();
@@ -457,18 +488,11 @@ uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bi
     s->ntt_coeffs.alloc((size_t)s->n_ntt * Ll * N);
     s->plain_coeffs.alloc((size_t)s->n_plain * N);
 
-    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
-    // scratch of the build is kept between calls (a DB build is dozens of BinBundles of the same shape)
-    DBuf<uint32_t> &d_first = build_first_, &d_size = build_size_, &d_rows = build_rows_;
-    DBuf<u64> &d_roots = build_roots_, &M = build_M_, &enc = build_enc_;
-    DBuf<int> &d_bad = build_bad_;
-    d_bad.ensure(1);
-    APSU_CUDA_CHECK(cudaMemsetAsync(d_bad.p, 0, sizeof(int), ctx.stream));
-    d_first.upload(first, ctx.stream);
-    d_size.ensure(nbins);
-    APSU_CUDA_CHECK(cudaMemcpyAsync(d_size.p, bin_sizes, nbins * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx.stream));
-    d_roots.ensure(std::max<size_t>(total, 1));
-    if (total) APSU_CUDA_CHECK(cudaMemcpyAsync(d_roots.p, roots, total * 8, cudaMemcpyHostToDevice, ctx.stream));
+    DBuf<u64> &M = build_M_, &enc = build_enc_;
+    if (!build_bad_.p) {
+        build_bad_.alloc(1);
+        APSU_CUDA_CHECK(cudaMemsetAsync(build_bad_.p, 0, sizeof(int), ctx.stream));
+    }
     M.ensure((size_t)ncoeffs * N);
     enc.ensure((size_t)ncoeffs * N);
     APSU_CUDA_CHECK(cudaMemsetAsync(M.p, 0, (size_t)ncoeffs * N * 8, ctx.stream));
@@ -480,7 +504,7 @@ uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bi
         if (ctx.t < (1ull << 30) && need_regs <= 64) {
             const int warps = 8;
             const unsigned grid = (nbins + warps - 1) / warps;
-            auto launch = [&](auto kern) { kern<<<grid, warps * 32, 0, ctx.stream>>>(d_first.p, d_size.p, d_roots.p, M.p, nbins, (u32)ctx.t, (int)N, d_bad.p); };
+            auto launch = [&](auto kern) { kern<<<grid, warps * 32, 0, ctx.stream>>>(d_first, d_size, d_roots, M.p, nbins, (u32)ctx.t, (int)N, build_bad_.p); };
             if (need_regs <= 4) launch(k_polyn_with_roots_reg<4>);
             else if (need_regs <= 8) launch(k_polyn_with_roots_reg<8>);
             else if (need_regs <= 16) launch(k_polyn_with_roots_reg<16>);
@@ -495,31 +519,28 @@ uint32_t Engine::add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bi
             const bool small = ctx.t < (1ull << 32);
             auto kern = small ? k_polyn_with_roots<true> : k_polyn_with_roots<false>;
             APSU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(nbins + warps - 1) / warps, warps * 32, smem, ctx.stream>>>(d_first.p, d_size.p, d_roots.p, M.p, nbins, max_deg, mt, (int)N, d_bad.p);
+            kern<<<(nbins + warps - 1) / warps, warps * 32, smem, ctx.stream>>>(d_first, d_size, d_roots, M.p, nbins, max_deg, mt, (int)N, build_bad_.p);
         }
         APSU_LAUNCH_CHECK();
-        int bad = 0;
-        APSU_CUDA_CHECK(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
-        APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
-        if (bad) throw std::invalid_argument("bin item is not a field element (>= plain_modulus)");
     }
     // BatchEncoder::encode: slot permutation + inverse NTT modulo t
     k_slot_scatter<<<dim3(N / 256, ncoeffs), 256, 0, ctx.stream>>>(M.p, enc.p, ctx.slot_map.p, (int)N);
     APSU_LAUNCH_CHECK();
     ctx.ntt(enc.p, enc.p, ncoeffs, { ctx.idx_t }, true);
-    for (uint32_t i = 0; i < s->n_plain; i++)
-        APSU_CUDA_CHECK(cudaMemcpyAsync(s->plain_coeffs.p + (size_t)i * N, enc.p + (size_t)plain_rows[i] * N, (size_t)N * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+    // coefficient-form plaintexts: rows plain_rows of enc, gathered in one launch
+    build_rows_.upload(plain_rows, ctx.stream);
+    k_gather_rows<<<dim3(N / 256, s->n_plain), 256, 0, ctx.stream>>>(enc.p, s->plain_coeffs.p, build_rows_.p, (int)N);
+    APSU_LAUNCH_CHECK();
     if (s->n_ntt) {
         // transform_to_ntt_inplace(pt, plaintext level): lift + NTT, then the tile-major split store
-        d_rows.upload(ntt_rows, ctx.stream);
+        build_rows2_.upload(ntt_rows, ctx.stream);
         stage_.ensure((size_t)s->n_ntt * Ll * N);
-        k_plain_lift<<<dim3(N / kEwThreads, Ll, s->n_ntt), kEwThreads, 0, ctx.stream>>>(enc.p, stage_.p, ctx.level[Ll], ctx.t, (int)N, d_rows.p);
+        k_plain_lift<<<dim3(N / kEwThreads, Ll, s->n_ntt), kEwThreads, 0, ctx.stream>>>(enc.p, stage_.p, ctx.level[Ll], ctx.t, (int)N, build_rows2_.p);
         APSU_LAUNCH_CHECK();
         ctx.ntt(stage_.p, stage_.p, s->n_ntt * Ll, ctx.pattern_q(Ll), false);
         pack_tile(stage_.p, s->ntt_coeffs.p, s->n_ntt, Ll);
     }
     prepare_plain_high(*s);
-    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
     uint32_t ci = s->cache_idx;
     db[bundle_idx].push_back(std::move(s));
     invalidate_plan();

@@ -71,6 +71,11 @@ public:
     uint32_t add_binbundle(uint32_t bundle_idx, const uint64_t *const *coeffs, uint32_t ncoeffs);
     uint32_t add_binbundle_synthetic(uint32_t bundle_idx, uint32_t ncoeffs, uint64_t seed);
     uint32_t add_binbundle_from_bins(uint32_t bundle_idx, const uint32_t *bin_sizes, const uint64_t *roots);
+    uint32_t add_binbundle_from_bins_device(uint32_t bundle_idx, const uint32_t *d_first, const uint32_t *d_size, const u64 *d_roots, uint32_t max_deg);
+    void throw_if_build_invalid();
+    // ReceiverDB::set_data / insert_or_assign on an empty DB (receiver_db.cpp:330-438, 966): first-fit insertion of the
+    // algebraised items into BinBundles and the build of every cache, on the device (dbbuild.cu)
+    void set_data(const uint64_t *felts, const uint64_t *cuckoo_idx, size_t n, bool on_device, uint32_t *bundle_counts);
     uint32_t total_bundles() const;
     uint64_t stream_bytes() const;
     void clear_db();
@@ -213,7 +218,7 @@ private:
     void prepare_plain_high(BinBundleStore &s);
     void pack_tile(const u64 *src, u64 *dst, uint32_t rows, uint32_t L);
     DBuf<u64> stage_;         // staging for uploads in the standard layout
-    DBuf<uint32_t> build_first_, build_size_, build_rows_; // scratch of add_binbundle_from_bins, kept between calls
+    DBuf<uint32_t> build_first_, build_size_, build_rows_, build_rows2_; // scratch of add_binbundle_from_bins, kept between calls
     DBuf<u64> build_roots_, build_M_, build_enc_;
     DBuf<int> build_bad_;
     DBuf<u64> aux_[6];        // scratch of the mask / decrypt entry points, kept between calls

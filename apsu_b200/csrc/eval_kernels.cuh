@@ -464,6 +464,14 @@ k_decode_gather(const u64 *__restrict__ ntt_plain, u64 *__restrict__ values, u64
     }
 }
 
+// out[p] = in[rows[p]] (rows of N words).  grid (N/256, n_rows)
+__global__ void k_gather_rows(const u64 *__restrict__ in, u64 *__restrict__ out, const u32 *__restrict__ rows, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t p = blockIdx.y;
+    out[p * N + i] = in[(size_t)rows[p] * N + i];
+}
+
 // BatchEncoder::encode scatter: out[p][map[i]] = values[p][i]
 __global__ void k_slot_scatter(const u64 *__restrict__ values, u64 *__restrict__ out, const u32 *__restrict__ map, int N)
 {

@@ -147,6 +147,19 @@ class ReceiverDB:
         capi.check(capi.lib().apsu_b200_db_add_binbundle_from_bins(self._h, bundle_idx, sizes, roots, C.byref(ci)))
         return ci.value
 
+    def set_data(self, felts, cuckoo_idx):
+        """ReceiverDB::set_data (receiver/apsu/receiver_db.cpp:966 -> insert_or_assign_worker :330-438 -> generate_caches
+        :808) on the device: felts [n][felts_per_item] and cuckoo_idx [n] (= location * felts_per_item) are the
+        reference's data_with_indices in its order; first-fit insertion into BinBundles and every cache are built on the
+        GPU.  Returns the number of BinBundles per bundle index."""
+        f = np.ascontiguousarray(felts, dtype=np.uint64)
+        c = np.ascontiguousarray(cuckoo_idx, dtype=np.uint64)
+        if f.ndim != 2 or f.shape[1] != self.params.item_params()["felts_per_item"] or f.shape[0] != c.shape[0]:
+            raise ValueError("felts must be [n][felts_per_item] and cuckoo_idx [n]")
+        counts = np.zeros(self.params.bundle_idx_count(), dtype=np.uint32)
+        capi.check(capi.lib().apsu_b200_db_set_data(self._h, capi.ptr(f), capi.ptr(c), f.shape[0], capi.ptr(counts)))
+        return [int(x) for x in counts]
+
     def get_bin_bundle_count(self, bundle_idx: int | None = None) -> int:
         v = C.c_uint32()
         if bundle_idx is None:

@@ -131,6 +131,17 @@ int apsu_b200_db_add_binbundle_synthetic(
  * bins' field elements concatenated (each below plain_modulus, else APSU_B200_ERR_INVALID_ARGUMENT). */
 int apsu_b200_db_add_binbundle_from_bins(
     apsu_b200_ctx *ctx, uint32_t bundle_idx, const uint32_t *bin_sizes, const uint64_t *roots, uint32_t *cache_idx);
+/* Row f1 — ReceiverDB::set_data / insert_or_assign on an empty DB (receiver/apsu/receiver_db.cpp:966, dispatch :446,
+ * insert_or_assign_worker :330-438) followed by generate_caches (:808): the whole DB build from the algebraised items,
+ * on the device.  Input = the reference's `data_with_indices` (preprocess_unlabeled_data, :246-307): item k has
+ * felts[k][0..felts_per_item) (each below plain_modulus) and cuckoo_idx[k] = location * felts_per_item, the first bin of
+ * the table slot it hashed to, in the order the reference would walk them (the order decides which BinBundle an item
+ * lands in: every item goes to the NEWEST BinBundle of its bundle index whose bins stay below max_items_per_bin, a new
+ * one is appended when none has room, :370-432).  The resulting BinBundles — items per bin and all cached plaintexts —
+ * are those of the reference, bit for bit.  Replaces the DB.  bundle_counts (optional): [bundle_idx_count] BinBundles
+ * created per bundle index. */
+int apsu_b200_db_set_data(apsu_b200_ctx *ctx, const uint64_t *felts, const uint64_t *cuckoo_idx, uint64_t n_items, uint32_t *bundle_counts);
+int apsu_b200_db_set_data_device(apsu_b200_ctx *ctx, const void *felts_device, const void *cuckoo_idx_device, uint64_t n_items, uint32_t *bundle_counts);
 /* ReceiverDB::get_bin_bundle_count(bundle_idx) / () — receiver_db.cpp:742-760. */
 int apsu_b200_db_bin_bundle_count(const apsu_b200_ctx *ctx, uint32_t bundle_idx, uint32_t *count);
 int apsu_b200_db_total_bin_bundle_count(const apsu_b200_ctx *ctx, uint32_t *count);
