@@ -119,6 +119,7 @@ SIGNATURES = {
     "apsu_b200_eval_all_stream": (C.c_int, [vp, vp, vp, vp]),
     "apsu_b200_ctx_set_eval_chunk": (C.c_int, [vp, C.c_uint32]),
     "apsu_b200_run_query": (C.c_int, [vp, u32p, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp]),
+    "apsu_b200_run_query_seeded": (C.c_int, [vp, u32p, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp]),
     "apsu_b200_query_begin_device": (C.c_int, [vp, u32p, C.c_uint32, vp]),
     "apsu_b200_set_relin_keys_device": (C.c_int, [vp, vp]),
     "apsu_b200_set_masks_device": (C.c_int, [vp, vp, C.c_uint32]),

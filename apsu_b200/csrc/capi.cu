@@ -393,6 +393,22 @@ int apsu_b200_run_query(
     });
 }
 
+int apsu_b200_run_query_seeded(
+    apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *c0, const uint8_t *seeds, const uint64_t *relin_c0,
+    const uint8_t *relin_seeds, const uint8_t *mask_seed, const uint8_t *padded, uint32_t npack, uint64_t *random_matrix, uint64_t *out,
+    uint32_t *bundle_idx, uint32_t *cache_idx)
+{
+    return guarded([&] {
+        Engine &e = E(ctx);
+        e.query_begin_seeded(src_powers, nsrc, c0, seeds);
+        e.set_relin_keys_seeded(relin_c0, relin_seeds);
+        e.generate_masks(mask_seed, padded, npack, random_matrix, nullptr, /*synchronise=*/false);
+        e.compute_powers();
+        e.eval_all();
+        e.fetch_results(out, bundle_idx, cache_idx);
+    });
+}
+
 int apsu_b200_ctx_modulus_index(const apsu_b200_ctx *ctx, int kind, uint32_t i, uint32_t *index)
 {
     return guarded([&] {

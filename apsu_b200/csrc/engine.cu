@@ -292,7 +292,7 @@ Engine::Engine(const apsu_b200_params &p, int device) : ctx(p, device)
     }
     if (const char *ev = std::getenv("APSU_B200_NO_GRAPH")) use_graphs_ = atoi(ev) == 0;
     if (const char *ev = std::getenv("APSU_B200_CHUNK")) eval_chunk_ = (uint32_t)std::max(1, atoi(ev));
-    if (const char *ev = std::getenv("APSU_B200_NO_FUSE")) fuse_ = atoi(ev) == 0; // A/B: element-wise kernels unfused
+    if (const char *ev = std::getenv("APSU_B200_FUSE")) fuse_ = atoi(ev) != 0; // A/B: element-wise producers fused into the transforms
     for (auto &ev : ev_) APSU_CUDA_CHECK(cudaEventCreate(&ev));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
 }
@@ -591,7 +591,7 @@ void Engine::encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t 
 // bytes (the reference takes them from random_bytes, :221-225; a NULL seed does the same here through getrandom),
 // one 32-bit draw per slot in (cache_idx, bundle_idx) order skipping padded pairs, the values' encodings (kept
 // resident as the masks of the next evaluation) and the PEQT blocks.
-void Engine::generate_masks(const uint8_t *seed64, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out)
+void Engine::generate_masks(const uint8_t *seed64, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out, bool synchronise)
 {
     if (!padded || !npack) throw std::invalid_argument("generate_masks: bad arguments");
     const uint32_t N = ctx.N, ipb = ctx.params.items_per_bundle;
@@ -625,7 +625,7 @@ void Engine::generate_masks(const uint8_t *seed64, const uint8_t *padded, uint32
     npack_ = npack;
     if (blocks_out) APSU_CUDA_CHECK(cudaMemcpyAsync(blocks_out, blocks.p, (size_t)npack * ipb * 2 * 8, cudaMemcpyDeviceToHost, ctx.stream));
     if (values_out) APSU_CUDA_CHECK(cudaMemcpyAsync(values_out, values.p, (size_t)npack * N * 8, cudaMemcpyDeviceToHost, ctx.stream));
-    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    if (synchronise) APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream)); // else: the outputs are valid after the next synchronising call
 }
 
 // sample_poly_uniform for `n` seeded polynomials of L primes each into arena blocks dst[k] ([L][N]); seeds on the host

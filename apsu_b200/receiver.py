@@ -365,6 +365,31 @@ class Receiver:
             capi.ptr(masks), masks.shape[0], capi.ptr(out), capi.ptr(b), capi.ptr(c)))
         return [ResultPackage(int(b[k]), int(c[k]), out[k].reshape(2, 1, N)) for k in range(n)]
 
+    def RunQuerySeeded(self, src_powers, c0, seeds, relin_c0, relin_seeds, mask_seed: bytes | None, cache_counts=None):
+        """The HE part of RunQuery fed as the reference's is (apsu_b200_run_query_seeded): seeded ciphertexts / keys as on
+        the wire, masks drawn inside the call.  -> (ResultPackages, random_matrix [npack][items_per_bundle][2])"""
+        p = self.db.params
+        bic, N = p.bundle_idx_count(), p.poly_modulus_degree()
+        if cache_counts is None:
+            cache_counts = [self.db.get_bin_bundle_count(b) for b in range(bic)]
+        alpha = max(max(cache_counts), 1)
+        padded = np.ascontiguousarray([1 if c >= cache_counts[b] else 0 for c in range(alpha) for b in range(bic)], dtype=np.uint8)
+        n = self.db.get_bin_bundle_count()
+        sp = np.ascontiguousarray(list(src_powers), dtype=np.uint32)
+        c0 = np.ascontiguousarray(c0, dtype=np.uint64)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8)
+        rc0 = None if relin_c0 is None else np.ascontiguousarray(relin_c0, dtype=np.uint64)
+        rs = None if relin_seeds is None else np.ascontiguousarray(relin_seeds, dtype=np.uint8)
+        ms = None if mask_seed is None else np.frombuffer(bytes(mask_seed), dtype=np.uint8).copy()
+        blocks = np.zeros((alpha * bic, p.items_per_bundle(), 2), dtype=np.uint64)
+        out = np.zeros((max(n, 1), 2, N), dtype=np.uint64)
+        b = np.zeros(max(n, 1), dtype=np.uint32)
+        c = np.zeros(max(n, 1), dtype=np.uint32)
+        capi.check(self._L.apsu_b200_run_query_seeded(
+            self.db._h, sp, len(sp), capi.ptr(c0), capi.ptr(seeds), capi.ptr(rc0), capi.ptr(rs), capi.ptr(ms), capi.ptr(padded), alpha * bic,
+            capi.ptr(blocks), capi.ptr(out), capi.ptr(b), capi.ptr(c)))
+        return [ResultPackage(int(b[k]), int(c[k]), out[k].reshape(2, 1, N)) for k in range(n)], blocks
+
     def timings(self) -> dict:
         t = capi.CTimings()
         capi.check(self._L.apsu_b200_last_timings(self.db._h, C.byref(t)))

@@ -456,6 +456,40 @@ def main():
     e2e_ms_local = (time.perf_counter() - w0) * 1e3 / args.steps
     barrier()
 
+    # ---- e2e, fed as the reference's RunQuery is (N=1): the query as on the wire (seeded ciphertexts and keys: c1 is a
+    # 64-byte seed expanded on the device, row f2) and the masks drawn on the device inside the call (row f3) ----
+    e2e_seeded = None
+    if mg is None:
+        rng = np.random.default_rng(SEEDS["query"] + 1)
+        c0_t, c0_p = pinned(np.ascontiguousarray(cts[:, :, 0]))
+        sd_t = torch.from_numpy(rng.integers(0, 256, size=(nsrc, bic, 64), dtype=np.uint8)).pin_memory()
+        rc0_t, rc0_p = pinned(np.ascontiguousarray(relin[:, 0]))
+        rsd_t = torch.from_numpy(rng.integers(0, 256, size=(K - 1, 64), dtype=np.uint8)).pin_memory()
+        mask_seed = np.frombuffer(bytes(range(64)), dtype=np.uint8).copy()
+        counts_b = [len(r) for r in degrees]
+        alpha = max(counts_b)
+        padded = np.ascontiguousarray([1 if c >= counts_b[b] else 0 for c in range(alpha) for b in range(bic)], dtype=np.uint8)
+        rm_t = torch.empty((alpha * bic, params.items_per_bundle(), 2), dtype=torch.int64).pin_memory()
+
+        def step_seeded():
+            capi.check(lib.apsu_b200_run_query_seeded(
+                h, src_powers, nsrc, capi.ptr(c0_p), C.c_void_p(sd_t.data_ptr()), capi.ptr(rc0_p), C.c_void_p(rsd_t.data_ptr()), capi.ptr(mask_seed),
+                capi.ptr(padded), alpha * bic, C.c_void_p(rm_t.data_ptr()), capi.ptr(out_p), capi.ptr(bidx), capi.ptr(cidx)))
+        saved = out_p[:n_bundles].copy(), bidx.copy(), cidx.copy()  # results of the expanded query: the parity sample below
+        for _ in range(args.warmup):
+            step_seeded()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_seeded()
+        ms_seeded = (time.perf_counter() - w0) * 1e3 / args.steps
+        out_p[:n_bundles], bidx[:], cidx[:] = saved
+        e2e_seeded = {"value": n_bundles / (ms_seeded / 1e3), "unit": "BinBundles/s", "ms_per_step": ms_seeded,
+                      "h2d_bytes_per_step": int(c0_p.nbytes + sd_t.numel() + rc0_p.nbytes + rsd_t.numel() + 64 + padded.nbytes),
+                      "d2h_bytes_per_step": int(n_bundles * 2 * N * 8 + rm_t.numel() * 8),
+                      "what": "apsu_b200_run_query_seeded: seeded query ciphertexts and relinearisation keys as on the wire (c1 expanded on the device), "
+                              "masks and PEQT blocks generated on the device (blake2xb), results + random_matrix back"}
+
     # max over ranks
     if dist is not None:
         v = torch.tensor([ms_step_local, e2e_ms_local], device="cuda", dtype=torch.float64)
@@ -504,6 +538,8 @@ def main():
             "launch_mode": "eager" if os.environ.get("APSU_B200_NO_GRAPH", "0") not in ("", "0") else
                            f"CUDA graphs replayed per query ({int(tm['kernel_launches'])} kernel nodes of this repo's kernels per query on rank 0)",
         }
+        if e2e_seeded is not None:
+            out["e2e_seeded"] = e2e_seeded
         # ---- parity at every N: the gathered results of the last e2e step against the oracle (one BinBundle per rank,
         # the fullest and the smallest at N=1) and their digest against the N=1 record ----
         got = {(int(bidx[k]), int(cidx[k])): out_p[k] for k in range(n_bundles)}

@@ -239,6 +239,14 @@ int apsu_b200_fetch_results(apsu_b200_ctx *ctx, uint64_t *out, uint32_t *bundle_
 int apsu_b200_run_query(
     apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys,
     const uint64_t *masks, uint32_t npack, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
+/* The same, fed as the reference's RunQuery is: the query as it is on the wire (seeded ciphertexts and keys,
+ * apsu_b200_query_begin_seeded / apsu_b200_set_relin_keys_seeded) and the masks drawn inside the call
+ * (apsu_b200_generate_masks; mask_seed NULL = OS randomness as in receiver_ddh.cpp:221-225).  Uploads c0 + seeds only,
+ * returns the result ciphertexts and random_matrix (the PEQT hand-off, [npack][items_per_bundle][2]). */
+int apsu_b200_run_query_seeded(
+    apsu_b200_ctx *ctx, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *c0, const uint8_t *seeds, const uint64_t *relin_c0,
+    const uint8_t *relin_seeds, const uint8_t *mask_seed, const uint8_t *padded, uint32_t npack, uint64_t *random_matrix, uint64_t *out,
+    uint32_t *bundle_idx, uint32_t *cache_idx);
 /* Device-resident variant used for sharded runs: cts/keys/masks already on this context's GPU.  These calls are
  * ASYNCHRONOUS: they queue device-to-device copies on the context stream and return; the source buffers must stay
  * valid (and unmodified) until apsu_b200_ctx_synchronize or a fetch of the results.  The residue-range check of the

@@ -148,3 +148,41 @@ def test_query_with_out_of_range_residue_is_rejected():
             rx.load_query(apsu_b200.Query(sc.src_powers, sc.cts, badk))
     finally:
         db.close()
+
+
+def test_run_query_seeded_whole_call():
+    """apsu_b200_run_query_seeded: seeded query + seeded keys + masks drawn on the device from a 64-byte seed, one call —
+    equals the oracle fed with the expanded ciphertexts and the restated masks; random_matrix equals the restatement."""
+    import apsu_b200
+    from harness import ref_generate_masks
+    degrees = [[30, 9], [20], [], [12], [18]]
+    sc = Scenario("1M-4096-com", degrees, planted=4)
+    p = sc.p
+    rng = np.random.default_rng(9)
+    nsrc, bic = sc.cts.shape[0], sc.cts.shape[1]
+    seeds = rng.integers(0, 256, size=(nsrc, bic, 64), dtype=np.uint8)
+    cts = sc.cts.copy()
+    for k in range(nsrc):
+        for b in range(bic):
+            cts[k, b, 1] = O.sample_poly_uniform(seeds[k, b].tobytes(), p.primes[:p.first_L], p.N)
+    relin = sc.relin.copy()
+    rseeds = rng.integers(0, 256, size=(p.K - 1, 64), dtype=np.uint8)
+    for J in range(p.K - 1):
+        relin[J, 1] = O.sample_poly_uniform(rseeds[J].tobytes(), p.primes, p.N)
+    mask_seed = bytes((5 * i + 2) & 0xFF for i in range(64))
+    values, blocks, _ = ref_generate_masks(p, mask_seed, [len(d) for d in degrees])
+    masks = np.stack([sc.ctx.encode(v) for v in values])
+    exp = {(b, c): ct for b, c, ct in sc.db.run_query(sc.src_powers, cts, relin, masks, threads=4).results()}
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(p.to_json()), 0)
+    try:
+        for b in range(bic):
+            for c in range(len(degrees[b])):
+                db.add_bin_bundle(b, [a for (_, a) in sc.db.bundle_coeffs(b, c)])
+        res, rm = apsu_b200.Receiver(db).RunQuerySeeded(sc.src_powers, cts[:, :, 0], seeds, relin[:, 0], rseeds, mask_seed)
+        assert np.array_equal(rm, blocks)
+        got = {(r.bundle_idx, r.cache_idx): r.psu_result.reshape(2, -1) for r in res}
+        assert set(got) == set(exp)
+        for key in exp:
+            assert np.array_equal(got[key], exp[key]), key
+    finally:
+        db.close()

@@ -494,3 +494,23 @@ def test_results_are_delivered_per_binbundle():
             assert np.array_equal(rp.psu_result.reshape(2, -1), exp[(rp.bundle_idx, rp.cache_idx)])
     finally:
         db.close()
+
+
+def test_fused_transform_prologues_are_bit_exact(monkeypatch):
+    """APSU_B200_FUSE=1: extension / tensor product / key-switch inner product computed inside the transforms that
+    consume them (ntt.cuh: NttFuse) — an alternative schedule of the same arithmetic, kept for A/B measurements."""
+    import apsu_b200
+    monkeypatch.setenv("APSU_B200_FUSE", "1")
+    for name, degrees in [("16M-4096", [[50], [], [46, 3], []]), ("256K-512", [[20, 63]])]:
+        sc = Scenario(name, degrees, planted=4)
+        db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0)
+        try:
+            _upload(sc, db)
+            got = {(r.bundle_idx, r.cache_idx): r.psu_result.reshape(2, -1)
+                   for r in apsu_b200.Receiver(db).RunQuery(apsu_b200.Query(sc.src_powers, sc.cts, sc.relin), sc.masks)}
+            exp = {(b, c): ct for b, c, ct in sc.db.run_query(sc.src_powers, sc.cts, sc.relin, sc.masks, threads=4).results()}
+            assert set(got) == set(exp)
+            for key in exp:
+                assert np.array_equal(got[key], exp[key]), (name, key)
+        finally:
+            db.close()
