@@ -57,11 +57,61 @@ void Engine::run_ks_mac(uint32_t L, uint32_t n_ops, const uint32_t *dig, const u
     k_ks_mac<<<dim3(ctx.N / kEwThreads, L + 1, n_ops * 2), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, dig, out, relin_keys_.p, ctx.ks[L], (int)ctx.N);
     APSU_LAUNCH_CHECK();
 }
-void Engine::run_ks_moddown(uint32_t L, uint32_t n_ops, const uint32_t *acc, const uint32_t *ct, const uint32_t *dst)
+void Engine::run_ks_moddown(uint32_t L, uint32_t n_ops, const uint32_t *acc, const uint32_t *ct, const uint32_t *dst, bool mirror)
 {
     if (!n_ops) return;
-    k_ks_moddown<<<dim3(ctx.N / kEwThreads, 2, n_ops), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, acc, ct, dst, ctx.ks[L], (int)ctx.N);
+    PeerArenas pa;
+    std::memset(&pa, 0, sizeof(pa));
+    if (mirror && p2p_.enabled) {
+        for (size_t k = 0; k < p2p_.arena.size(); k++)
+            if ((int)k != p2p_.me) pa.base[pa.n++] = p2p_.arena[k];
+        k_ks_moddown<true><<<dim3(ctx.N / kEwThreads, 2, n_ops), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, acc, ct, dst, ctx.ks[L], (int)ctx.N, pa);
+    } else {
+        k_ks_moddown<false><<<dim3(ctx.N / kEwThreads, 2, n_ops), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, acc, ct, dst, ctx.ks[L], (int)ctx.N, pa);
+    }
     APSU_LAUNCH_CHECK();
+}
+// barrier between the ranks that split the PowersDag over peer memory (no-op unless set_powers_p2p enabled it)
+void Engine::run_peer_barrier()
+{
+    if (!p2p_.enabled) return;
+    PeerFlags f;
+    std::memset(&f, 0, sizeof(f));
+    f.n = (int)p2p_.flags.size();
+    f.me = p2p_.me;
+    for (int k = 0; k < f.n; k++) f.peer[k] = p2p_.flags[k];
+    f.mine = p2p_flags_.p;
+    f.epoch = p2p_flags_.p + kMaxPeers + 1;
+    f.error = query_bad_.p + 2;
+    k_xgpu_barrier<<<1, 32, 0, ctx.stream>>>(f, 4000000000ll); // ~2 s at 2 GHz
+    APSU_LAUNCH_CHECK();
+    query_checked_ = true;
+}
+uint32_t *Engine::p2p_flags()
+{
+    if (!p2p_flags_.p) {
+        p2p_flags_.alloc(kMaxPeers + 2);
+        APSU_CUDA_CHECK(cudaMemsetAsync(p2p_flags_.p, 0, (kMaxPeers + 2) * sizeof(uint32_t), ctx.stream));
+        APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    }
+    return p2p_flags_.p;
+}
+u64 *Engine::arena_base()
+{
+    if (!plan_valid_) build_plan();
+    return arena_.buf.p;
+}
+// peer arenas / flag arrays of the ranks of the PowersDag partition, indexed by partition rank (own entries ignored);
+// empty vectors switch the peer-memory exchange off (the caller all-gathers the levels itself)
+void Engine::set_powers_p2p(const std::vector<u64 *> &arenas, const std::vector<uint32_t *> &flags)
+{
+    APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    if (arenas.size() > (size_t)kMaxPeers + 1 || arenas.size() != flags.size()) throw std::invalid_argument("set_powers_p2p: bad peer tables");
+    p2p_.arena = arenas;
+    p2p_.flags = flags;
+    p2p_.me = (int)powers_part_rank_;
+    p2p_.enabled = arenas.size() > 1 && arenas.size() == powers_part_size_;
+    drop_graphs(); // the captured launches carry the peer pointers
 }
 void Engine::run_mod_switch_next(uint32_t L, uint32_t n, const uint32_t *src, const uint32_t *dst)
 {
@@ -170,7 +220,7 @@ struct ProgramBuilder {
 
     // relinearize_inplace: size-3 ct3[o] ([3][L][N]) -> size-2 dst[o] ([2][L][N]).
     // scratch: n_ops*(L + 2)*(L + 1) polynomials
-    void relinearize(uint32_t L, const std::vector<uint32_t> &ct3, const std::vector<uint32_t> &dst, uint32_t scratch)
+    void relinearize(uint32_t L, const std::vector<uint32_t> &ct3, const std::vector<uint32_t> &dst, uint32_t scratch, bool mirror = false)
     {
         if (ct3.empty()) return;
         const uint32_t R = L + 1, n_ops = (uint32_t)ct3.size();
@@ -199,7 +249,7 @@ struct ProgramBuilder {
             step([=] { en->run_ks_mac(L, n_ops, en->idx_.at(dg), en->idx_.at(ac)); });
             ntt_run(acc0, n_ops * 2 * R, ctx.pattern_ks(L), true);
         }
-        step([=] { en->run_ks_moddown(L, n_ops, en->idx_.at(ac), en->idx_.at(ct), en->idx_.at(ds)); });
+        step([=] { en->run_ks_moddown(L, n_ops, en->idx_.at(ac), en->idx_.at(ct), en->idx_.at(ds), mirror); });
     }
     static uint32_t relin_scratch(uint32_t L, uint32_t n_ops) { return n_ops * (L + 2) * (L + 1); }
 
@@ -278,8 +328,8 @@ Engine::Engine(const apsu_b200_params &p, int device) : ctx(p, device)
         fold_stages_ = (uint32_t)std::min<unsigned __int128>(cap / kKtTS, 0x7FFFFFFFu);
     }
     levels_dev_.upload(ctx.level, ctx.stream);
-    query_bad_.alloc(2);
-    APSU_CUDA_CHECK(cudaMemsetAsync(query_bad_.p, 0, 2 * sizeof(int), ctx.stream));
+    query_bad_.alloc(3);
+    APSU_CUDA_CHECK(cudaMemsetAsync(query_bad_.p, 0, 3 * sizeof(int), ctx.stream));
     {
         // function attributes are per device: set once per context, not per launch
         auto kern = k_db_mac_kt<kKtStages, kKtCtasPerSm>;
@@ -725,10 +775,10 @@ void Engine::check_range(const u64 *base, uint32_t n_polys, const uint64_t *modu
 void Engine::throw_if_query_invalid()
 {
     if (!query_checked_) return;
-    int bad[2] = { 0, 0 }; // [0] residue out of range, [1] rejection list overflow of a seed expansion
+    int bad[3] = { 0, 0, 0 }; // [0] residue out of range, [1] rejection list overflow of a seed expansion, [2] peer barrier timed out
     APSU_CUDA_CHECK(cudaMemcpyAsync(bad, query_bad_.p, sizeof(bad), cudaMemcpyDeviceToHost, ctx.stream));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
-    if (bad[0] | bad[1]) APSU_CUDA_CHECK(cudaMemsetAsync(query_bad_.p, 0, sizeof(bad), ctx.stream));
+    if (bad[0] | bad[1] | bad[2]) APSU_CUDA_CHECK(cudaMemsetAsync(query_bad_.p, 0, sizeof(bad), ctx.stream));
     query_checked_ = false;
     if (bad[0]) {
         query_loaded_ = false;
@@ -737,6 +787,10 @@ void Engine::throw_if_query_invalid()
     if (bad[1]) {
         query_loaded_ = false;
         throw std::runtime_error("seed expansion: more rejected samples than the device list holds");
+    }
+    if (bad[2]) {
+        query_loaded_ = false;
+        throw std::runtime_error("multi-GPU ComputePowers: a peer of the PowersDag partition did not reach the barrier");
     }
 }
 
@@ -950,9 +1004,15 @@ void Engine::build_plan()
                     o++;
                 }
             }
+            // split PowersDag over peer memory: the first level must not overwrite a peer's level regions while that peer
+            // still reads them (tail of its previous query); every level ends with the barrier that makes the mirrored
+            // products of all ranks visible (run_peer_barrier is a no-op without set_powers_p2p)
+            Engine *self = this;
+            if (part > 1 && d == 1) pb.step([=] { self->run_peer_barrier(); });
             pb.extend(Lf, ext_cts, ext_dst);
             pb.multiply(Lf, a, bb, prod, mscr);
-            pb.relinearize(Lf, prod, dst, rscr); // relinearize == using_keyswitching (checked in ctor)
+            pb.relinearize(Lf, prod, dst, rscr, /*mirror=*/part > 1); // relinearize == using_keyswitching (checked in ctor)
+            if (part > 1) pb.step([=] { self->run_peer_barrier(); });
             powers_stage_end_.push_back(powers_prog_.size());
         }
         // tail: mod-switch every target to its level; low powers to NTT form (:446-478)

@@ -118,6 +118,12 @@ public:
     uint32_t powers_stage_count();
     void compute_powers_stage(uint32_t stage);
     uint32_t powers_exchange_regions(uint32_t level, void **ptrs, uint64_t *chunk_bytes, uint32_t capacity);
+    // split PowersDag exchanged through NVLink peer memory instead of a collective: the key-switch epilogue of every DAG
+    // level stores its products into the peers' arenas too, a flag barrier on the stream closes the level (kernels.cuh)
+    void set_powers_p2p(const std::vector<u64 *> &arenas, const std::vector<uint32_t *> &flags);
+    bool powers_p2p_enabled() const { return p2p_.enabled; }
+    u64 *arena_base();
+    uint32_t *p2p_flags();
     void eval_all();
     void fetch_results(uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
     void eval_all_stream(uint64_t *out, void (*fn)(void *, uint32_t, uint32_t, const uint64_t *), void *user);
@@ -231,7 +237,7 @@ private:
     // seed expansion (blake2.cuh) and query validation
     DBuf<unsigned char> seed_buf_;
     DBuf<uint32_t> seed_dst_, rej_; // rej_: [count per polynomial][positions]
-    DBuf<int> query_bad_;           // [0] residue out of range, [1] rejection-list overflow
+    DBuf<int> query_bad_;           // [0] residue out of range, [1] rejection-list overflow, [2] peer barrier timeout
     bool query_checked_ = false;
     std::vector<uint32_t> partial_rank_; // sorted rank of every source power of a partially loaded query
     std::vector<uint32_t> check_query_powers(const uint32_t *src_powers, uint32_t nsrc);
@@ -252,7 +258,15 @@ private:
     void run_tensor(uint32_t L, uint32_t n_ops, const uint32_t *a, const uint32_t *b, const uint32_t *d);
     void run_scale_down(uint32_t L, uint32_t n_polys, const uint32_t *src, const uint32_t *dst);
     void run_ks_mac(uint32_t L, uint32_t n_ops, const uint32_t *dig, const uint32_t *out);
-    void run_ks_moddown(uint32_t L, uint32_t n_ops, const uint32_t *acc, const uint32_t *ct, const uint32_t *dst);
+    void run_ks_moddown(uint32_t L, uint32_t n_ops, const uint32_t *acc, const uint32_t *ct, const uint32_t *dst, bool mirror = false);
+    void run_peer_barrier();
+    struct P2P {
+        std::vector<u64 *> arena;       // arena base of every rank of the PowersDag partition (peer-mapped)
+        std::vector<uint32_t *> flags;  // their barrier flag arrays
+        int me = 0;
+        bool enabled = false;
+    } p2p_;
+    DBuf<uint32_t> p2p_flags_; // [kMaxPeers + 1] epochs published by the peers, then this rank's own epoch counter
     void run_mod_switch_next(uint32_t L, uint32_t n_polys, const uint32_t *src, const uint32_t *dst);
     void note_launch() { ctx.launches++; }
 };

@@ -176,23 +176,78 @@ k_ks_mac(u64 *A, const u32 *__restrict__ dig_idx, const u32 *__restrict__ out_id
 // ---- key switching: divide by the special prime with rounding and add to (c0, c1) ----
 // grid (N/256, 2, n_ops).  acc[o] -> [2][R][N] coefficient form; ct[o] -> [>=2][L][N] (c0,c1 read);
 // dst[o] -> [2][L][N].
+// PEERS: the PowersDag of a bundle index is split over several GPUs (collective C2) and this launch
+// produces this rank's share of a DAG level: every output word is ALSO stored into the same place of the peers'
+// arenas through NVLink peer memory (plain coalesced 8-byte stores, 256 B per warp), so the exchange of the level
+// overlaps the arithmetic that produces it and no separate collective runs; k_xgpu_barrier closes the level.
+constexpr int kMaxPeers = 7;
+struct PeerArenas {
+    u64 *base[kMaxPeers];
+    int n;
+};
+template <bool PEERS>
 __global__ void __launch_bounds__(kEwThreads)
-k_ks_moddown(u64 *A, const u32 *__restrict__ acc_idx, const u32 *__restrict__ ct_idx, const u32 *__restrict__ dst_idx, KeySwitchConsts c, int N)
+k_ks_moddown(u64 *A, const u32 *__restrict__ acc_idx, const u32 *__restrict__ ct_idx, const u32 *__restrict__ dst_idx, KeySwitchConsts c, int N, PeerArenas peers)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 comp = blockIdx.y, o = blockIdx.z;
     const int L = c.L, R = L + 1;
     const u64 *ac = A + ((size_t)acc_idx[o] + (size_t)comp * R) * N + n;
     const u64 *ct = A + ((size_t)ct_idx[o] + (size_t)comp * L) * N + n;
-    u64 *dst = A + ((size_t)dst_idx[o] + (size_t)comp * L) * N + n;
+    const size_t dst_off = ((size_t)dst_idx[o] + (size_t)comp * L) * N + n;
     const u64 P = c.key_mod[L].q;
     u64 u = add_mod(ac[(size_t)L * N], c.half_P, P);
     for (int i = 0; i < L; i++) {
         const DMod m = c.key_mod[i];
         u64 delta = sub_mod(barrett64(u, m), c.half_P_mod[i], m.q);
         u64 v = mul_shoup(sub_mod(ac[(size_t)i * N], delta, m.q), c.inv_P[i], m.q);
-        dst[(size_t)i * N] = add_mod(ct[(size_t)i * N], v, m.q);
+        const u64 r = add_mod(ct[(size_t)i * N], v, m.q);
+        A[dst_off + (size_t)i * N] = r;
+        if (PEERS) {
+#pragma unroll
+            for (int k = 0; k < kMaxPeers; k++)
+                if (k < peers.n) peers.base[k][dst_off + (size_t)i * N] = r;
+        }
     }
+}
+
+// Barrier between the GPUs that split a PowersDag, on the stream: every rank bumps its own epoch, publishes it into its
+// slot of every peer's flag array (release, system scope: the peer-memory stores of the preceding kernels are ordered
+// before it) and waits until every peer has published at least the same epoch (acquire).  One warp.  A peer that never
+// arrives (it failed) must not hang this GPU: the wait gives up after `timeout_cycles` and raises flags.error.
+struct PeerFlags {
+    u32 *peer[kMaxPeers + 1]; // flag array of rank k of the group (entry `me` unused)
+    u32 *mine;                // this rank's flag array [kMaxPeers + 1]
+    u32 *epoch;               // this rank's barrier counter
+    int *error;               // set when a wait timed out
+    int n, me;
+};
+__global__ void k_xgpu_barrier(PeerFlags f, long long timeout_cycles)
+{
+    __shared__ u32 e_s;
+    const int l = threadIdx.x;
+    if (l == 0) {
+        e_s = *f.epoch + 1;
+        *f.epoch = e_s;
+    }
+    __syncthreads();
+    const u32 e = e_s;
+    __threadfence_system();
+    if (l < f.n && l != f.me) {
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.peer[l] + f.me), "r"(e) : "memory");
+        const long long t0 = clock64();
+        u32 v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.mine + l) : "memory");
+            if ((int)(v - e) >= 0) break;
+            if (clock64() - t0 > timeout_cycles) {
+                atomicExch(f.error, 1);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
 }
 
 // ---- mod_switch_to_next (divide_and_round_q_last): [L][N] -> [L-1][N] ----

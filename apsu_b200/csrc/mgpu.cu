@@ -14,6 +14,7 @@
 #include "engine.hpp"
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 #include <algorithm>
 #include <cstring>
 #include <functional>
@@ -103,6 +104,10 @@ struct apsu_b200_mgpu {
     std::vector<uint32_t> counts;                   // [rank] -> number of BinBundles
     std::vector<uint32_t> all_bundle_idx, all_cache_idx; // global (bundle_idx, cache_idx) of every result, rank-major
     uint32_t part_rank = 0, part_size = 1;
+    // split PowersDag over NVLink peer memory: mapped arenas / flag arrays of the group (own entry = own pointers)
+    bool p2p = false;
+    std::vector<void *> ipc_opened;
+    u64 *arena_at_commit = nullptr;
     // staging
     DBuf<u64> q_stage;  // root: [bundle_idx_count][nsrc][2][L][N]; others: [owned][nsrc][2][L][N]
     DBuf<u64> gathered; // root: [total][2][N]
@@ -115,6 +120,7 @@ void destroy(apsu_b200_mgpu *m)
 {
     if (!m) return;
     if (m->eng) cudaSetDevice(m->eng->ctx.device);
+    for (void *q : m->ipc_opened) cudaIpcCloseMemHandle(q);
     if (m->part_comm) nccl().CommDestroy(m->part_comm);
     if (m->comm) nccl().CommDestroy(m->comm);
     for (auto e : m->chunk_ev) cudaEventDestroy(e);
@@ -135,6 +141,107 @@ std::vector<uint32_t> allgather_u32(apsu_b200_mgpu &m, const std::vector<uint32_
     APSU_CUDA_CHECK(cudaMemcpyAsync(all.data(), m.meta.p + n, all.size() * 4, cudaMemcpyDeviceToHost, st));
     APSU_CUDA_CHECK(cudaStreamSynchronize(st));
     return all;
+}
+
+// Peer-memory exchange of the split PowersDag: every rank of the group publishes its arena and its barrier flags
+// (CUDA IPC handles between processes, plain pointers + cudaDeviceEnablePeerAccess between threads of one process),
+// maps the others', and hands the tables to its engine.  Any rank that cannot (no peer access, different arena layout)
+// makes the whole group fall back to the ncclAllGather exchange.
+struct P2PInfo {
+    unsigned long long pid, arena_ptr, flags_ptr, layout;
+    int device, pad;
+    cudaIpcMemHandle_t arena_h, flags_h;
+};
+void setup_p2p(apsu_b200_mgpu &m)
+{
+    Engine &e = *m.eng;
+    for (void *q : m.ipc_opened) cudaIpcCloseMemHandle(q);
+    m.ipc_opened.clear();
+    m.p2p = false;
+    e.set_powers_p2p({}, {});
+    if (m.part_size < 2 || m.part_size > 8) return;
+    if (const char *ev = std::getenv("APSU_B200_NO_P2P"))
+        if (atoi(ev)) return;
+    cudaStream_t st = e.ctx.stream;
+    P2PInfo mine;
+    std::memset(&mine, 0, sizeof(mine));
+    mine.pid = (unsigned long long)getpid();
+    mine.device = e.ctx.device;
+    mine.arena_ptr = (unsigned long long)e.arena_base(); // builds the plan: the arena is final until the DB changes
+    mine.flags_ptr = (unsigned long long)e.p2p_flags();
+    {   // the exchange regions must sit at the same arena offsets on every rank of the group
+        std::vector<void *> ptrs(e.ctx.params.bundle_idx_count);
+        std::vector<uint64_t> bytes(e.ctx.params.bundle_idx_count);
+        unsigned long long h = 1469598103934665603ull;
+        for (uint32_t lv = 1; lv <= e.dag.depth(); lv++) {
+            const uint32_t n = e.powers_exchange_regions(lv, ptrs.data(), bytes.data(), (uint32_t)ptrs.size());
+            for (uint32_t k = 0; k < n; k++)
+                for (unsigned long long v : { (unsigned long long)((char *)ptrs[k] - (char *)e.arena_base()), (unsigned long long)bytes[k] }) h = (h ^ v) * 1099511628211ull;
+        }
+        mine.layout = h;
+    }
+    bool ok = cudaIpcGetMemHandle(&mine.arena_h, (void *)mine.arena_ptr) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags_h, (void *)mine.flags_ptr) == cudaSuccess;
+    cudaGetLastError();
+    // all-gather the records inside the group
+    const size_t rec = sizeof(P2PInfo);
+    DBuf<unsigned char> buf;
+    buf.alloc(rec * (m.part_size + 1));
+    APSU_CUDA_CHECK(cudaMemcpyAsync(buf.p, &mine, rec, cudaMemcpyHostToDevice, st));
+    APSU_NCCL_CHECK(nccl().AllGather(buf.p, buf.p + rec, rec, ncclUint8, m.part_comm, st));
+    std::vector<P2PInfo> all(m.part_size);
+    APSU_CUDA_CHECK(cudaMemcpyAsync(all.data(), buf.p + rec, rec * m.part_size, cudaMemcpyDeviceToHost, st));
+    APSU_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<u64 *> arenas(m.part_size, nullptr);
+    std::vector<uint32_t *> flags(m.part_size, nullptr);
+    for (uint32_t k = 0; k < m.part_size && ok; k++) {
+        if (all[k].layout != mine.layout) ok = false;
+        if (k == m.part_rank) {
+            arenas[k] = (u64 *)mine.arena_ptr;
+            flags[k] = (uint32_t *)mine.flags_ptr;
+            continue;
+        }
+        if (all[k].pid == mine.pid) { // a thread of this process: direct peer access
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, e.ctx.device, all[k].device) != cudaSuccess || !can) ok = false;
+            else {
+                cudaError_t r = cudaDeviceEnablePeerAccess(all[k].device, 0);
+                if (r != cudaSuccess && r != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+                cudaGetLastError();
+                arenas[k] = (u64 *)all[k].arena_ptr;
+                flags[k] = (uint32_t *)all[k].flags_ptr;
+            }
+        } else {
+            void *a = nullptr, *f = nullptr;
+            if (cudaIpcOpenMemHandle(&a, all[k].arena_h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+            else m.ipc_opened.push_back(a);
+            if (ok && cudaIpcOpenMemHandle(&f, all[k].flags_h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+            else if (ok) m.ipc_opened.push_back(f);
+            cudaGetLastError();
+            arenas[k] = (u64 *)a;
+            flags[k] = (uint32_t *)f;
+        }
+    }
+    // unanimous or not at all
+    std::vector<uint32_t> votes;
+    {
+        DBuf<uint32_t> v;
+        v.alloc(m.part_size + 1);
+        const uint32_t my = ok ? 1u : 0u;
+        APSU_CUDA_CHECK(cudaMemcpyAsync(v.p, &my, 4, cudaMemcpyHostToDevice, st));
+        APSU_NCCL_CHECK(nccl().AllGather(v.p, v.p + 1, 1, ncclUint32, m.part_comm, st));
+        votes.resize(m.part_size);
+        APSU_CUDA_CHECK(cudaMemcpyAsync(votes.data(), v.p + 1, 4 * m.part_size, cudaMemcpyDeviceToHost, st));
+        APSU_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    for (uint32_t x : votes) ok &= x == 1;
+    if (!ok) {
+        for (void *q : m.ipc_opened) cudaIpcCloseMemHandle(q);
+        m.ipc_opened.clear();
+        return;
+    }
+    e.set_powers_p2p(arenas, flags);
+    m.arena_at_commit = (u64 *)mine.arena_ptr;
+    m.p2p = true;
 }
 
 void commit(apsu_b200_mgpu &m, const uint32_t *global_cache_idx, int dag_split)
@@ -203,6 +310,7 @@ void commit(apsu_b200_mgpu &m, const uint32_t *global_cache_idx, int dag_split)
         m.part_rank = 0;
     }
     e.set_powers_partition(m.part_rank, m.part_size);
+    setup_p2p(m);
     // 4. staging
     const apsu_b200_params &p = e.ctx.params;
     const size_t ct_words = (size_t)2 * e.ctx.first_L * e.ctx.N, idx_words = (size_t)p.query_power_count * ct_words;
@@ -226,6 +334,12 @@ void compute_powers(apsu_b200_mgpu &m)
         return;
     }
     const uint32_t stages = e.powers_stage_count();
+    if (m.p2p) {
+        // the levels are exchanged by the kernels themselves (mirrored stores + flag barrier on the stream)
+        if (e.arena_base() != m.arena_at_commit) throw std::logic_error("the DB changed since apsu_b200_mgpu_commit: commit again");
+        for (uint32_t s = 0; s < stages; s++) e.compute_powers_stage(s);
+        return;
+    }
     std::vector<void *> ptrs(e.ctx.params.bundle_idx_count);
     std::vector<uint64_t> bytes(e.ctx.params.bundle_idx_count);
     for (uint32_t s = 0; s < stages; s++) {
@@ -410,7 +524,7 @@ int apsu_b200_mgpu_commit(apsu_b200_mgpu *m, const uint32_t *global_cache_idx, i
     });
 }
 
-int apsu_b200_mgpu_info(const apsu_b200_mgpu *m, uint32_t *total_bin_bundles, uint32_t *dag_group_size, int *nccl_version)
+int apsu_b200_mgpu_info(const apsu_b200_mgpu *m, uint32_t *total_bin_bundles, uint32_t *dag_group_size, int *dag_exchange, int *nccl_version)
 {
     return guarded_call([&] {
         if (!m || !m->committed) throw std::logic_error("apsu_b200_mgpu_commit has not been called");
@@ -418,6 +532,7 @@ int apsu_b200_mgpu_info(const apsu_b200_mgpu *m, uint32_t *total_bin_bundles, ui
         for (uint32_t c : m->counts) total += c;
         if (total_bin_bundles) *total_bin_bundles = total;
         if (dag_group_size) *dag_group_size = m->part_size;
+        if (dag_exchange) *dag_exchange = m->part_size < 2 ? 0 : (m->p2p ? 2 : 1);
         if (nccl_version) APSU_NCCL_CHECK(nccl().GetVersion(nccl_version));
     });
 }

@@ -447,7 +447,7 @@ public:
         const std::size_t N = p.seal_params().poly_modulus_degree, bic = p.bundle_idx_count();
         std::uint32_t L = 0, total = 0;
         detail::check(apsu_b200_ctx_level(dbs_[0]->handle(), 0, &L));
-        detail::check(apsu_b200_mgpu_info(mg_[0], &total, nullptr, nullptr));
+        detail::check(apsu_b200_mgpu_info(mg_[0], &total, nullptr, nullptr, nullptr));
         const std::size_t ct_words = 2 * static_cast<std::size_t>(L) * N;
         std::uint64_t *cts = dbs_[0]->pinned(0, query.data().size() * bic * ct_words);
         std::vector<std::uint32_t> src;

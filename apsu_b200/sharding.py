@@ -60,9 +60,10 @@ class MultiGpu:
 
     def info(self) -> dict:
         C = self._C
-        total, group, ver = C.c_uint32(), C.c_uint32(), C.c_int()
-        self._capi.check(self._L.apsu_b200_mgpu_info(self._h, C.byref(total), C.byref(group), C.byref(ver)))
-        return {"total_bin_bundles": total.value, "dag_group_size": group.value, "nccl_version": ver.value}
+        total, group, exch, ver = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_int()
+        self._capi.check(self._L.apsu_b200_mgpu_info(self._h, C.byref(total), C.byref(group), C.byref(exch), C.byref(ver)))
+        return {"total_bin_bundles": total.value, "dag_group_size": group.value, "nccl_version": ver.value,
+                "dag_exchange": ["none", "ncclAllGather per level", "NVLink peer-memory stores + flag barrier"][exch.value]}
 
     def compute_powers(self):
         self._capi.check(self._L.apsu_b200_mgpu_compute_powers(self._h))

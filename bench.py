@@ -376,7 +376,7 @@ def main():
         mg_info = mg.commit([c for (_, c, _) in mine], 0 if args.no_dag_split else (1 if args.dag_split else -1))
         if mg_info["dag_group_size"] > 1:
             config["parallelism"] = (f"BinBundles sharded over {world} GPU(s); PowersDag of a bundle index split over the "
-                                     f"{mg_info['dag_group_size']} rank(s) that share it, powers all-gathered per DAG level (ncclAllGather)")
+                                     f"{mg_info['dag_group_size']} rank(s) that share it, levels exchanged by {mg_info['dag_exchange']}")
         config["multi_gpu"] = f"C++ host path apsu_b200_mgpu_* over NCCL {mg_info['nccl_version']}: query scattered by bundle index, results gathered unpadded"
 
     nsrc = len(params.query_powers())

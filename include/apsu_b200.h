@@ -284,7 +284,11 @@ void apsu_b200_mgpu_destroy(apsu_b200_mgpu *m);
  * PowersDag, 0 = every rank recomputes it, -1 = split only large DAGs (>= 128 products: below that a level's all-gather
  * costs more than the products it saves, profiles/README.md). */
 int apsu_b200_mgpu_commit(apsu_b200_mgpu *m, const uint32_t *global_cache_idx, int dag_split);
-int apsu_b200_mgpu_info(const apsu_b200_mgpu *m, uint32_t *total_bin_bundles, uint32_t *dag_group_size, int *nccl_version);
+/* dag_exchange: how a split PowersDag is exchanged — 0 not split, 1 ncclAllGather per DAG level, 2 through NVLink peer
+ * memory: the key-switch epilogue of every level stores its products straight into the peers' arenas (CUDA IPC between
+ * processes, peer access between threads) and a flag barrier on the stream closes the level; chosen automatically at
+ * commit when every rank of the group can map the others, APSU_B200_NO_P2P=1 forces the NCCL exchange. */
+int apsu_b200_mgpu_info(const apsu_b200_mgpu *m, uint32_t *total_bin_bundles, uint32_t *dag_group_size, int *dag_exchange, int *nccl_version);
 /* The HE part of Receiver::RunQuery (receiver_ddh.cpp:295-369) over all ranks, host buffers in and out.  Root passes
  * cts / relin_keys (layouts of apsu_b200_run_query) and receives out = uint64_t[total][2][N] with the ResultPackage
  * indices of every result (rank-major, each rank's results in its result order); the other ranks pass NULL for them.

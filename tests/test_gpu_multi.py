@@ -27,7 +27,7 @@ def _run_ranks(world, fn):
 
 @pytest.mark.parametrize("name,degrees,dag_split,expect_group", [
     ("1M-4096-com", [[30, 9], [20], [], [12], [18]], -1, 1),   # ranks own different bundle indices: scatter by index
-    ("16M-4096", [[140, 45]], 1, 2),                            # both ranks on ONE bundle index: PowersDag split (C2)
+    ("16M-4096", [[], [140, 45], [], []], 1, 2),                # both ranks on ONE bundle index: PowersDag split (C2)
     ("256K-512", [[63, 20, 5]], 1, 2),                          # direct evaluation, depth-1 DAG, split
     ("16M-4096", [[50], [], [46, 3], []], 0, 1),                # empty bundle indices, no split
 ])
@@ -68,6 +68,7 @@ def test_two_gpu_query_matches_oracle(name, degrees, dag_split, expect_group):
 
     res = _run_ranks(world, rank_main)
     info0, (out, bidx, cidx) = res[0]
+    print("multi-GPU info:", info0)
     assert info0["total_bin_bundles"] == len(exp)
     assert info0["dag_group_size"] == expect_group and res[1][0]["dag_group_size"] == expect_group
     got = {(int(bidx[k]), int(cidx[k])): out[k] for k in range(len(exp))}
