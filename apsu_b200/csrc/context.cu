@@ -2,6 +2,7 @@
 #include "hostmath.hpp"
 #include "ntt.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace apsu_b200 {
@@ -255,16 +256,17 @@ NttArgs DeviceContext::make_args(const std::vector<uint32_t> &pattern) const
     return a;
 }
 
-template <int LOGN, int DIV, int MODE>
+template <int LOGN, int DIV, int MODE, bool TWS = false>
 static void launch_ntt_shape(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, const NttFuse &f, bool inverse, cudaStream_t st)
 {
     constexpr int threads = (1 << LOGN) / DIV;
-    constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4)); // + one pad word per 16
+    // polynomial + one pad word per 16 (+ the modulus' twiddle table, 16 bytes per entry, when staged: ntt.cuh TWS)
+    constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4)) + (TWS ? (size_t)16 << LOGN : 0);
     // the forward transform fuses kNttExtend, the inverse one kNttTensor / kNttKsMac (ntt.cuh)
     if (inverse) {
-        if constexpr (MODE != kNttExtend) ntt_kernel<LOGN, false, DIV, MODE><<<count, threads, smem, st>>>(in, out, a, s, f);
+        if constexpr (MODE != kNttExtend) ntt_kernel<LOGN, false, DIV, MODE, TWS><<<count, threads, smem, st>>>(in, out, a, s, f);
     } else {
-        if constexpr (MODE == kNttPlain || MODE == kNttExtend) ntt_kernel<LOGN, true, DIV, MODE><<<count, threads, smem, st>>>(in, out, a, s, f);
+        if constexpr (MODE == kNttPlain || MODE == kNttExtend) ntt_kernel<LOGN, true, DIV, MODE, TWS><<<count, threads, smem, st>>>(in, out, a, s, f);
     }
 }
 
@@ -280,12 +282,27 @@ static void configure_ntt_shape()
     APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV, kNttTensor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV, kNttKsMac>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
+constexpr bool ntt_tws_fits(int logn) { return logn <= 13; } // 69.6 + 128 KB at N = 8192
 template <int LOGN>
 static void configure_ntt()
 {
     constexpr int kLatDiv = (LOGN == 12 || LOGN == 13) ? 8 : 16;
     configure_ntt_shape<LOGN, kLatDiv>();
     configure_ntt_shape<LOGN, 32>();
+    if constexpr (ntt_tws_fits(LOGN)) {
+        constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4)) + ((size_t)16 << LOGN);
+        APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true, kLatDiv, kNttPlain, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, kLatDiv, kNttPlain, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+}
+
+static int ntt_tws_mode()
+{
+    static const int mode = [] {
+        const char *ev = std::getenv("APSU_B200_NTT_TWS");
+        return ev ? atoi(ev) : 1;
+    }();
+    return mode;
 }
 
 // picks the launch shape by batch size (ntt.cuh): more threads per polynomial while the batch leaves SMs idle
@@ -295,9 +312,16 @@ static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a
     // measured (N = 8192, one bundle index): 24..112 polynomials take 16 us with N/8 threads and 20-22 us with N/32;
     // N/16 threads for 150..300 polynomials made no difference
     constexpr int kLatDiv = (LOGN == 12 || LOGN == 13) ? 8 : 16; // at most 1024 threads per CTA
-    if (count <= (uint32_t)sms * ntt_min_blocks(LOGN, kLatDiv))
+    if (count <= (uint32_t)sms * ntt_min_blocks(LOGN, kLatDiv)) {
+        if constexpr (MODE == kNttPlain && ntt_tws_fits(LOGN)) {
+            // a batch of at most one CTA per SM: twiddles staged in shared memory (one CTA per SM at N = 8192)
+            if (ntt_tws_mode() && count <= (uint32_t)sms * (LOGN == 13 ? 1 : 2)) {
+                launch_ntt_shape<LOGN, kLatDiv, MODE, true>(in, out, count, a, s, f, inverse, st);
+                return;
+            }
+        }
         launch_ntt_shape<LOGN, kLatDiv, MODE>(in, out, count, a, s, f, inverse, st);
-    else
+    } else
         launch_ntt_shape<LOGN, 32, MODE>(in, out, count, a, s, f, inverse, st);
 }
 

@@ -87,7 +87,14 @@ __device__ __forceinline__ u64 fused_input(const u64 *A, const NttSrc &src, cons
 
 // Butterflies with the 3q-lazy Shoup product (modarith.cuh: mul_shoup_lazy3): forward values live in [0, 6q),
 // inverse values in [0, 3q); nq = 2^64 - q, q3 = 3q (q < 2^61.4, so 6q fits a word).
-template <int R>
+// twiddle fetch: from the global table through the read-only path, or from the copy staged in shared memory (TWS)
+template <bool TWS>
+__device__ __forceinline__ ulonglong2 tw_at(const ulonglong2 *tw, unsigned i)
+{
+    return TWS ? tw[i] : __ldg(&tw[i]);
+}
+
+template <int R, bool TWS = false>
 __device__ __forceinline__ void fwd_group(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, unsigned hi, int s, u64 nq, u64 q3)
 {
 #pragma unroll
@@ -97,7 +104,7 @@ __device__ __forceinline__ void fwd_group(u64 (&x)[1 << R], const ulonglong2 *__
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) {
             if (k & d) continue;
-            ulonglong2 w = __ldg(&tw[mbase + (k >> (R - r))]);
+            ulonglong2 w = tw_at<TWS>(tw, mbase + (k >> (R - r)));
             const u64 u = csub(x[k], q3);                              // [0, 3q)
             const u64 v = mul_shoup_lazy3(x[k + d], w.x, w.y, nq);     // [0, 3q)
             x[k] = u + v;                                              // [0, 6q)
@@ -106,7 +113,7 @@ __device__ __forceinline__ void fwd_group(u64 (&x)[1 << R], const ulonglong2 *__
     }
 }
 
-template <int R>
+template <int R, bool TWS = false>
 __device__ __forceinline__ void inv_group(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, unsigned hi, int s, u64 nq, u64 q3)
 {
 #pragma unroll
@@ -116,7 +123,7 @@ __device__ __forceinline__ void inv_group(u64 (&x)[1 << R], const ulonglong2 *__
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) {
             if (k & d) continue;
-            ulonglong2 w = __ldg(&tw[mbase + (k >> (R - r))]);
+            ulonglong2 w = tw_at<TWS>(tw, mbase + (k >> (R - r)));
             const u64 u = x[k], v = x[k + d];                          // [0, 3q)
             x[k] = csub(u + v, q3);                                    // [0, 3q)
             x[k + d] = mul_shoup_lazy3(u + q3 - v, w.x, w.y, nq);      // [0, 3q)
@@ -149,7 +156,7 @@ __device__ __forceinline__ void inv_group_upper(u64 (&x)[1 << R], const ulonglon
 __device__ __forceinline__ unsigned pad_idx(unsigned i) { return i + (i >> 4); }
 
 // one pass over stages [s, s+R) on the shared-memory polynomial
-template <int LOGN, int R, bool FWD>
+template <int LOGN, int R, bool FWD, bool TWS = false>
 __device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict__ tw, int s, u64 nq, u64 q3)
 {
     constexpr int N = 1 << LOGN;
@@ -162,9 +169,9 @@ __device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict_
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) x[k] = sm[pad_idx(base + k * stride)];
         if (FWD)
-            fwd_group<R>(x, tw, hi, s, nq, q3);
+            fwd_group<R, TWS>(x, tw, hi, s, nq, q3);
         else
-            inv_group<R>(x, tw, hi, s, nq, q3);
+            inv_group<R, TWS>(x, tw, hi, s, nq, q3);
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) sm[pad_idx(base + k * stride)] = x[k];
     }
@@ -172,23 +179,23 @@ __device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict_
 
 // middle passes (shared memory -> shared memory), COUNT passes of three stages starting at stage S;
 // the inverse transform runs the same passes in the opposite order
-template <int LOGN, bool FWD, int S, int COUNT>
+template <int LOGN, bool FWD, int S, int COUNT, bool TWS = false>
 struct MidRunner {
     __device__ static __forceinline__ void run(u64 *sm, const ulonglong2 *tw, u64 nq, u64 q3)
     {
         if (FWD) {
-            smem_pass<LOGN, 3, true>(sm, tw, S, nq, q3);
+            smem_pass<LOGN, 3, true, TWS>(sm, tw, S, nq, q3);
             __syncthreads();
-            MidRunner<LOGN, FWD, S + 3, COUNT - 1>::run(sm, tw, nq, q3);
+            MidRunner<LOGN, FWD, S + 3, COUNT - 1, TWS>::run(sm, tw, nq, q3);
         } else {
-            MidRunner<LOGN, FWD, S + 3, COUNT - 1>::run(sm, tw, nq, q3);
-            smem_pass<LOGN, 3, false>(sm, tw, S, nq, q3);
+            MidRunner<LOGN, FWD, S + 3, COUNT - 1, TWS>::run(sm, tw, nq, q3);
+            smem_pass<LOGN, 3, false, TWS>(sm, tw, S, nq, q3);
             __syncthreads();
         }
     }
 };
-template <int LOGN, bool FWD, int S>
-struct MidRunner<LOGN, FWD, S, 0> {
+template <int LOGN, bool FWD, int S, bool TWS>
+struct MidRunner<LOGN, FWD, S, 0, TWS> {
     __device__ static __forceinline__ void run(u64 *, const ulonglong2 *, u64, u64) {}
 };
 
@@ -211,9 +218,24 @@ constexpr int ntt_min_blocks(int logn, int div)
 }
 // in and out may alias (in-place transforms, gather/scatter inside one arena): each CTA reads its whole polynomial
 // before its first store and no CTA's destination is another CTA's source, so neither pointer is __restrict__.
-template <int LOGN, bool FWD, int DIV, int MODE = kNttPlain>
+// TWS (latency shape only): the modulus' whole twiddle table (N entries, 16 bytes each) is copied into shared memory
+// with cp.async while the polynomial is being loaded, and every pass but the one on stages [0, RF) (15 entries, the
+// same for all threads) takes its twiddles from there.  A transform alone on its SM has nobody to hide the L2 latency
+// of its twiddle loads behind (ncu, 168 polynomials: long-scoreboard is the top stall, issue slots 33 % busy); with
+// one CTA per SM the 128 KB at N = 8192 fit next to the polynomial.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+template <int LOGN, bool FWD, int DIV, int MODE = kNttPlain, bool TWS = false>
 __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) ntt_kernel(const u64 *in, u64 *out, NttArgs a, NttSrc src, NttFuse fuse = NttFuse())
 {
+    static_assert(!TWS || MODE == kNttPlain, "staged twiddles are implemented for the plain transform");
     constexpr int N = 1 << LOGN;
     constexpr int RF = (LOGN % 3 == 0) ? 3 : (LOGN % 3 == 1 ? 4 : 2); // 13 = 4+3+3+3: one shared-memory round trip less than 1+3+3+3+3
     constexpr int MID = (LOGN - RF - 3) / 3;
@@ -223,6 +245,10 @@ __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) 
     const DMod m = a.mod[slot];
     const u64 q = m.q, nq = 0 - m.q, q3 = 3 * m.q;
     const ulonglong2 *tw = a.tw + ((size_t)a.table[slot] * 2 + (FWD ? 0 : 1)) * N;
+    ulonglong2 *tws = reinterpret_cast<ulonglong2 *>(sm + N + (N >> 4)); // TWS: behind the padded polynomial
+    if (TWS) {
+        for (unsigned k = threadIdx.x; k < (unsigned)N; k += blockDim.x) cp_async16(tws + k, tw + k);
+    }
     u64 *op = out + (size_t)(src.dst_idx ? src.dst_idx[p] : p) * N;
     const bool reduce = src.reduce_input != 0;
     // fused prologue: the input is computed element by element into shared memory and the first pass runs from there
@@ -275,14 +301,15 @@ __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) 
                 }
             }
         }
+        if (TWS) cp_async_wait_all();
         __syncthreads();
-        MidRunner<LOGN, true, RF, MID>::run(sm, tw, nq, q3);
+        MidRunner<LOGN, true, RF, MID, TWS>::run(sm, TWS ? tws : tw, nq, q3);
         // stages [LOGN-3, LOGN): shared -> registers -> global, fully reduced
         for (unsigned g = threadIdx.x; g < (N >> 3); g += blockDim.x) {
             u64 x[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = sm[pad_idx(8 * g + k)];
-            fwd_group<3>(x, tw, g, LOGN - 3, nq, q3);
+            fwd_group<3, TWS>(x, TWS ? tws : tw, g, LOGN - 3, nq, q3);
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = csub(csub(csub(x[k], q3), 2 * q), q); // [0, 6q) -> [0, q)
             ulonglong2 *o2 = reinterpret_cast<ulonglong2 *>(op + 8 * g);
@@ -301,12 +328,16 @@ __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) 
                 x[2 * k] = reduce ? barrett64(v.x, m) : v.x;
                 x[2 * k + 1] = reduce ? barrett64(v.y, m) : v.y;
             }
-            inv_group<3>(x, tw, g, LOGN - 3, nq, q3);
+            if (TWS) { // the table must have landed: N/8 groups = threads in this shape, so this runs once per thread
+                cp_async_wait_all();
+                __syncthreads();
+            }
+            inv_group<3, TWS>(x, TWS ? tws : tw, g, LOGN - 3, nq, q3);
 #pragma unroll
             for (int k = 0; k < 8; k++) sm[pad_idx(8 * g + k)] = x[k];
         }
         __syncthreads();
-        MidRunner<LOGN, false, RF, MID>::run(sm, tw, nq, q3);
+        MidRunner<LOGN, false, RF, MID, TWS>::run(sm, TWS ? tws : tw, nq, q3);
         // stages [0, RF) last: shared -> registers -> global.  The N^-1 scaling rides on the very last stage (one
         // twiddle, psi^-(N/2)): x[k] = (u+v)*N^-1, x[k+d] = (u-v)*(w*N^-1), two lazy products instead of one lazy and
         // two exact ones
