@@ -198,6 +198,42 @@ def db_build_measure(pj, name, params, device, with_cpu):
     return out
 
 
+def full_db_build_measure(pj, params, device, db_log2):
+    """Row f1, whole DB: ReceiverDB::set_data (first-fit insertion, receiver_db.cpp:330-438, + every BinBundle cache) on
+    the device from the algebraised items: 2^db_log2 items x hash_func_count table locations in the reference's own order
+    (location-major, preprocess_unlabeled_data :292-301), uniform felts.  The items are generated on the device (torch)
+    and handed over resident (apsu_b200_db_set_data_device): the time is the build, not the upload of 2.4 GB."""
+    import ctypes as C
+    import torch
+    import apsu_b200
+    from apsu_b200 import capi
+    tp, F = pj["table_params"], pj["item_params"]["felts_per_item"]
+    n = (1 << db_log2) * tp["hash_func_count"]
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEEDS["db"] + 11)
+    locs = torch.sort(torch.randint(0, tp["table_size"], (n,), device="cuda", generator=g, dtype=torch.int64)).values
+    cidx = (locs * F).contiguous()
+    felts = torch.randint(0, params.plain_modulus(), (n, F), device="cuda", generator=g, dtype=torch.int64).contiguous()
+    torch.cuda.synchronize()
+    db = apsu_b200.ReceiverDB(params, device)
+    try:
+        counts = np.zeros(params.bundle_idx_count(), dtype=np.uint32)
+        ms = []
+        for _ in range(2):  # the second build reuses the scratch of the first
+            t0 = time.perf_counter()
+            capi.check(capi.lib().apsu_b200_db_set_data_device(db._h, C.c_void_p(felts.data_ptr()), C.c_void_p(cidx.data_ptr()), n, capi.ptr(counts)))
+            ms.append((time.perf_counter() - t0) * 1e3)
+        nb = int(counts.sum())
+    finally:
+        db.close()
+    del felts, cidx, locs
+    torch.cuda.empty_cache()
+    return {"what": "whole DB from the algebraised items on the device (apsu_b200_db_set_data_device: sort by slot, first-fit windows, "
+                    "polyn_with_roots + encode + NTT of every BinBundle), items resident",
+            "items": int(n), "bin_bundles": nb, "per_bundle_index": [int(x) for x in counts], "ms": float(min(ms)), "ms_first": float(ms[0]),
+            "items_per_s": float(n / (min(ms) / 1e3))}
+
+
 def oracle_results(pj, name, degrees, cts, relin, masks, pairs, threads):
     """Result ciphertexts of the BinBundles `pairs` = [(bundle_idx, cache_idx), ...] of the synthetic DB, computed by
     the CPU oracle (same seeds as the GPU DB): the checker of `parity_sample`.  -> {pair: ndarray [2][N]}"""
@@ -574,6 +610,11 @@ def main():
             out["cpu_baseline"] = cpu_baseline(pj, name, degrees, cts, relin, masks, os.cpu_count() or 1)
         if not args.no_db_build and world == 1:
             out["db_build"] = db_build_measure(pj, name, params, local_rank, not args.no_cpu_baseline)
+            db.close()  # free the query DB: the full build below needs the memory of a second one
+            try:
+                out["db_build_full"] = full_db_build_measure(pj, params, local_rank, args.db_log2)
+            except Exception as e:  # noqa: BLE001
+                out["db_build_full"] = {"error": repr(e)}
         print(json.dumps(out))
     if mg is not None:
         mg.close()
