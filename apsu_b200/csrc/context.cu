@@ -299,8 +299,11 @@ static void configure_ntt()
 static int ntt_tws_mode()
 {
     static const int mode = [] {
+        // measured on B200 (tools/bench_ntt.py, 24..273 polynomials): no gain (N = 8192, 148 polynomials: 16.6 us either
+        // way; N = 4096, 84: 10.0 vs 10.4 us) — a lone transform is bound by its own multiplier instructions (ntt.cuh),
+        // not by twiddle latency; kept for A/B runs, off by default
         const char *ev = std::getenv("APSU_B200_NTT_TWS");
-        return ev ? atoi(ev) : 1;
+        return ev ? atoi(ev) : 0;
     }();
     return mode;
 }

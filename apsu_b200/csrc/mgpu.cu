@@ -289,7 +289,9 @@ void commit(apsu_b200_mgpu &m, const uint32_t *global_cache_idx, int dag_split)
     size_t products = 0;
     for (auto &lv : e.dag.levels()) products += lv.size();
     products -= e.dag.levels().empty() ? 0 : e.dag.levels()[0].size();
-    const bool want = dag_split > 0 || (dag_split < 0 && products >= 128);
+    // auto (-1): split when the levels can be exchanged through peer memory (cheap: measured 0.62 -> 0.53 ms per bundle
+    // index of 16M-4096 on 2 GPUs) or when the DAG is large enough to pay for ncclAllGather per level (>= 128 products)
+    const bool want = dag_split != 0;
     bool split = eligible && want && e.dag.depth() > 0;
     // every rank must take the same decision about calling ncclCommSplit: `eligible` and `want` are global facts
     bool any_group = false;
@@ -311,6 +313,15 @@ void commit(apsu_b200_mgpu &m, const uint32_t *global_cache_idx, int dag_split)
     }
     e.set_powers_partition(m.part_rank, m.part_size);
     setup_p2p(m);
+    if (dag_split < 0 && m.part_size > 1 && !m.p2p && products < 128) {
+        // no peer memory and a small DAG: recomputing is faster than all-gathering (every rank of the group decides alike:
+        // the peer-memory vote is unanimous)
+        nccl().CommDestroy(m.part_comm);
+        m.part_comm = nullptr;
+        m.part_size = 1;
+        m.part_rank = 0;
+        e.set_powers_partition(0, 1);
+    }
     // 4. staging
     const apsu_b200_params &p = e.ctx.params;
     const size_t ct_words = (size_t)2 * e.ctx.first_L * e.ctx.N, idx_words = (size_t)p.query_power_count * ct_words;
@@ -355,8 +366,10 @@ void compute_powers(apsu_b200_mgpu &m)
     }
 }
 
+// shared_query: every rank was handed the query (the same host memory: threads of one process, or processes mapping
+// one shared segment) and uploads its own part over its own PCIe link — no scatter, no broadcast
 void run_query(apsu_b200_mgpu &m, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys, const uint64_t *masks_local,
-               uint32_t npack_local, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx)
+               uint32_t npack_local, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx, bool shared_query)
 {
     if (!m.committed) throw std::logic_error("apsu_b200_mgpu_commit has not been called");
     Engine &e = *m.eng;
@@ -369,10 +382,24 @@ void run_query(apsu_b200_mgpu &m, const uint32_t *src_powers, uint32_t nsrc, con
     const size_t ct_words = (size_t)2 * e.ctx.first_L * e.ctx.N, ct_bytes = ct_words * 8, idx_words = (size_t)nsrc * ct_words;
     const size_t key_words = e.ctx.using_keyswitching() ? (size_t)(e.ctx.K - 1) * 2 * e.ctx.K * e.ctx.N : 0;
     if (is_root && (!cts || (key_words && !relin_keys) || !out)) throw std::invalid_argument("root rank needs the query, the keys and the output buffer");
+    if (shared_query && (!cts || (key_words && !relin_keys))) throw std::invalid_argument("shared query: every rank needs the query and the keys");
     e.query_begin_partial(src_powers, nsrc);
+    if (shared_query) {
+        if (key_words) {
+            e.reserve_relin_keys();
+            APSU_CUDA_CHECK(cudaMemcpyAsync(e.relin_keys_device(), relin_keys, key_words * 8, cudaMemcpyHostToDevice, st));
+            e.relin_keys_loaded();
+        }
+        uint32_t slot = 0;
+        for (uint32_t b : m.owned[m.rank]) { // host [nsrc][bic][ct] -> device [nsrc][ct]
+            u64 *buf = m.q_stage.p + (size_t)(is_root ? b : slot++) * idx_words;
+            APSU_CUDA_CHECK(cudaMemcpy2DAsync(buf, ct_bytes, cts + (size_t)b * ct_words, (size_t)bic * ct_bytes, ct_bytes, nsrc, cudaMemcpyHostToDevice, st));
+            e.query_load_index(b, buf);
+        }
+    }
 
     // ---- C1: keys to everyone, ciphertexts of bundle index b to the ranks that own BinBundles of b ----
-    if (is_root) {
+    if (!shared_query && is_root) {
         // uploads run on the copy stream, chunk by chunk; the sends of chunk b wait for its event only
         APSU_CUDA_CHECK(cudaEventRecord(m.ready_ev, st)); // staging buffers are free once earlier work on st is done
         APSU_CUDA_CHECK(cudaStreamWaitEvent(m.copy_stream, m.ready_ev, 0));
@@ -391,13 +418,15 @@ void run_query(apsu_b200_mgpu &m, const uint32_t *src_powers, uint32_t nsrc, con
             APSU_CUDA_CHECK(cudaEventRecord(m.chunk_ev[b], m.copy_stream));
         }
     }
-    if (key_words) {
+    if (key_words && !shared_query) {
         if (is_root) APSU_CUDA_CHECK(cudaStreamWaitEvent(st, m.chunk_ev[bic], 0));
         else e.reserve_relin_keys();
         if (m.world > 1) APSU_NCCL_CHECK(nc.Broadcast(e.relin_keys_device(), e.relin_keys_device(), key_words, ncclUint64, (int)m.root, m.comm, st));
         e.relin_keys_loaded();
     }
-    if (is_root) {
+    if (shared_query) {
+        // nothing to exchange
+    } else if (is_root) {
         for (uint32_t b = 0; b < bic; b++) {
             std::vector<uint32_t> dst;
             bool mine = false;
@@ -553,7 +582,18 @@ int apsu_b200_mgpu_run_query(
     return guarded_call([&] {
         if (!m) throw std::invalid_argument("mgpu is null");
         APSU_CUDA_CHECK(cudaSetDevice(m->eng->ctx.device));
-        run_query(*m, src_powers, nsrc, cts, relin_keys, masks_local, npack_local, out, bundle_idx, cache_idx);
+        run_query(*m, src_powers, nsrc, cts, relin_keys, masks_local, npack_local, out, bundle_idx, cache_idx, false);
+    });
+}
+
+int apsu_b200_mgpu_run_query_shared(
+    apsu_b200_mgpu *m, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys, const uint64_t *masks_local,
+    uint32_t npack_local, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx)
+{
+    return guarded_call([&] {
+        if (!m) throw std::invalid_argument("mgpu is null");
+        APSU_CUDA_CHECK(cudaSetDevice(m->eng->ctx.device));
+        run_query(*m, src_powers, nsrc, cts, relin_keys, masks_local, npack_local, out, bundle_idx, cache_idx, true);
     });
 }
 

@@ -465,9 +465,10 @@ public:
         each_rank([&](std::size_t r) {
             const bool root = r == 0;
             const std::vector<std::uint64_t> *m = r < masks.size() && !masks[r].empty() ? &masks[r] : nullptr;
-            detail::check(apsu_b200_mgpu_run_query(
-                mg_[r], src.data(), static_cast<std::uint32_t>(src.size()), root ? cts : nullptr,
-                root && !query.relin_keys().empty() ? query.relin_keys().data() : nullptr, m ? m->data() : nullptr,
+            // the ranks are threads of this process: every GPU uploads its own part of the query in parallel
+            detail::check(apsu_b200_mgpu_run_query_shared(
+                mg_[r], src.data(), static_cast<std::uint32_t>(src.size()), cts,
+                !query.relin_keys().empty() ? query.relin_keys().data() : nullptr, m ? m->data() : nullptr,
                 m ? static_cast<std::uint32_t>(m->size() / N) : 0, root ? out : nullptr, root ? bidx.data() : nullptr, root ? cidx.data() : nullptr));
         });
         for (std::uint32_t k = 0; k < total; k++) {

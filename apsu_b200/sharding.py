@@ -68,9 +68,10 @@ class MultiGpu:
     def compute_powers(self):
         self._capi.check(self._L.apsu_b200_mgpu_compute_powers(self._h))
 
-    def run_query(self, src_powers, cts, relin_keys, masks_local, out=None, bundle_idx=None, cache_idx=None):
+    def run_query(self, src_powers, cts, relin_keys, masks_local, out=None, bundle_idx=None, cache_idx=None, shared: bool = False):
         """root (rank 0): cts / relin_keys host arrays and `out` [total][2][N] (allocated when None); other ranks pass
-        None.  Returns (out, bundle_idx, cache_idx) on root, None elsewhere."""
+        None — or, with shared=True, the same query (one host buffer every rank can read): every rank then uploads its own
+        part and nothing is scattered.  Returns (out, bundle_idx, cache_idx) on root, None elsewhere."""
         np, ptr = self._np, self._capi.ptr
         sp = np.ascontiguousarray(list(src_powers), dtype=np.uint32)
         root = self.rank == 0
@@ -80,8 +81,10 @@ class MultiGpu:
         if root and bundle_idx is None:
             bundle_idx, cache_idx = np.zeros(out.shape[0], dtype=np.uint32), np.zeros(out.shape[0], dtype=np.uint32)
         npack = 0 if masks_local is None else masks_local.shape[0]
-        self._capi.check(self._L.apsu_b200_mgpu_run_query(
-            self._h, sp, len(sp), ptr(cts) if root else None, ptr(relin_keys) if root else None, ptr(masks_local), npack,
+        fn = self._L.apsu_b200_mgpu_run_query_shared if shared else self._L.apsu_b200_mgpu_run_query
+        have = root or shared
+        self._capi.check(fn(
+            self._h, sp, len(sp), ptr(cts) if have else None, ptr(relin_keys) if have else None, ptr(masks_local), npack,
             ptr(out) if root else None, ptr(bundle_idx) if root else None, ptr(cache_idx) if root else None))
         return (out, bundle_idx, cache_idx) if root else None
 

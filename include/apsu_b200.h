@@ -281,8 +281,9 @@ void apsu_b200_mgpu_destroy(apsu_b200_mgpu *m);
 /* After the rank's BinBundles are loaded (and after every DB change): publishes which BinBundles each rank holds.
  * global_cache_idx[k] = cache index, in the whole DB, of this rank's k-th BinBundle in result order (bundle_idx major,
  * local cache index minor); NULL = the local indices.  dag_split: 1 = ranks sharing one bundle index split its
- * PowersDag, 0 = every rank recomputes it, -1 = split only large DAGs (>= 128 products: below that a level's all-gather
- * costs more than the products it saves, profiles/README.md). */
+ * PowersDag, 0 = every rank recomputes it, -1 = split when the levels can be exchanged through NVLink peer memory (see
+ * apsu_b200_mgpu_info) or, failing that, only large DAGs (>= 128 products: below that ncclAllGather per level costs more
+ * than the products it saves, profiles/README.md). */
 int apsu_b200_mgpu_commit(apsu_b200_mgpu *m, const uint32_t *global_cache_idx, int dag_split);
 /* dag_exchange: how a split PowersDag is exchanged — 0 not split, 1 ncclAllGather per DAG level, 2 through NVLink peer
  * memory: the key-switch epilogue of every level stores its products straight into the peers' arenas (CUDA IPC between
@@ -295,6 +296,13 @@ int apsu_b200_mgpu_info(const apsu_b200_mgpu *m, uint32_t *total_bin_bundles, ui
  * masks_local: this rank's dense mask table for its local cache indices (NULL keeps the resident masks, e.g. after
  * apsu_b200_generate_masks). */
 int apsu_b200_mgpu_run_query(
+    apsu_b200_mgpu *m, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys, const uint64_t *masks_local,
+    uint32_t npack_local, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
+/* The same when EVERY rank can read the query in host memory (threads of one process, or processes that map one shared
+ * segment the receiving process wrote the query into): every rank passes cts / relin_keys and uploads the ciphertexts of
+ * its own bundle indices over its own PCIe link — the uploads run in parallel and no scatter / broadcast happens.
+ * Results are gathered on the root as above. */
+int apsu_b200_mgpu_run_query_shared(
     apsu_b200_mgpu *m, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys, const uint64_t *masks_local,
     uint32_t npack_local, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
 /* ComputePowers of this rank with the per-level exchange of a split PowersDag (query already loaded). */
