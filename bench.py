@@ -492,6 +492,21 @@ def main():
     e2e_ms_local = (time.perf_counter() - w0) * 1e3 / args.steps
     barrier()
 
+    # ---- e2e at N>1 when every rank can read the query in host memory (one shared segment / threads of one process; here
+    # every process holds an identical pinned copy): each rank uploads its own part over its own PCIe link, no scatter ----
+    e2e_shared_local = 0.0
+    if mg is not None:
+        def step_shared():
+            mg.run_query(src_powers, cts_p, relin_p, masks_p, out_p, bidx, cidx, shared=True)
+        for _ in range(args.warmup):
+            step_shared()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_shared()
+        e2e_shared_local = (time.perf_counter() - w0) * 1e3 / args.steps
+        barrier()
+
     # ---- e2e, fed as the reference's RunQuery is (N=1): the query as on the wire (seeded ciphertexts and keys: c1 is a
     # 64-byte seed expanded on the device, row f2) and the masks drawn on the device inside the call (row f3) ----
     e2e_seeded = None
@@ -528,11 +543,11 @@ def main():
 
     # max over ranks
     if dist is not None:
-        v = torch.tensor([ms_step_local, e2e_ms_local], device="cuda", dtype=torch.float64)
+        v = torch.tensor([ms_step_local, e2e_ms_local, e2e_shared_local], device="cuda", dtype=torch.float64)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        ms_step, e2e_ms = float(v[0]), float(v[1])
+        ms_step, e2e_ms, e2e_shared_ms = float(v[0]), float(v[1]), float(v[2])
     else:
-        ms_step, e2e_ms = ms_step_local, e2e_ms_local
+        ms_step, e2e_ms, e2e_shared_ms = ms_step_local, e2e_ms_local, 0.0
 
     if rank == 0:
         # N=1: local cache indices are the global ones (one rank holds everything, in order)
@@ -576,6 +591,13 @@ def main():
         }
         if e2e_seeded is not None:
             out["e2e_seeded"] = e2e_seeded
+        if mg is not None:
+            nb_keys = int(relin.nbytes)
+            out["e2e_shared_query"] = {
+                "value": n_bundles / (e2e_shared_ms / 1e3), "unit": "BinBundles/s", "ms_per_step": e2e_shared_ms,
+                "h2d_bytes_per_step": int(cts.nbytes + world * nb_keys + masks.nbytes), "d2h_bytes_per_step": int(n_bundles * 2 * N * 8),
+                "what": "apsu_b200_mgpu_run_query_shared: every rank reads the query from host memory it can see and uploads the ciphertexts of its "
+                        "own bundle indices + the keys over its own PCIe link in parallel; results gathered on rank 0 over NCCL"}
         # ---- parity at every N: the gathered results of the last e2e step against the oracle (one BinBundle per rank,
         # the fullest and the smallest at N=1) and their digest against the N=1 record ----
         got = {(int(bidx[k]), int(cidx[k])): out_p[k] for k in range(n_bundles)}
