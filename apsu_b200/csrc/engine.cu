@@ -355,6 +355,7 @@ Engine::~Engine()
         if (g.copied) cudaEventDestroy(g.copied);
     }
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    if (flags_host_) cudaFreeHost(flags_host_);
     for (auto &e : ev_)
         if (e) cudaEventDestroy(e);
     for (auto &pr : mac_events_) {
@@ -775,11 +776,24 @@ void Engine::check_range(const u64 *base, uint32_t n_polys, const uint64_t *modu
 void Engine::throw_if_query_invalid()
 {
     if (!query_checked_) return;
-    int bad[3] = { 0, 0, 0 }; // [0] residue out of range, [1] rejection list overflow of a seed expansion, [2] peer barrier timed out
-    APSU_CUDA_CHECK(cudaMemcpyAsync(bad, query_bad_.p, sizeof(bad), cudaMemcpyDeviceToHost, ctx.stream));
+    enqueue_flag_read();
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
-    if (bad[0] | bad[1] | bad[2]) APSU_CUDA_CHECK(cudaMemsetAsync(query_bad_.p, 0, sizeof(bad), ctx.stream));
+    check_flags_after_sync();
+}
+// the flag read rides on whatever synchronisation the caller does next: enqueue (pinned destination, truly
+// asynchronous), let the caller enqueue its own copies and synchronise once, then check
+void Engine::enqueue_flag_read()
+{
+    if (!query_checked_) return;
+    if (!flags_host_) APSU_CUDA_CHECK(cudaHostAlloc(&flags_host_, 3 * sizeof(int), cudaHostAllocDefault));
+    APSU_CUDA_CHECK(cudaMemcpyAsync(flags_host_, query_bad_.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+}
+void Engine::check_flags_after_sync()
+{
+    if (!query_checked_) return;
     query_checked_ = false;
+    const int bad[3] = { flags_host_[0], flags_host_[1], flags_host_[2] }; // [0] residue out of range, [1] rejection list overflow, [2] peer barrier timed out
+    if (bad[0] | bad[1] | bad[2]) APSU_CUDA_CHECK(cudaMemsetAsync(query_bad_.p, 0, sizeof(bad), ctx.stream));
     if (bad[0]) {
         query_loaded_ = false;
         throw std::invalid_argument("query ciphertexts or keys are not valid for the encryption parameters (residue >= modulus)");
@@ -1624,10 +1638,11 @@ void Engine::collect_timings()
 void Engine::fetch_results(uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx)
 {
     if (!eval_done_) throw std::logic_error("fetch_results called before eval_all");
-    throw_if_query_invalid();
     size_t n = result_order_.size();
+    enqueue_flag_read(); // is_valid_for of the query that produced these results: one synchronisation for both
     if (out && n) APSU_CUDA_CHECK(cudaMemcpyAsync(out, results_.p, n * 2 * ctx.N * 8, cudaMemcpyDeviceToHost, ctx.stream));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    check_flags_after_sync();
     for (size_t k = 0; k < n; k++) {
         if (bundle_idx) bundle_idx[k] = result_order_[k].first;
         if (cache_idx) cache_idx[k] = result_order_[k].second;

@@ -239,6 +239,9 @@ private:
     DBuf<uint32_t> seed_dst_, rej_; // rej_: [count per polynomial][positions]
     DBuf<int> query_bad_;           // [0] residue out of range, [1] rejection-list overflow, [2] peer barrier timeout
     bool query_checked_ = false;
+    int *flags_host_ = nullptr; // pinned landing zone of query_bad_
+    void enqueue_flag_read();
+    void check_flags_after_sync();
     std::vector<uint32_t> partial_rank_; // sorted rank of every source power of a partially loaded query
     std::vector<uint32_t> check_query_powers(const uint32_t *src_powers, uint32_t nsrc);
     void check_range(const u64 *base, uint32_t n_polys, const uint64_t *moduli, uint32_t nmods);
