@@ -78,7 +78,7 @@ __global__ void k_ff_window(FfState st, u32 B)
     const u32 *A = st.arrivals + st.slot_first[st.slot0 + s];
     const u32 len = st.slot_first[st.slot0 + s + 1] - st.slot_first[st.slot0 + s];
     u32 start = st.start[s];
-    if (B > 1 || st.creation[0] != kNoCreation) {
+    if (B >= 1) { // (not "creation[0] is set": other threads are writing creation[B] of THIS window right now)
         // window that ended with creation[B-1]: arrivals before it were placed among BinBundles 0..B-2
         const unsigned long long prev = st.creation[B - 1];
         const u32 g = (u32)(prev >> 16), trig = (u32)(prev & 0xFFFF);
