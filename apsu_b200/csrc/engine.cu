@@ -1477,8 +1477,12 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<KtGroup> &grou
         // one persistent launch over all groups (shared-memory opt-in and occupancy: Engine ctor, per device)
         auto kern = k_db_mac_kt<kKtStages, kKtCtasPerSm>;
         constexpr size_t smem = kt_smem_bytes(kKtStages);
+        // persistent grid, balanced: with W = ceil(items / resident CTAs) waves every CTA gets W (or W-1) items — a grid
+        // of all resident CTAs would leave most of them idle in the last wave (256K-512: 320 items on 296 CTAs = two
+        // waves for 8 % more work than one)
         const uint32_t items = n * (L * ctx.N / kKtCols);
-        const uint32_t grid = std::min<uint32_t>(items, kt_grid_cap_);
+        const uint32_t waves = (items + kt_grid_cap_ - 1) / kt_grid_cap_;
+        const uint32_t grid = (items + waves - 1) / waves;
         kern<<<grid, kKtThreads, smem, ctx.stream>>>(arena_.buf.p, gd, n, ctx.level[L], (int)ctx.N, split_, fold_stages_, 0u);
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;

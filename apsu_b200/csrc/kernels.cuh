@@ -165,11 +165,19 @@ k_ks_mac(u64 *A, const u32 *__restrict__ dig_idx, const u32 *__restrict__ out_id
     const u32 o = blockIdx.z >> 1, comp = blockIdx.z & 1;
     const int key_index = I == c.L ? c.K - 1 : I;
     const u64 *dg = A + ((size_t)dig_idx[o] + I) * N + n;
+    // all 2L loads first, then the products: ncu (profiles/ncu_r02_keyswitch_summary.json) showed the rolled loop waiting on
+    // one load pair at a time (long-scoreboard 6.6 of 9.6 stall cycles per issue, FMA pipe 26 % busy)
+    u64 dv[kMaxQ], kv[kMaxQ];
+#pragma unroll
+    for (int J = 0; J < kMaxQ; J++)
+        if (J < c.L) {
+            dv[J] = dg[(size_t)J * R * N];
+            kv[J] = keys[(((size_t)J * 2 + comp) * c.K + key_index) * N + n];
+        }
     Acc128 acc{ 0, 0 };
-    for (int J = 0; J < c.L; J++) {
-        u64 kv = keys[(((size_t)J * 2 + comp) * c.K + key_index) * N + n];
-        mac128(acc, dg[(size_t)J * R * N], kv);
-    }
+#pragma unroll
+    for (int J = 0; J < kMaxQ; J++)
+        if (J < c.L) mac128(acc, dv[J], kv[J]);
     A[((size_t)out_idx[o] + (size_t)comp * R + I) * N + n] = barrett_prod(acc.lo, acc.hi, c.key_mod[I]); // <= 5 products of reduced operands
 }
 

@@ -11,10 +11,32 @@ from __future__ import annotations
 
 def shard_bundles(degrees, world: int):
     """degrees[bundle_idx][cache_idx] -> per-rank lists of (bundle_idx, cache_idx, degree), balanced by the
-    number of plaintexts (degree + 1)."""
+    number of plaintexts (degree + 1).  A rank recomputes the query powers of every bundle index it holds BinBundles of,
+    so: with at least as many ranks as populated bundle indices every rank gets BinBundles of ONE index only (ranks are
+    dealt to the indices in proportion to their plaintexts; the ranks of an index can then split its PowersDag, collective
+    C2); with fewer ranks the (bundle_idx, cache_idx) list is cut into contiguous runs."""
+    weights = [sum(d + 1 for d in row) for row in degrees]
+    active = [b for b, w in enumerate(weights) if w]
+    parts = [[] for _ in range(world)]
+    if active and world >= len(active):
+        total = sum(weights)
+        ranks = {b: 1 for b in active}
+        for _ in range(world - len(active)):  # one more rank to the index with the most plaintexts per rank
+            b = max(active, key=lambda i: (weights[i] / ranks[i], -i))
+            ranks[b] += 1
+        r0 = 0
+        for b in active:
+            acc = 0
+            for c, d in enumerate(degrees[b]):
+                w = d + 1
+                k = min(ranks[b] - 1, int((acc + w / 2) * ranks[b] / weights[b]))
+                parts[r0 + k].append((b, c, d))
+                acc += w
+            r0 += ranks[b]
+        assert total and r0 == world
+        return parts
     flat = [(b, c, d) for b, row in enumerate(degrees) for c, d in enumerate(row)]
     total = sum(d + 1 for _, _, d in flat)
-    parts = [[] for _ in range(world)]
     acc = 0
     for b, c, d in flat:
         w = d + 1

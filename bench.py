@@ -541,6 +541,14 @@ def main():
                       "what": "apsu_b200_run_query_seeded: seeded query ciphertexts and relinearisation keys as on the wire (c1 expanded on the device), "
                               "masks and PEQT blocks generated on the device (blake2xb), results + random_matrix back"}
 
+    # per-rank view (diagnostics): every rank's own loop time and scopes
+    per_rank = None
+    if dist is not None:
+        mine_info = {"rank": rank, "bin_bundles": len(mine), "bundle_indices": sorted({b for (b, _, _) in mine}), "ms_per_step": ms_step_local,
+                     "e2e_ms": e2e_ms_local, "compute_powers_ms": tm["compute_powers_ms"], "eval_ms": tm["eval_ms"]}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine_info)
+
     # max over ranks
     if dist is not None:
         v = torch.tensor([ms_step_local, e2e_ms_local, e2e_shared_local], device="cuda", dtype=torch.float64)
@@ -589,6 +597,8 @@ def main():
             "launch_mode": "eager" if os.environ.get("APSU_B200_NO_GRAPH", "0") not in ("", "0") else
                            f"CUDA graphs replayed per query ({int(tm['kernel_launches'])} kernel nodes of this repo's kernels per query on rank 0)",
         }
+        if per_rank is not None:
+            out["per_rank"] = per_rank
         if e2e_seeded is not None:
             out["e2e_seeded"] = e2e_seeded
         if mg is not None:
