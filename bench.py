@@ -461,9 +461,11 @@ def main():
     if mine:
         for _ in range(args.warmup):
             step_resident()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # the barrier comes AFTER the sampler start (NVML initialisation takes a different time on every rank): ranks that
+    # split a PowersDag wait for each other inside the step, so a start skew would be billed to whoever started first
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     if mine:
