@@ -599,6 +599,24 @@ def main():
             "launch_mode": "eager" if os.environ.get("APSU_B200_NO_GRAPH", "0") not in ("", "0") else
                            f"CUDA graphs replayed per query ({int(tm['kernel_launches'])} kernel nodes of this repo's kernels per query on rank 0)",
         }
+        if world == 1:
+            # the integer-pipe side of the path: the transforms (49 % of the query) against the multiplier bound of their
+            # butterfly (436 quarter-rate + 494 half-rate multiplier instructions per 68 butterflies
+            # = 57 ns per N = 8192 polynomial on 148 SMs at 1965 MHz)
+            ntt = {}
+            for inv, key in ((0, "forward"), (1, "inverse")):
+                ms = C.c_float()
+                capi.check(lib.apsu_b200_bench_ntt(h, 2960, 20, inv, C.byref(ms)))
+                ntt[key] = ms.value * 1e6 / 2960
+            logn = N.bit_length() - 1
+            bound_ns = (N // 2 * logn) / 32 * (2732 / 68) / 4 / 148 / 1.965  # warp-butterflies x pipe cycles / sub-partitions / SMs / GHz
+            out["roofline_int"] = {
+                "kernel": "ntt_kernel (negacyclic NTT / iNTT, one RNS prime)", "bound": "int32 multiplier pipe (IMAD.WIDE quarter rate)",
+                "unit": "ns per polynomial", "achieved_forward": ntt["forward"], "achieved_inverse": ntt["inverse"], "bound_ns": bound_ns,
+                "frac": bound_ns / max(ntt["forward"], ntt["inverse"]),
+                "effective_gbs": 16 * N / min(ntt["forward"], ntt["inverse"]), "batch": "2960 polynomials per launch, 20 launches",
+                "source": "instruction mix from cuobjdump -sass (DESIGN.md §4); ncu: fmaheavy 65-71 % busy (profiles/ncu_r01_ntt_final_raw.csv); "
+                          "k_ks_mac / k_ks_moddown: profiles/ncu_r02_keyswitch_summary.json"}
         if per_rank is not None:
             out["per_rank"] = per_rank
         if e2e_seeded is not None:
