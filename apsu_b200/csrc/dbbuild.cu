@@ -187,7 +187,7 @@ void Engine::set_data(const uint64_t *felts, const uint64_t *cuckoo_idx, size_t 
     const uint32_t F = p.felts_per_item, ipb = p.items_per_bundle, bic = p.bundle_idx_count, table = p.table_size;
     const uint32_t cap = p.max_items_per_bin - 1;
     if (!felts || !cuckoo_idx) throw std::invalid_argument("set_data: items are null");
-    if (n >= (1ull << 32)) throw std::invalid_argument("set_data: too many items");
+    if (n >= (1ull << 31)) throw std::invalid_argument("set_data: too many items (item indices are 32-bit, the sort takes an int count)");
     if (p.max_items_per_bin < 2) throw std::invalid_argument("max_items_per_bin must be at least 2 to hold an item");
     if (ipb > 0xFFFF) throw std::invalid_argument("set_data: too many slots per bundle");
     clear_db();
