@@ -34,7 +34,7 @@ constexpr unsigned long long kNoCreation = ~0ull;
 
 // location (table slot) of every item + validation: the cuckoo index is the first bin of a slot
 __global__ void k_ff_keys(const u64 *__restrict__ cuckoo_idx, size_t n, u32 felts_per_item, u32 table_size, u32 *__restrict__ keys, u32 *__restrict__ vals,
-                          u32 *__restrict__ slot_count, int *__restrict__ bad)
+                          int *__restrict__ bad)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -46,7 +46,19 @@ __global__ void k_ff_keys(const u64 *__restrict__ cuckoo_idx, size_t n, u32 felt
     }
     keys[i] = (u32)loc;
     vals[i] = (u32)i;
-    atomicAdd(&slot_count[loc], 1u);
+}
+// slot_first[k] = number of items in slots below k = lower bound of k in the sorted keys (k = 0 .. table_size)
+__global__ void k_ff_slot_first(const u32 *__restrict__ sorted_keys, u32 n, u32 table_size, u32 *__restrict__ slot_first)
+{
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > table_size) return;
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        const u32 mid = lo + ((hi - lo) >> 1);
+        if (sorted_keys[mid] < k) lo = mid + 1;
+        else hi = mid;
+    }
+    slot_first[k] = lo;
 }
 
 struct FfState {
@@ -208,12 +220,11 @@ void Engine::set_data(const uint64_t *felts, const uint64_t *cuckoo_idx, size_t 
         d_cidx = d_cidx_own.p;
     }
     // ---- stable sort by slot ----
-    DBuf<uint32_t> keys, vals, keys2, arrivals, slot_count;
+    DBuf<uint32_t> keys, vals, keys2, arrivals, slot_first;
     DBuf<int> bad;
-    keys.alloc(n), vals.alloc(n), keys2.alloc(n), arrivals.alloc(n), slot_count.alloc(table + 1), bad.alloc(1);
-    APSU_CUDA_CHECK(cudaMemsetAsync(slot_count.p, 0, (table + 1) * 4, st));
+    keys.alloc(n), vals.alloc(n), keys2.alloc(n), arrivals.alloc(n), slot_first.alloc(table + 1), bad.alloc(1);
     APSU_CUDA_CHECK(cudaMemsetAsync(bad.p, 0, 4, st));
-    k_ff_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_cidx, n, F, table, keys.p, vals.p, slot_count.p, bad.p);
+    k_ff_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_cidx, n, F, table, keys.p, vals.p, bad.p);
     APSU_CUDA_CHECK(cudaGetLastError());
     int bits = 1;
     while ((1u << bits) < table) bits++;
@@ -222,19 +233,15 @@ void Engine::set_data(const uint64_t *felts, const uint64_t *cuckoo_idx, size_t 
     DBuf<unsigned char> tmp;
     tmp.alloc(tmp_bytes);
     APSU_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, vals.p, arrivals.p, (int)n, 0, bits, st));
-    std::vector<uint32_t> h_count(table + 1), h_first(table + 1);
+    k_ff_slot_first<<<(table + 1 + 255) / 256, 256, 0, st>>>(keys2.p, (u32)n, table, slot_first.p);
+    APSU_CUDA_CHECK(cudaGetLastError());
+    std::vector<uint32_t> h_count(table + 1, 0), h_first(table + 1);
     int h_bad = 0;
-    APSU_CUDA_CHECK(cudaMemcpyAsync(h_count.data(), slot_count.p, (table + 1) * 4, cudaMemcpyDeviceToHost, st));
+    APSU_CUDA_CHECK(cudaMemcpyAsync(h_first.data(), slot_first.p, (table + 1) * 4, cudaMemcpyDeviceToHost, st));
     APSU_CUDA_CHECK(cudaMemcpyAsync(&h_bad, bad.p, 4, cudaMemcpyDeviceToHost, st));
     APSU_CUDA_CHECK(cudaStreamSynchronize(st));
     if (h_bad) throw std::invalid_argument("set_data: a cuckoo index is not the first bin of a table slot");
-    uint32_t run = 0;
-    for (uint32_t k = 0; k <= table; k++) {
-        h_first[k] = run;
-        run += k < table ? h_count[k] : 0;
-    }
-    DBuf<uint32_t> slot_first;
-    slot_first.upload(h_first, st);
+    for (uint32_t k = 0; k < table; k++) h_count[k] = h_first[k + 1] - h_first[k];
     keys.release(), vals.release(), keys2.release(), tmp.release();
 
     DBuf<uint32_t> item_bundle, item_pos;

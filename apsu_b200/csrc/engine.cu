@@ -546,8 +546,7 @@ uint32_t Engine::add_binbundle_from_bins_device(uint32_t bundle_idx, const uint3
     }
     M.ensure((size_t)ncoeffs * N);
     enc.ensure((size_t)ncoeffs * N);
-    APSU_CUDA_CHECK(cudaMemsetAsync(M.p, 0, (size_t)ncoeffs * N * 8, ctx.stream));
-    APSU_CUDA_CHECK(cudaMemsetAsync(enc.p, 0, (size_t)ncoeffs * N * 8, ctx.stream));
+    APSU_CUDA_CHECK(cudaMemsetAsync(M.p, 0, (size_t)ncoeffs * N * 8, ctx.stream)); // (enc is written whole by the slot scatter)
     {
         // one warp per bin: registers for plain moduli below 2^30 and up to 2048 coefficients, shared memory otherwise
         const DMod mt = ctx.mod_host[ctx.idx_t];
