@@ -170,7 +170,7 @@ struct ProgramBuilder {
                 }
             }
         Engine *en = &e;
-        if (e.fuse_) {
+        if (e.fuse_ && ndst.size() <= e.fuse_max_) {
             // one launch: the transform of polynomial (rp, j) computes its own input (ntt.cuh: kNttExtend)
             size_t so = idx.add(esrc), dn = idx.add(ndst);
             const uint32_t count = (uint32_t)ndst.size();
@@ -203,7 +203,7 @@ struct ProgramBuilder {
         }
         size_t ao = idx.add(a), bo = idx.add(b), dof = idx.add(d), so = idx.add(ssrc), sd = idx.add(sdst);
         Engine *en = &e;
-        if (e.fuse_) {
+        if (e.fuse_ && (size_t)n_ops * 3 * LS <= e.fuse_max_) {
             // tensor product computed on the way into the inverse transform (ntt.cuh: kNttTensor)
             const std::vector<uint32_t> pat = ctx.pattern_ext(L);
             step([=] {
@@ -238,7 +238,7 @@ struct ProgramBuilder {
         ntt(nsrc, ndst, ctx.pattern_ks(L), false, /*reduce=*/true);
         size_t dg = idx.add(dig), ac = idx.add(acc), ct = idx.add(ct3), ds = idx.add(dst);
         Engine *en = &e;
-        if (e.fuse_) {
+        if (e.fuse_ && (size_t)n_ops * 2 * R <= e.fuse_max_) {
             // inner product with the keys computed on the way into the inverse transform (ntt.cuh: kNttKsMac)
             const std::vector<uint32_t> pat = ctx.pattern_ks(L);
             step([=] {
@@ -343,6 +343,7 @@ Engine::Engine(const apsu_b200_params &p, int device) : ctx(p, device)
     if (const char *ev = std::getenv("APSU_B200_NO_GRAPH")) use_graphs_ = atoi(ev) == 0;
     if (const char *ev = std::getenv("APSU_B200_CHUNK")) eval_chunk_ = (uint32_t)std::max(1, atoi(ev));
     if (const char *ev = std::getenv("APSU_B200_FUSE")) fuse_ = atoi(ev) != 0; // A/B: element-wise producers fused into the transforms
+    if (const char *ev = std::getenv("APSU_B200_FUSE_MAX")) fuse_max_ = (size_t)std::max(0, atoi(ev)); // ... for launches of at most this many polynomials
     for (auto &ev : ev_) APSU_CUDA_CHECK(cudaEventCreate(&ev));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
 }

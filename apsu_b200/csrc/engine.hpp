@@ -216,6 +216,7 @@ private:
     // SLOWER on B200 (16M-4096: 6.38 vs 5.88 ms per query; 256K-512: 0.224 vs 0.209 ms): the prologue runs at the
     // transform's low occupancy and costs a shared-memory pass more than the launch it saves.  Off unless APSU_B200_FUSE=1.
     bool fuse_ = false;
+    size_t fuse_max_ = ~size_t(0); // with fuse_: only launches of at most this many polynomials (the latency-bound ones)
     void run_steps(std::vector<Step> &prog, size_t lo, size_t hi, ProgGraph &g);
     void drop_graphs();
     void invalidate_plan()

@@ -264,7 +264,16 @@ __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) 
         from_smem = MODE != kNttPlain;
     }
     if (MODE != kNttPlain && from_smem) {
-        for (unsigned n = threadIdx.x; n < (unsigned)N; n += blockDim.x) sm[pad_idx(n)] = fused_input<MODE>(in, src, fuse, p, n, N, m);
+        // four elements per trip, all their loads issued before the first product: a lone CTA has nobody to hide a
+        // load round trip per element behind (N / blockDim is a multiple of 4 in every launch shape)
+        constexpr unsigned U = 4;
+        for (unsigned n0 = threadIdx.x; n0 < (unsigned)N; n0 += blockDim.x * U) {
+            u64 v[U];
+#pragma unroll
+            for (unsigned u = 0; u < U; u++) v[u] = fused_input<MODE>(in, src, fuse, p, n0 + u * blockDim.x, N, m);
+#pragma unroll
+            for (unsigned u = 0; u < U; u++) sm[pad_idx(n0 + u * blockDim.x)] = v[u];
+        }
         __syncthreads();
     }
 
