@@ -24,6 +24,9 @@
 #include "engine.hpp"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 namespace apsu_b200 {
@@ -202,7 +205,18 @@ void Engine::set_data(const uint64_t *felts, const uint64_t *cuckoo_idx, size_t 
     if (n >= (1ull << 31)) throw std::invalid_argument("set_data: too many items (item indices are 32-bit, the sort takes an int count)");
     if (p.max_items_per_bin < 2) throw std::invalid_argument("max_items_per_bin must be at least 2 to hold an item");
     if (ipb > 0xFFFF) throw std::invalid_argument("set_data: too many slots per bundle");
+    // APSU_B200_BUILD_TIMING=1: host-timed phases (with a stream synchronisation each) on stderr
+    const bool timing = std::getenv("APSU_B200_BUILD_TIMING") && atoi(std::getenv("APSU_B200_BUILD_TIMING"));
+    auto t_last = std::chrono::steady_clock::now();
+    auto phase = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(ctx.stream);
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[set_data] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     clear_db();
+    phase("clear_db (frees)");
     cudaStream_t st = ctx.stream;
     if (!n) {
         if (bundle_counts) std::fill(bundle_counts, bundle_counts + bic, 0u);
@@ -243,6 +257,7 @@ void Engine::set_data(const uint64_t *felts, const uint64_t *cuckoo_idx, size_t 
     if (h_bad) throw std::invalid_argument("set_data: a cuckoo index is not the first bin of a table slot");
     for (uint32_t k = 0; k < table; k++) h_count[k] = h_first[k + 1] - h_first[k];
     keys.release(), vals.release(), keys2.release(), tmp.release();
+    phase("upload + sort by slot");
 
     DBuf<uint32_t> item_bundle, item_pos;
     item_bundle.alloc(n), item_pos.alloc(n);
@@ -289,6 +304,7 @@ void Engine::set_data(const uint64_t *felts, const uint64_t *cuckoo_idx, size_t 
             if (!overflow) break;
             max_bundles *= 2;
         }
+        phase("first-fit windows");
         // ---- every item's BinBundle and position; counts are rebuilt by the replay ----
         APSU_CUDA_CHECK(cudaMemsetAsync(counts.p, 0, (size_t)max_bundles * ipb * 4, st));
         FfState fs{ arrivals.p, slot_first.p, start.p, counts.p, creation.p, slot0, ipb, cap, max_bundles };
@@ -320,11 +336,13 @@ void Engine::set_data(const uint64_t *felts, const uint64_t *cuckoo_idx, size_t 
         k_ff_scatter<<<(unsigned)((n_b + 255) / 256), 256, 0, st>>>(d_felts, arrivals.p, item_bundle.p, item_pos.p, slot_first.p, slot0, ipb, F, bin_first.p,
                                                                    bundle_base.p, roots.p);
         APSU_CUDA_CHECK(cudaGetLastError());
+        phase("assign + scatter");
         // ---- BinBundle::regen_cache for each of them (engine.cu), asynchronous ----
         for (uint32_t c = 0; c < B; c++)
             add_binbundle_from_bins_device(b, bin_first.p + (size_t)c * nbins, bin_size.p + (size_t)c * nbins, roots.p + h_base[c], max_deg[c]);
         if (bundle_counts) bundle_counts[b] = B;
         APSU_CUDA_CHECK(cudaStreamSynchronize(st)); // the tables above go out of scope
+        phase("BinBundle caches");
     }
     throw_if_build_invalid();
 }
