@@ -57,10 +57,15 @@ def test_two_gpu_query_matches_oracle(name, degrees, dag_split, expect_group):
                 masks[b + lc * bic] = sc.masks[b + c * bic]
             mg = MultiGpu(db, uid, r, world)
             info = mg.commit(gidx, dag_split)
-            out = None
-            for _ in range(2):  # twice: the second query replays the captured graphs and reuses the staging buffers
-                out = mg.run_query(sc.src_powers, sc.cts if r == 0 else None, sc.relin if r == 0 else None, masks)
-            return info, out
+            outs = []
+            for shared in (False, False, True):  # twice: the second query replays the captured graphs and reuses the staging
+                # buffers; then the shared-query call: every rank reads the query and uploads its own part
+                have = shared or r == 0
+                outs.append(mg.run_query(sc.src_powers, sc.cts if have else None, sc.relin if have else None, masks, shared=shared))
+            if r == 0:
+                for k in range(3):
+                    assert np.array_equal(outs[0][k], outs[2][k])  # results and indices of the scattered and the shared call
+            return info, outs[1]
         finally:
             if mg is not None:
                 mg.close()

@@ -1,12 +1,7 @@
-python - <<'PY'
-import os, sys, json, time
-os.environ["APSU_B200_BUILD_TIMING"]="1"
-sys.path.insert(0,'.')
-import bench, apsu_b200, torch
-pj=bench.load_params_json("16M-4096")
-params=apsu_b200.PSUParams.Load(json.dumps(pj))
-for i in range(2):
-    print("---- run", i, flush=True)
-    r=bench.full_db_build_measure(pj, params, 0, 24)
-    print({k:r[k] for k in ("ms","ms_first","bin_bundles")}, flush=True)
-PY
+python -m pytest tests/test_gpu_multi.py -q -s 2>&1 | grep -E "info|passed|failed|Error|error" | tail -12
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2e_n2.json 2> gpurun_out/r2e_n2.err
+python -c "
+import json
+j=json.loads(open('gpurun_out/r2e_n2.json').read().strip().splitlines()[-1])
+print(round(j['ms_per_step'],3), j['e2e']['ms_per_step'], j['e2e_root_scatter']['ms_per_step'], j.get('parity_sample',{}).get('bit_exact_vs_oracle'), j.get('results_sha256_matches_n1_record'), j.get('INVALID'))
+"
