@@ -21,11 +21,14 @@
 //   KSwitchKeys members: parms_id u64[4] | keys_dim1 u64 | per row: keys_dim2 u64 | per key: PublicKey (own SEALHeader |
 //                       Ciphertext members)
 //   parms_id = BLAKE2b-256 over the u64 words [scheme (bfv = 1), poly_modulus_degree, coeff_modulus..., plain_modulus]
-// Compression: only compr_mode none is decoded here; SEAL's default when built with zstd is zstd — ask the sender for
-// compr_mode_type::none or inflate before calling (the frames are standard zlib / zstd streams after the header).
+// Compression (SEAL's default when built with zstd — the vcpkg port APSU uses — is compr_mode_type::zstd): an object saved
+// compressed is its SEALHeader followed by ONE zstd frame / zlib stream of the uncompressed members (nested objects inside
+// are saved uncompressed).  The decoders are bound at run time (dlopen of libzstd.so.1 / libz.so.1), so this header has no
+// link-time dependency beyond -ldl; without the library a compressed object raises std::runtime_error.
 // FlatBuffers: a read-only table walker and a writer for the one ResultPackage layout, following the FlatBuffers
 // binary format (tables with vtables, little-endian uoffset32).
 #pragma once
+#include <dlfcn.h>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -157,7 +160,8 @@ struct SEALHeader {
     std::uint8_t version_major = 3, version_minor = 7, compr_mode = 0;
     std::uint64_t size = 0;
 };
-inline SEALHeader read_header(Reader &r)
+// header only; compr_mode is returned, not judged (nested objects must be uncompressed: see read_plain_header)
+inline SEALHeader read_any_header(Reader &r)
 {
     if (r.u16() != 0xA15E) throw std::runtime_error("seal_wire: bad SEALHeader magic");
     if (r.u8() != 0x10) throw std::runtime_error("seal_wire: bad SEALHeader size");
@@ -167,8 +171,102 @@ inline SEALHeader read_header(Reader &r)
     h.compr_mode = r.u8();
     r.u16();
     h.size = r.u64();
-    if (h.compr_mode != 0) throw std::runtime_error("seal_wire: compressed SEAL object (compr_mode != none); inflate it first or have the sender use compr_mode_type::none");
+    if (h.compr_mode > 2) throw std::runtime_error("seal_wire: unknown compr_mode");
     return h;
+}
+inline SEALHeader read_header(Reader &r)
+{
+    SEALHeader h = read_any_header(r);
+    if (h.compr_mode != 0) throw std::runtime_error("seal_wire: nested SEAL object is compressed");
+    return h;
+}
+
+// zstd frame / zlib stream -> bytes, with the system libraries bound at run time
+inline bytes inflate(std::uint8_t compr_mode, const std::uint8_t *p, std::size_t n)
+{
+    if (compr_mode == 2) {
+        static void *so = dlopen("libzstd.so.1", RTLD_NOW);
+        if (!so) throw std::runtime_error("seal_wire: zstd-compressed SEAL object and libzstd.so.1 is not available");
+        using init_t = void *(*)();
+        using free_t = std::size_t (*)(void *);
+        struct Buf {
+            const void *src;
+            std::size_t size, pos;
+        };
+        struct OBuf {
+            void *dst;
+            std::size_t size, pos;
+        };
+        using step_t = std::size_t (*)(void *, OBuf *, Buf *);
+        using iserr_t = unsigned (*)(std::size_t);
+        static auto create = reinterpret_cast<init_t>(dlsym(so, "ZSTD_createDStream"));
+        static auto destroy = reinterpret_cast<free_t>(dlsym(so, "ZSTD_freeDStream"));
+        static auto step = reinterpret_cast<step_t>(dlsym(so, "ZSTD_decompressStream"));
+        static auto iserr = reinterpret_cast<iserr_t>(dlsym(so, "ZSTD_isError"));
+        if (!create || !destroy || !step || !iserr) throw std::runtime_error("seal_wire: libzstd lacks the streaming API");
+        void *ds = create();
+        if (!ds) throw std::runtime_error("seal_wire: ZSTD_createDStream failed");
+        bytes out;
+        Buf in{ p, n, 0 };
+        std::vector<std::uint8_t> chunk(1 << 20);
+        for (;;) {
+            OBuf ob{ chunk.data(), chunk.size(), 0 };
+            const std::size_t rc = step(ds, &ob, &in);
+            if (iserr(rc)) {
+                destroy(ds);
+                throw std::runtime_error("seal_wire: zstd stream is corrupt");
+            }
+            out.insert(out.end(), chunk.begin(), chunk.begin() + (std::ptrdiff_t)ob.pos);
+            if (rc == 0 && in.pos == in.size) break;                 // frame complete, input consumed
+            if (in.pos == in.size && ob.pos == 0) {                  // input exhausted inside a frame
+                destroy(ds);
+                throw std::runtime_error("seal_wire: zstd stream is truncated");
+            }
+        }
+        destroy(ds);
+        return out;
+    }
+    if (compr_mode == 1) {
+        static void *so = dlopen("libz.so.1", RTLD_NOW);
+        if (!so) throw std::runtime_error("seal_wire: zlib-compressed SEAL object and libz.so.1 is not available");
+        using unc_t = int (*)(unsigned char *, unsigned long *, const unsigned char *, unsigned long);
+        static auto unc = reinterpret_cast<unc_t>(dlsym(so, "uncompress"));
+        if (!unc) throw std::runtime_error("seal_wire: libz lacks uncompress");
+        for (std::size_t cap = n * 4 + 4096;; cap *= 2) { // Z_BUF_ERROR (-5): output too small
+            bytes out(cap);
+            unsigned long len = (unsigned long)cap;
+            const int rc = unc(out.data(), &len, p, (unsigned long)n);
+            if (rc == 0) {
+                out.resize(len);
+                return out;
+            }
+            if (rc != -5 || cap > (std::size_t(1) << 33)) throw std::runtime_error("seal_wire: zlib stream is corrupt");
+        }
+    }
+    return bytes(p, p + n);
+}
+// Opens a top-level SEAL object: consumes its header and hands back the uncompressed members (a copy when it was compressed)
+struct OpenedObject {
+    SEALHeader header;
+    bytes storage;              // holds the inflated members when the object was compressed
+    const std::uint8_t *p = nullptr;
+    std::size_t n = 0;
+};
+inline OpenedObject open_object(const std::uint8_t *buf, std::size_t len)
+{
+    Reader r(buf, len);
+    OpenedObject o;
+    o.header = read_any_header(r);
+    if (o.header.size > len || o.header.size < 16) throw std::runtime_error("seal_wire: SEAL object is truncated");
+    if (o.header.compr_mode) {
+        o.storage = inflate(o.header.compr_mode, buf + 16, (std::size_t)o.header.size - 16);
+        o.p = o.storage.data();
+        o.n = o.storage.size();
+    } else {
+        o.p = buf + 16;
+        o.n = (std::size_t)o.header.size - 16;
+    }
+    return o;
 }
 inline void write_header(bytes &o, std::uint64_t total_size, std::uint8_t vmaj = 3, std::uint8_t vmin = 7)
 {
@@ -220,11 +318,10 @@ inline Ciphertext read_ciphertext_members(Reader &r)
 }
 inline Ciphertext read_ciphertext(const std::uint8_t *p, std::size_t n, std::size_t *consumed = nullptr)
 {
-    Reader r(p, n);
-    SEALHeader h = read_header(r);
-    if (h.size > n) throw std::runtime_error("seal_wire: ciphertext is truncated");
+    OpenedObject o = open_object(p, n);
+    Reader r(o.p, o.n);
     Ciphertext c = read_ciphertext_members(r);
-    if (consumed) *consumed = (std::size_t)h.size;
+    if (consumed) *consumed = (std::size_t)o.header.size;
     return c;
 }
 // Ciphertext::save (compr_mode none) of a fully expanded ciphertext
@@ -257,8 +354,8 @@ struct RelinKeys {
 };
 inline RelinKeys read_relin_keys(const std::uint8_t *p, std::size_t n)
 {
-    Reader r(p, n);
-    read_header(r);
+    OpenedObject o = open_object(p, n);
+    Reader r(o.p, o.n);
     RelinKeys k;
     r.words(k.parms_id.data(), 4);
     const std::uint64_t dim1 = r.u64();

@@ -34,9 +34,37 @@ static bytes seeded_blob(const Ciphertext &full, const std::array<std::uint8_t, 
     return b;
 }
 
-int main()
+#include <fstream>
+#include <iterator>
+static bytes slurp(const char *path)
+{
+    std::ifstream f(path, std::ios::binary);
+    return bytes(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+}
+
+// `test_wire dump <file>`: writes the uncompressed reference ciphertext object; `test_wire check <file>...`: every file
+// must parse (whatever its compr_mode) to that ciphertext.  No arguments: the self-contained round trips.
+int main(int argc, char **argv)
 {
     const std::uint64_t N = 64, L = 3;
+    if (argc >= 3 && std::string(argv[1]) == "dump") {
+        bytes b = write_ciphertext(make_ct(N, L, 2, 1));
+        std::ofstream(argv[2], std::ios::binary).write(reinterpret_cast<const char *>(b.data()), (std::streamsize)b.size());
+        return 0;
+    }
+    if (argc >= 3 && std::string(argv[1]) == "check") {
+        Ciphertext ref = make_ct(N, L, 2, 1);
+        for (int i = 2; i < argc; i++) {
+            bytes b = slurp(argv[i]);
+            Ciphertext c = read_ciphertext(b.data(), b.size());
+            if (c.data != ref.data || c.parms_id != ref.parms_id || c.size != 2) {
+                std::printf("mismatch in %s\n", argv[i]);
+                return 1;
+            }
+            std::printf("parsed %s compr_mode=%d\n", argv[i], (int)b[5]);
+        }
+        return 0;
+    }
     auto id = parms_id(8192, { 0xfffffffff70001ULL, 0xfffffffff78001ULL, 0xfffffffffb4001ULL, 0x3ffffffffc001ULL }, 4079617);
     std::printf("parms_id=%016llx,%016llx,%016llx,%016llx\n", (unsigned long long)id[0], (unsigned long long)id[1], (unsigned long long)id[2],
                 (unsigned long long)id[3]);

@@ -213,10 +213,52 @@ def test_seal_wire_formats(tmp_path):
     import hashlib
     import struct
     exe = tmp_path / "test_wire"
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-o", str(exe), str(ROOT / "tests" / "cpp" / "test_wire.cpp")])
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-o", str(exe), str(ROOT / "tests" / "cpp" / "test_wire.cpp"), "-ldl"])
     out = subprocess.check_output([str(exe)], text=True)
     assert "ok=1" in out
     words = [1, 8192, 0xfffffffff70001, 0xfffffffff78001, 0xfffffffffb4001, 0x3ffffffffc001, 4079617]
     d = hashlib.blake2b(struct.pack("<7Q", *words), digest_size=32).digest()
     assert "parms_id=" + ",".join("%016x" % x for x in struct.unpack("<4Q", d)) in out
     assert f"ct_bytes={16 + 32 + 1 + 5 * 8 + 16 + 8 + 2 * 3 * 64 * 8}" in out
+
+
+def test_seal_wire_compressed_objects(tmp_path):
+    """SEAL's default compr_mode when built with zstd (the vcpkg port APSU uses) is zstd: a compressed object is its
+    SEALHeader + one zstd frame / zlib stream of the members.  seal_wire.hpp inflates both through the system libraries
+    (dlopen); the compressed inputs are made here with Python's zlib and with libzstd through ctypes."""
+    import ctypes
+    import struct
+    import zlib
+    exe = tmp_path / "test_wire"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", str(exe), str(ROOT / "tests" / "cpp" / "test_wire.cpp"), "-ldl"])
+    plain = tmp_path / "ct_none.bin"
+    subprocess.check_call([str(exe), "dump", str(plain)])
+    raw = plain.read_bytes()
+    members = raw[16:]
+
+    def wrap(mode, payload):
+        return raw[:5] + bytes([mode]) + raw[6:8] + struct.pack("<Q", 16 + len(payload)) + payload
+
+    files = [plain]
+    z = tmp_path / "ct_zlib.bin"
+    z.write_bytes(wrap(1, zlib.compress(members)))
+    files.append(z)
+    try:
+        zs = ctypes.CDLL("libzstd.so.1")
+    except OSError:
+        zs = None
+    if zs is not None:
+        zs.ZSTD_compressBound.restype = ctypes.c_size_t
+        zs.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+        zs.ZSTD_compress.restype = ctypes.c_size_t
+        zs.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        cap = zs.ZSTD_compressBound(len(members))
+        dst = ctypes.create_string_buffer(cap)
+        n = zs.ZSTD_compress(dst, cap, members, len(members), 3)
+        assert not zs.ZSTD_isError(n)
+        f = tmp_path / "ct_zstd.bin"
+        f.write_bytes(wrap(2, dst.raw[:n]))
+        files.append(f)
+    out = subprocess.check_output([str(exe), "check"] + [str(f) for f in files], text=True)
+    assert out.count("parsed") == len(files) and "compr_mode=1" in out
+    assert zs is None or "compr_mode=2" in out
