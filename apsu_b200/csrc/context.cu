@@ -264,9 +264,9 @@ static void launch_ntt_shape(const u64 *in, u64 *out, uint32_t count, const NttA
     constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4)) + (TWS ? (size_t)16 << LOGN : 0);
     // the forward transform fuses kNttExtend, the inverse one kNttTensor / kNttKsMac (ntt.cuh)
     if (inverse) {
-        if constexpr (MODE != kNttExtend) ntt_kernel<LOGN, false, DIV, MODE, TWS><<<count, threads, smem, st>>>(in, out, a, s, f);
+        if constexpr (MODE != kNttExtend) launch_pdl(ntt_kernel<LOGN, false, DIV, MODE, TWS>, dim3(count), dim3(threads), smem, st, in, out, a, s, f);
     } else {
-        if constexpr (MODE == kNttPlain || MODE == kNttExtend) ntt_kernel<LOGN, true, DIV, MODE, TWS><<<count, threads, smem, st>>>(in, out, a, s, f);
+        if constexpr (MODE == kNttPlain || MODE == kNttExtend) launch_pdl(ntt_kernel<LOGN, true, DIV, MODE, TWS>, dim3(count), dim3(threads), smem, st, in, out, a, s, f);
     }
 }
 
@@ -282,6 +282,36 @@ static void configure_ntt_shape()
     APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV, kNttTensor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, DIV, kNttKsMac>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
+// split transforms (ntt.cuh: ntt_split_kernel): 2^LC CTAs (one cluster) per polynomial
+template <int LOGN, int LC>
+static void launch_ntt_split(const u64 *in, u64 *out, uint32_t count, const NttArgs &a, const NttSrc &s, bool inverse, cudaStream_t st)
+{
+    constexpr int LOGM = LOGN - LC, DIV = 8, threads = (1 << LOGM) / DIV;
+    constexpr size_t smem = (sizeof(u64) << LOGM) + (sizeof(u64) << (LOGM - 4));
+    if (inverse)
+        launch_pdl(ntt_split_kernel<LOGN, LC, false, DIV>, dim3(count << LC), dim3(threads), smem, st, in, out, a, s);
+    else
+        launch_pdl(ntt_split_kernel<LOGN, LC, true, DIV>, dim3(count << LC), dim3(threads), smem, st, in, out, a, s);
+}
+template <int LOGN, int LC>
+static void configure_ntt_split()
+{
+    constexpr int LOGM = LOGN - LC;
+    constexpr size_t smem = (sizeof(u64) << LOGM) + (sizeof(u64) << (LOGM - 4));
+    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_split_kernel<LOGN, LC, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_split_kernel<LOGN, LC, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+// APSU_B200_NTT_SPLIT: unset = by batch size (launch_ntt); 0 = never; 2 / 4 = that many CTAs per polynomial whatever
+// the batch size (A/B runs, tools/bench_ntt.py)
+static int ntt_split_mode()
+{
+    static const int mode = [] {
+        const char *ev = std::getenv("APSU_B200_NTT_SPLIT");
+        return ev ? atoi(ev) : -1;
+    }();
+    return mode;
+}
+
 constexpr bool ntt_tws_fits(int logn) { return logn <= 13; } // 69.6 + 128 KB at N = 8192
 template <int LOGN>
 static void configure_ntt()
@@ -289,11 +319,26 @@ static void configure_ntt()
     constexpr int kLatDiv = (LOGN == 12 || LOGN == 13) ? 8 : 16;
     configure_ntt_shape<LOGN, kLatDiv>();
     configure_ntt_shape<LOGN, 32>();
+    configure_ntt_split<LOGN, 1>();
+    configure_ntt_split<LOGN, 2>();
     if constexpr (ntt_tws_fits(LOGN)) {
         constexpr size_t smem = (sizeof(u64) << LOGN) + (sizeof(u64) << (LOGN - 4)) + ((size_t)16 << LOGN);
         APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, true, kLatDiv, kNttPlain, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         APSU_CUDA_CHECK(cudaFuncSetAttribute(ntt_kernel<LOGN, false, kLatDiv, kNttPlain, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+}
+
+bool pdl_enabled()
+{
+    // measured on B200 with the launch sequences replayed as CUDA graphs (profiles/bench_r02_pdl_ab.json): 16M-4096
+    // 5.91 -> 5.93 ms, 1M-4096-com 1.66 -> 1.70, 256K-512 0.213 -> 0.227, 1M-1024-cmp 0.729 -> 0.689: a graph's
+    // kernel-to-kernel edges leave nothing for the programmatic edge to hide, so it is off by default
+    // (APSU_B200_PDL=1 for A/B runs; results are bit-identical either way)
+    static const bool on = [] {
+        const char *ev = std::getenv("APSU_B200_PDL");
+        return ev ? atoi(ev) != 0 : false;
+    }();
+    return on;
 }
 
 static int ntt_tws_mode()
@@ -315,6 +360,23 @@ static void launch_ntt(const u64 *in, u64 *out, uint32_t count, const NttArgs &a
     // measured (N = 8192, one bundle index): 24..112 polynomials take 16 us with N/8 threads and 20-22 us with N/32;
     // N/16 threads for 150..300 polynomials made no difference
     constexpr int kLatDiv = (LOGN == 12 || LOGN == 13) ? 8 : 16; // at most 1024 threads per CTA
+    if constexpr (MODE == kNttPlain) {
+        const int split = ntt_split_mode();
+        // measured (tools/bench_ntt.py, profiles/ntt_split_r02.jsonl; N = 8192 forward, 24 / 42 / 84 polynomials: 16.4 us
+        // unsplit, 10.3 / 10.3 / 16.4 us two ways, 8.3 / 10.3 / 14.4 us four ways): a slice costs its share of ONE SM's
+        // multiplier time, so splitting pays only while the slices still find idle SMs.  The inverse is never split by
+        // default: its stride-C stores are partial-sector writes (15.5 -> 14.4 us at 24 polynomials, slower from 42 on).
+        const bool four = split == 4 || (split < 0 && !inverse && LOGN >= 13 && (uint64_t)count * 4 <= (uint64_t)sms);
+        const bool two = split == 2 || (split < 0 && !inverse && (uint64_t)count * 2 <= (uint64_t)sms);
+        if (four) {
+            launch_ntt_split<LOGN, 2>(in, out, count, a, s, inverse, st);
+            return;
+        }
+        if (two) {
+            launch_ntt_split<LOGN, 1>(in, out, count, a, s, inverse, st);
+            return;
+        }
+    }
     if (count <= (uint32_t)sms * ntt_min_blocks(LOGN, kLatDiv)) {
         if constexpr (MODE == kNttPlain && ntt_tws_fits(LOGN)) {
             // a batch of at most one CTA per SM: twiddles staged in shared memory (one CTA per SM at N = 8192)

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace apsu_b200 {
@@ -20,6 +21,27 @@ struct CudaError : std::runtime_error {
         if (e__ != cudaSuccess)                                                                                        \
             throw ::apsu_b200::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__));                         \
     } while (0)
+
+// Kernel launch with a programmatic (PDL) edge to the preceding kernel of the stream: the kernel may be scheduled
+// while its predecessor is still running and waits for it in pdl_enter() (modarith.cuh) — ONLY for kernels that call
+// pdl_enter() before touching memory.  Inside stream capture the edge becomes a programmatic graph dependency.
+// Off unless APSU_B200_PDL=1 (measured: no gain under graph replay, context.cu pdl_enabled).
+bool pdl_enabled();
+template <typename... P, typename... A>
+inline void launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    APSU_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...));
+}
 
 // simple owning device buffer
 template <typename T>

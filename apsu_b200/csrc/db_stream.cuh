@@ -204,6 +204,7 @@ template <int STAGES, int MINB>
 __global__ void __launch_bounds__(kKtThreads, MINB)
 k_db_mac_kt(u64 *A, const KtGroup *__restrict__ groups, u32 n_groups, LevelConsts c, int N, int split, u32 fold_stages, u32 zero)
 {
+    pdl_enter();
     extern __shared__ __align__(128) u64 smem[];
     u64 *ring = smem;                              // [stage][kKtStageWords]
     u64 *full = smem + STAGES * kKtStageWords;     // [stage]
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(128) k_pack_tile(const u64 *__restrict__ src, 
 // grid (L*N/128, T*2, tables), block 128; table z: sources src[z*T*2 ..], destination arena index dst_idx[z]
 __global__ void __launch_bounds__(128) k_pack_powers(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst_idx, u32 T, int N, int split)
 {
+    pdl_enter();
     const u32 tile = blockIdx.x, tc = blockIdx.y, z = blockIdx.z, c = threadIdx.x;
     const size_t col = (size_t)tile * kKtCols + c; // l*N + n: consecutive primes are consecutive polynomials
     u64 *dst = A + (size_t)dst_idx[z] * N;

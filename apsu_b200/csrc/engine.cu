@@ -23,38 +23,38 @@ namespace apsu_b200 {
     } while (0)
 
 // specialised (|q|, |Bsk|) instances of the BEHZ kernels; anything else runs the generic <0,0> instance
-#define APSU_DISPATCH_LS(KERN, L, S, ...)                                                                              \
+#define APSU_DISPATCH_LS(KERN, L, S, GRID, ...)                                                                        \
     do {                                                                                                               \
-        if ((L) == 1 && (S) == 2) KERN<1, 2> __VA_ARGS__;                                                              \
-        else if ((L) == 2 && (S) == 3) KERN<2, 3> __VA_ARGS__;                                                         \
-        else if ((L) == 3 && (S) == 4) KERN<3, 4> __VA_ARGS__;                                                         \
-        else if ((L) == 4 && (S) == 5) KERN<4, 5> __VA_ARGS__;                                                         \
-        else KERN<0, 0> __VA_ARGS__;                                                                                   \
+        if ((L) == 1 && (S) == 2) launch_pdl(KERN<1, 2>, GRID, dim3(kEwThreads), 0, ctx.stream, __VA_ARGS__);          \
+        else if ((L) == 2 && (S) == 3) launch_pdl(KERN<2, 3>, GRID, dim3(kEwThreads), 0, ctx.stream, __VA_ARGS__);     \
+        else if ((L) == 3 && (S) == 4) launch_pdl(KERN<3, 4>, GRID, dim3(kEwThreads), 0, ctx.stream, __VA_ARGS__);     \
+        else if ((L) == 4 && (S) == 5) launch_pdl(KERN<4, 5>, GRID, dim3(kEwThreads), 0, ctx.stream, __VA_ARGS__);     \
+        else launch_pdl(KERN<0, 0>, GRID, dim3(kEwThreads), 0, ctx.stream, __VA_ARGS__);                               \
     } while (0)
 
 void Engine::run_extend(uint32_t L, uint32_t n, const uint32_t *src, const uint32_t *dst)
 {
     if (!n) return;
-    APSU_DISPATCH_LS(k_behz_extend, L, (uint32_t)ctx.level[L].S, <<<dim3(ctx.N / kEwThreads, n), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N));
+    APSU_DISPATCH_LS(k_behz_extend, L, (uint32_t)ctx.level[L].S, dim3(ctx.N / kEwThreads, n), arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N);
     APSU_LAUNCH_CHECK();
 }
 void Engine::run_tensor(uint32_t L, uint32_t n_ops, const uint32_t *a, const uint32_t *b, const uint32_t *d)
 {
     if (!n_ops) return;
     const LevelConsts &c = ctx.level[L];
-    k_tensor<<<dim3(ctx.N / kEwThreads, c.L + c.S, n_ops), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, a, b, d, c, (int)ctx.N);
+    launch_pdl(k_tensor, dim3(ctx.N / kEwThreads, c.L + c.S, n_ops), dim3(kEwThreads), 0, ctx.stream, arena_.buf.p, a, b, d, c, (int)ctx.N);
     APSU_LAUNCH_CHECK();
 }
 void Engine::run_scale_down(uint32_t L, uint32_t n, const uint32_t *src, const uint32_t *dst)
 {
     if (!n) return;
-    APSU_DISPATCH_LS(k_behz_scale_down, L, (uint32_t)ctx.level[L].S, <<<dim3(ctx.N / kEwThreads, n), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N));
+    APSU_DISPATCH_LS(k_behz_scale_down, L, (uint32_t)ctx.level[L].S, dim3(ctx.N / kEwThreads, n), arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N);
     APSU_LAUNCH_CHECK();
 }
 void Engine::run_ks_mac(uint32_t L, uint32_t n_ops, const uint32_t *dig, const uint32_t *out)
 {
     if (!n_ops) return;
-    k_ks_mac<<<dim3(ctx.N / kEwThreads, L + 1, n_ops * 2), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, dig, out, relin_keys_.p, ctx.ks[L], (int)ctx.N);
+    launch_pdl(k_ks_mac, dim3(ctx.N / kEwThreads, L + 1, n_ops * 2), dim3(kEwThreads), 0, ctx.stream, arena_.buf.p, dig, out, (const u64 *)relin_keys_.p, ctx.ks[L], (int)ctx.N);
     APSU_LAUNCH_CHECK();
 }
 void Engine::run_ks_moddown(uint32_t L, uint32_t n_ops, const uint32_t *acc, const uint32_t *ct, const uint32_t *dst, bool mirror)
@@ -65,9 +65,9 @@ void Engine::run_ks_moddown(uint32_t L, uint32_t n_ops, const uint32_t *acc, con
     if (mirror && p2p_.enabled) {
         for (size_t k = 0; k < p2p_.arena.size(); k++)
             if ((int)k != p2p_.me) pa.base[pa.n++] = p2p_.arena[k];
-        k_ks_moddown<true><<<dim3(ctx.N / kEwThreads, 2, n_ops), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, acc, ct, dst, ctx.ks[L], (int)ctx.N, pa);
+        launch_pdl(k_ks_moddown<true>, dim3(ctx.N / kEwThreads, 2, n_ops), dim3(kEwThreads), 0, ctx.stream, arena_.buf.p, acc, ct, dst, ctx.ks[L], (int)ctx.N, pa);
     } else {
-        k_ks_moddown<false><<<dim3(ctx.N / kEwThreads, 2, n_ops), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, acc, ct, dst, ctx.ks[L], (int)ctx.N, pa);
+        launch_pdl(k_ks_moddown<false>, dim3(ctx.N / kEwThreads, 2, n_ops), dim3(kEwThreads), 0, ctx.stream, arena_.buf.p, acc, ct, dst, ctx.ks[L], (int)ctx.N, pa);
     }
     APSU_LAUNCH_CHECK();
 }
@@ -116,7 +116,7 @@ void Engine::set_powers_p2p(const std::vector<u64 *> &arenas, const std::vector<
 void Engine::run_mod_switch_next(uint32_t L, uint32_t n, const uint32_t *src, const uint32_t *dst)
 {
     if (!n) return;
-    k_mod_switch_next<<<dim3(ctx.N / kEwThreads, n), kEwThreads, 0, ctx.stream>>>(arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N);
+    launch_pdl(k_mod_switch_next, dim3(ctx.N / kEwThreads, n), dim3(kEwThreads), 0, ctx.stream, arena_.buf.p, src, dst, ctx.level[L], (int)ctx.N);
     APSU_LAUNCH_CHECK();
 }
 
@@ -271,8 +271,8 @@ struct ProgramBuilder {
         uint32_t nz = (uint32_t)dst.size();
         Engine *en = &e;
         step([=] {
-            k_pack_powers<<<dim3(L * en->ctx.N / kKtCols, T * 2, nz), kKtCols, 0, en->ctx.stream>>>(en->arena_.buf.p, en->idx_.at(so), en->idx_.at(dn), T,
-                                                                                                  (int)en->ctx.N, en->split_);
+            launch_pdl(k_pack_powers, dim3(L * en->ctx.N / kKtCols, T * 2, nz), dim3(kKtCols), 0, en->ctx.stream, en->arena_.buf.p, (const u32 *)en->idx_.at(so),
+                       (const u32 *)en->idx_.at(dn), T, (int)en->ctx.N, en->split_);
             APSU_CUDA_CHECK(cudaGetLastError());
             en->ctx.launches++;
         });
@@ -293,8 +293,8 @@ struct ProgramBuilder {
         uint32_t n = (uint32_t)dst.size();
         Engine *en = &e;
         step([=] {
-            k_sum_polys<<<dim3(en->ctx.N / kEwThreads, L, n), kEwThreads, 0, en->ctx.stream>>>(
-                en->arena_.buf.p, en->idx_.at(fo), en->idx_.at(fi), en->idx_.at(cn), en->idx_.at(ds), en->ctx.level[L], (int)en->ctx.N);
+            launch_pdl(k_sum_polys, dim3(en->ctx.N / kEwThreads, L, n), dim3(kEwThreads), 0, en->ctx.stream, en->arena_.buf.p, (const u32 *)en->idx_.at(fo),
+                       (const u32 *)en->idx_.at(fi), (const u32 *)en->idx_.at(cn), (const u32 *)en->idx_.at(ds), en->ctx.level[L], (int)en->ctx.N);
             APSU_CUDA_CHECK(cudaGetLastError());
             en->ctx.launches++;
         });
@@ -1266,8 +1266,8 @@ void Engine::build_plan()
                     }
                     size_t so = idx_.add(sum_idx), lo = idx_.add(last_idx), dn = idx_.add(dst_idx);
                     pb.step([=] {
-                        k_ms_sum_last<<<dim3(ctx.N / kEwThreads, 2, nb), kEwThreads, 0, ctx.stream>>>(
-                            arena_.buf.p, idx_.at(so), idx_.at(lo), idx_.at(dn), ps, ctx.level[Ll], (int)ctx.N);
+                        launch_pdl(k_ms_sum_last, dim3(ctx.N / kEwThreads, 2, nb), dim3(kEwThreads), 0, ctx.stream, arena_.buf.p, (const u32 *)idx_.at(so),
+                                   (const u32 *)idx_.at(lo), (const u32 *)idx_.at(dn), ps, ctx.level[Ll], (int)ctx.N);
                         APSU_CUDA_CHECK(cudaGetLastError());
                         ctx.launches++;
                     });
@@ -1483,7 +1483,7 @@ void Engine::emit_mac(ProgramBuilder &pb, uint32_t L, std::vector<KtGroup> &grou
         const uint32_t items = n * (L * ctx.N / kKtCols);
         const uint32_t waves = (items + kt_grid_cap_ - 1) / kt_grid_cap_;
         const uint32_t grid = (items + waves - 1) / waves;
-        kern<<<grid, kKtThreads, smem, ctx.stream>>>(arena_.buf.p, gd, n, ctx.level[L], (int)ctx.N, split_, fold_stages_, 0u);
+        launch_pdl(kern, dim3(grid), dim3(kKtThreads), smem, ctx.stream, arena_.buf.p, gd, n, ctx.level[L], (int)ctx.N, split_, fold_stages_, 0u);
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;
         if (timed) {
@@ -1500,8 +1500,8 @@ void Engine::emit_mul_terms(ProgramBuilder &pb, uint32_t L, std::vector<MulTerms
     uint32_t n = (uint32_t)jobs.size();
     jobs.clear();
     pb.step([=] {
-        k_db_mul_last<<<dim3(ctx.N / kMacThreads, nterms, n), kMacThreads, 0, ctx.stream>>>(
-            arena_.buf.p, reinterpret_cast<const MulTermsJob *>(desc_dev_.p + off), ctx.level[L], (int)ctx.N, split_);
+        launch_pdl(k_db_mul_last, dim3(ctx.N / kMacThreads, nterms, n), dim3(kMacThreads), 0, ctx.stream, arena_.buf.p,
+                   reinterpret_cast<const MulTermsJob *>(desc_dev_.p + off), ctx.level[L], (int)ctx.N, split_);
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;
     });
@@ -1524,9 +1524,9 @@ void Engine::emit_finalize(ProgramBuilder &pb, uint32_t Ls, std::vector<Finalize
     int drop = hm::bit_length(p.coeff_modulus[0]) - keep;
     u64 clear_mask = drop > 0 ? ~((1ull << drop) - 1) : ~0ull;
     pb.step([=] {
-        k_finalize<<<dim3(ctx.N / kEwThreads, 2, n), kEwThreads, 0, ctx.stream>>>(
-            arena_.buf.p, reinterpret_cast<const FinalizeJob *>(desc_dev_.p + off), levels_dev_.p, masks_.p, results_.p, (int)Ls, ctx.t,
-            clear_mask, (int)ctx.N);
+        launch_pdl(k_finalize, dim3(ctx.N / kEwThreads, 2, n), dim3(kEwThreads), 0, ctx.stream, arena_.buf.p,
+                   reinterpret_cast<const FinalizeJob *>(desc_dev_.p + off), (const LevelConsts *)levels_dev_.p, (const u64 *)masks_.p, results_.p, (int)Ls, ctx.t,
+                   clear_mask, (int)ctx.N);
         APSU_CUDA_CHECK(cudaGetLastError());
         ctx.launches++;
         if (fin_groups_[group].done) APSU_CUDA_CHECK(record_event(fin_groups_[group].done, ctx.stream));

@@ -36,6 +36,7 @@ struct MulTermsJob {
 __global__ void __launch_bounds__(kMacThreads)
 k_db_mul_last(u64 *A, const MulTermsJob *__restrict__ jobs, LevelConsts c, int N, int split)
 {
+    pdl_enter();
     const MulTermsJob jb = jobs[blockIdx.z];
     const u32 j = blockIdx.y;
     if (j >= jb.nterms) return;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(kEwThreads)
 k_ms_sum_last(u64 *A, const u32 *__restrict__ sum_idx, const u32 *__restrict__ last_idx, const u32 *__restrict__ dst_idx, u32 nterms,
               LevelConsts c, int N)
 {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 comp = blockIdx.y, b = blockIdx.z;
     const int L = c.L;
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(kEwThreads)
 k_finalize(u64 *A, const FinalizeJob *__restrict__ jobs, const LevelConsts *__restrict__ levels, const u64 *__restrict__ masks,
            u64 *__restrict__ results, int Ls, u64 t, u64 clear_mask, int N)
 {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 comp = blockIdx.y;
     const FinalizeJob jb = jobs[blockIdx.z];

@@ -40,6 +40,7 @@ template <int TL, int TS>
 __global__ void __launch_bounds__(kEwThreads)
 k_behz_extend(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst, LevelConsts c, int N)
 {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 rp = blockIdx.y;
     const u64 *x = A + (size_t)src[rp] * N + n;
@@ -76,6 +77,7 @@ k_behz_extend(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst, 
 __global__ void __launch_bounds__(kEwThreads)
 k_tensor(u64 *A, const u32 *__restrict__ a_idx, const u32 *__restrict__ b_idx, const u32 *__restrict__ d_idx, LevelConsts c, int N)
 {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, LS = c.L + c.S;
     const u32 o = blockIdx.z;
@@ -104,6 +106,7 @@ template <int TL, int TS>
 __global__ void __launch_bounds__(kEwThreads)
 k_behz_scale_down(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst, LevelConsts c, int N)
 {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 rp = blockIdx.y;
     const u64 *d = A + (size_t)src[rp] * N + n;
@@ -160,6 +163,7 @@ k_behz_scale_down(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ d
 __global__ void __launch_bounds__(kEwThreads)
 k_ks_mac(u64 *A, const u32 *__restrict__ dig_idx, const u32 *__restrict__ out_idx, const u64 *__restrict__ keys, KeySwitchConsts c, int N)
 {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int I = blockIdx.y, R = c.L + 1;
     const u32 o = blockIdx.z >> 1, comp = blockIdx.z & 1;
@@ -197,6 +201,7 @@ template <bool PEERS>
 __global__ void __launch_bounds__(kEwThreads)
 k_ks_moddown(u64 *A, const u32 *__restrict__ acc_idx, const u32 *__restrict__ ct_idx, const u32 *__restrict__ dst_idx, KeySwitchConsts c, int N, PeerArenas peers)
 {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 comp = blockIdx.y, o = blockIdx.z;
     const int L = c.L, R = L + 1;
@@ -263,6 +268,7 @@ __global__ void k_xgpu_barrier(PeerFlags f, long long timeout_cycles)
 __global__ void __launch_bounds__(kEwThreads)
 k_mod_switch_next(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst, LevelConsts c, int N)
 {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 rp = blockIdx.y;
     const u64 *x = A + (size_t)src[rp] * N + n;
@@ -283,6 +289,7 @@ __global__ void __launch_bounds__(kEwThreads)
 k_sum_polys(u64 *A, const u32 *__restrict__ terms, const u32 *__restrict__ first, const u32 *__restrict__ n_terms,
             const u32 *__restrict__ dst, LevelConsts c, int N)
 {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     const u32 rp = blockIdx.z;

@@ -26,6 +26,16 @@ struct DShoup {
     u64 op, quot;
 };
 
+// Programmatic dependent launch (launch_pdl, context.hpp): every kernel of the query path starts with this.  The wait
+// returns once the preceding kernel of the stream has completed and its writes are visible (immediately when the launch
+// carries no programmatic edge); the trigger then lets the NEXT kernel's CTAs be scheduled while this one runs, so its
+// launch latency is hidden behind this kernel instead of following it (they block in their own wait until this grid
+// is complete, so every data dependency of the launch sequence holds transitively).
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ u64 mulhi(u64 a, u64 b) { return __umul64hi(a, b); }
 
 // x * w mod q for x < 2^64, result in [0, 2q)

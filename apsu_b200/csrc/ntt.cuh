@@ -95,12 +95,14 @@ __device__ __forceinline__ ulonglong2 tw_at(const ulonglong2 *tw, unsigned i)
 }
 
 template <int R, bool TWS = false>
-__device__ __forceinline__ void fwd_group(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, unsigned hi, int s, u64 nq, u64 q3)
+__device__ __forceinline__ void fwd_group(u64 (&x)[1 << R], const ulonglong2 *__restrict__ tw, unsigned hi, int s, u64 nq, u64 q3, unsigned root = 1u)
 {
+    // root: 1 for a whole transform; C + c for slice c of a transform cut into C contiguous slices after its first
+    // log2 C stages (ntt_split_kernel): stage s of the slice is stage s + log2 C of the transform, groups c*2^s ...
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int d = 1 << (R - 1 - r);          // pair distance inside the register group
-        const unsigned mbase = (1u << (s + r)) + (hi << r);
+        const unsigned mbase = (root << (s + r)) + (hi << r);
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) {
             if (k & d) continue;
@@ -157,7 +159,7 @@ __device__ __forceinline__ unsigned pad_idx(unsigned i) { return i + (i >> 4); }
 
 // one pass over stages [s, s+R) on the shared-memory polynomial
 template <int LOGN, int R, bool FWD, bool TWS = false>
-__device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict__ tw, int s, u64 nq, u64 q3)
+__device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict__ tw, int s, u64 nq, u64 q3, unsigned root = 1u)
 {
     constexpr int N = 1 << LOGN;
     const int log_stride = LOGN - s - R;
@@ -169,7 +171,7 @@ __device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict_
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) x[k] = sm[pad_idx(base + k * stride)];
         if (FWD)
-            fwd_group<R, TWS>(x, tw, hi, s, nq, q3);
+            fwd_group<R, TWS>(x, tw, hi, s, nq, q3, root);
         else
             inv_group<R, TWS>(x, tw, hi, s, nq, q3);
 #pragma unroll
@@ -181,12 +183,12 @@ __device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict_
 // the inverse transform runs the same passes in the opposite order
 template <int LOGN, bool FWD, int S, int COUNT, bool TWS = false>
 struct MidRunner {
-    __device__ static __forceinline__ void run(u64 *sm, const ulonglong2 *tw, u64 nq, u64 q3)
+    __device__ static __forceinline__ void run(u64 *sm, const ulonglong2 *tw, u64 nq, u64 q3, unsigned root = 1u)
     {
         if (FWD) {
-            smem_pass<LOGN, 3, true, TWS>(sm, tw, S, nq, q3);
+            smem_pass<LOGN, 3, true, TWS>(sm, tw, S, nq, q3, root);
             __syncthreads();
-            MidRunner<LOGN, FWD, S + 3, COUNT - 1, TWS>::run(sm, tw, nq, q3);
+            MidRunner<LOGN, FWD, S + 3, COUNT - 1, TWS>::run(sm, tw, nq, q3, root);
         } else {
             MidRunner<LOGN, FWD, S + 3, COUNT - 1, TWS>::run(sm, tw, nq, q3);
             smem_pass<LOGN, 3, false, TWS>(sm, tw, S, nq, q3);
@@ -196,7 +198,7 @@ struct MidRunner {
 };
 template <int LOGN, bool FWD, int S, bool TWS>
 struct MidRunner<LOGN, FWD, S, 0, TWS> {
-    __device__ static __forceinline__ void run(u64 *, const ulonglong2 *, u64, u64) {}
+    __device__ static __forceinline__ void run(u64 *, const ulonglong2 *, u64, u64, unsigned = 1u) {}
 };
 
 // One CTA per polynomial.  Stages are grouped as [RF | 3 | 3 | ... | 3] with RF = 2..4; the pass that touches
@@ -235,6 +237,7 @@ __device__ __forceinline__ void cp_async_wait_all()
 template <int LOGN, bool FWD, int DIV, int MODE = kNttPlain, bool TWS = false>
 __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) ntt_kernel(const u64 *in, u64 *out, NttArgs a, NttSrc src, NttFuse fuse = NttFuse())
 {
+    pdl_enter();
     static_assert(!TWS || MODE == kNttPlain, "staged twiddles are implemented for the plain transform");
     constexpr int N = 1 << LOGN;
     constexpr int RF = (LOGN % 3 == 0) ? 3 : (LOGN % 3 == 1 ? 4 : 2); // 13 = 4+3+3+3: one shared-memory round trip less than 1+3+3+3+3
@@ -365,6 +368,174 @@ __global__ void __launch_bounds__((1 << LOGN) / DIV, ntt_min_blocks(LOGN, DIV)) 
                 const u64 hi = mul_shoup_lazy3(u + q3 - v, inv_n_w.op, inv_n_w.quot, nq);
                 op[g + k * stride] = csub(csub(lo, 2 * q), q);
                 op[g + (k + d) * stride] = csub(csub(hi, 2 * q), q);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Split transforms: C = 2^LC CTAs (one thread-block cluster) per polynomial, for batches that leave SMs idle.
+//
+// A lone transform is bound by ONE SM's multiplier pipe and its own dependent chains (16 us at N = 8192 however few
+// polynomials the launch has), and the ComputePowers chain of one bundle index is ~30 such launches in a row.  Here
+// every CTA owns a slice of M = N / C coefficients on which all but log2 C stages are an independent M-point transform:
+//   forward (strides N/2 ... 1): after the first LC stages slice c = positions [c*M, (c+1)*M) is on its own.  A CTA
+//     computes ITS outputs of those LC stages straight from the C inputs each depends on (C = 4: three products per
+//     coefficient instead of one per two coefficients and stage -- every CTA reads the whole polynomial, redundant
+//     work 8 % at C = 2 and 31 % at C = 4, spread over C SMs), then runs the M-point passes with the twiddles of
+//     its sub-tree: stage s of the slice uses tw[(C + c) * 2^s + group].
+//   inverse (strides 1 ... N/2): after the first LC stages the positions congruent to c mod C are on their own, and
+//     stage s of that strided slice uses tw[2^s + group] of the SAME table -- the M-point inverse code unchanged.
+//     Outputs go to positions m*C + c (8-byte stores at stride C: acceptable for a launch that does not fill the GPU).
+// The N^-1 scaling and the reduction to canonical residues are as in ntt_kernel, so results are bit-identical.
+// in and out may alias (in-place): a CTA must not store before its cluster peers have read the polynomial, hence one
+// split cluster barrier (arrive after the loads were consumed, wait before the first global store).
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// output c of the first LC forward stages at slice offset j; x = the C inputs at j + i*M (canonical), result in [0, 6q)
+template <int LC>
+__device__ __forceinline__ u64 fwd_split_head(const u64 (&x)[1 << LC], const ulonglong2 *__restrict__ tw, unsigned c, u64 nq, u64 q3)
+{
+    const ulonglong2 w1 = __ldg(&tw[1]);
+    if (LC == 1) {
+        const u64 t = mul_shoup_lazy3(x[1], w1.x, w1.y, nq);
+        return c ? x[0] + q3 - t : x[0] + t;
+    } else {
+        const u64 t2 = mul_shoup_lazy3(x[2], w1.x, w1.y, nq), t3 = mul_shoup_lazy3(x[3], w1.x, w1.y, nq);
+        const u64 A = (c & 2) ? x[0] + q3 - t2 : x[0] + t2; // [0, 4q)
+        const u64 B = (c & 2) ? x[1] + q3 - t3 : x[1] + t3;
+        const ulonglong2 w2 = __ldg(&tw[2 + (c >> 1)]);
+        const u64 u = csub(A, q3), v = mul_shoup_lazy3(B, w2.x, w2.y, nq);
+        return (c & 1) ? u + q3 - v : u + v;
+    }
+}
+// output c of the first LC inverse stages for the C consecutive inputs x of block mm (positions mm*C ...), in [0, 3q)
+template <int LC, int LOGN>
+__device__ __forceinline__ u64 inv_split_head(const u64 (&x)[1 << LC], const ulonglong2 *__restrict__ tw, unsigned mm, unsigned c, u64 nq, u64 q3)
+{
+    constexpr unsigned H = 1u << (LOGN - 1);
+    if (LC == 1) {
+        if (!c) return csub(x[0] + x[1], q3);
+        const ulonglong2 w = __ldg(&tw[H + mm]);
+        return mul_shoup_lazy3(x[0] + q3 - x[1], w.x, w.y, nq);
+    } else {
+        u64 A, B;
+        if (c & 1) {
+            const ulonglong2 wa = __ldg(&tw[H + 2 * mm]), wb = __ldg(&tw[H + 2 * mm + 1]);
+            A = mul_shoup_lazy3(x[0] + q3 - x[1], wa.x, wa.y, nq);
+            B = mul_shoup_lazy3(x[2] + q3 - x[3], wb.x, wb.y, nq);
+        } else {
+            A = csub(x[0] + x[1], q3);
+            B = csub(x[2] + x[3], q3);
+        }
+        if (!(c & 2)) return csub(A + B, q3);
+        const ulonglong2 w = __ldg(&tw[(H >> 1) + mm]);
+        return mul_shoup_lazy3(A + q3 - B, w.x, w.y, nq);
+    }
+}
+
+template <int LOGN, int LC, bool FWD, int DIV>
+__global__ void __cluster_dims__(1 << LC, 1, 1) __launch_bounds__((1 << (LOGN - LC)) / DIV) ntt_split_kernel(const u64 *in, u64 *out, NttArgs a, NttSrc src)
+{
+    pdl_enter();
+    constexpr int LOGM = LOGN - LC, M = 1 << LOGM, C = 1 << LC;
+    constexpr int RF = (LOGM % 3 == 0) ? 3 : (LOGM % 3 == 1 ? 4 : 2);
+    constexpr int MID = (LOGM - RF - 3) / 3;
+    static_assert(LOGM >= RF + 3, "slice too small");
+    extern __shared__ u64 sm[];
+    const unsigned p = blockIdx.x >> LC, c = blockIdx.x & (C - 1);
+    const int slot = p % a.pattern_len;
+    const DMod m = a.mod[slot];
+    const u64 q = m.q, nq = 0 - m.q, q3 = 3 * m.q;
+    const ulonglong2 *tw = a.tw + ((size_t)a.table[slot] * 2 + (FWD ? 0 : 1)) * (size_t)(1 << LOGN);
+    const u64 *ip = in + (size_t)(src.src_idx ? src.src_idx[p] : p) * (1 << LOGN);
+    u64 *op = out + (size_t)(src.dst_idx ? src.dst_idx[p] : p) * (1 << LOGN);
+    const bool reduce = src.reduce_input != 0;
+
+    if (FWD) {
+        // head stages + stages [0, RF) of the slice: global -> registers -> shared
+        constexpr unsigned stride = M >> RF;
+        for (unsigned g = threadIdx.x; g < stride; g += blockDim.x) {
+            u64 raw[1 << RF][C];
+#pragma unroll
+            for (int k = 0; k < (1 << RF); k++)
+#pragma unroll
+                for (int i = 0; i < C; i++) raw[k][i] = ip[g + k * stride + i * M];
+            u64 x[1 << RF];
+#pragma unroll
+            for (int k = 0; k < (1 << RF); k++) {
+                if (reduce) {
+#pragma unroll
+                    for (int i = 0; i < C; i++) raw[k][i] = barrett64(raw[k][i], m);
+                }
+                x[k] = fwd_split_head<LC>(raw[k], tw, c, nq, q3);
+            }
+            fwd_group<RF>(x, tw, 0, 0, nq, q3, C + c);
+#pragma unroll
+            for (int k = 0; k < (1 << RF); k++) sm[pad_idx(g + k * stride)] = x[k];
+        }
+        __syncthreads();
+        cluster_arrive();
+        MidRunner<LOGM, true, RF, MID>::run(sm, tw, nq, q3, C + c);
+        cluster_wait();
+        u64 *oc = op + (size_t)c * M;
+        for (unsigned g = threadIdx.x; g < (M >> 3); g += blockDim.x) {
+            u64 x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = sm[pad_idx(8 * g + k)];
+            fwd_group<3>(x, tw, g, LOGM - 3, nq, q3, C + c);
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = csub(csub(csub(x[k], q3), 2 * q), q);
+            ulonglong2 *o2 = reinterpret_cast<ulonglong2 *>(oc + 8 * g);
+#pragma unroll
+            for (int k = 0; k < 4; k++) o2[k] = make_ulonglong2(x[2 * k], x[2 * k + 1]);
+        }
+    } else {
+        // head stages + stages [LOGM-3, LOGM) of the strided slice: 8*C consecutive inputs per thread
+        for (unsigned g = threadIdx.x; g < (M >> 3); g += blockDim.x) {
+            u64 raw[8][C];
+            const ulonglong2 *i2 = reinterpret_cast<const ulonglong2 *>(ip + (size_t)8 * C * g);
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+#pragma unroll
+                for (int i = 0; i < C; i += 2) {
+                    const ulonglong2 v = i2[(k * C + i) >> 1];
+                    raw[k][i] = v.x;
+                    raw[k][i + 1] = v.y;
+                }
+            u64 x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (reduce) {
+#pragma unroll
+                    for (int i = 0; i < C; i++) raw[k][i] = barrett64(raw[k][i], m);
+                }
+                x[k] = inv_split_head<LC, LOGN>(raw[k], tw, 8 * g + k, c, nq, q3);
+            }
+            inv_group<3>(x, tw, g, LOGM - 3, nq, q3);
+#pragma unroll
+            for (int k = 0; k < 8; k++) sm[pad_idx(8 * g + k)] = x[k];
+        }
+        __syncthreads();
+        cluster_arrive();
+        MidRunner<LOGM, false, RF, MID>::run(sm, tw, nq, q3);
+        cluster_wait();
+        const DShoup inv_n = a.inv_n[slot], inv_n_w = a.inv_n_w[slot];
+        constexpr unsigned stride = M >> RF;
+        for (unsigned g = threadIdx.x; g < stride; g += blockDim.x) {
+            u64 x[1 << RF];
+#pragma unroll
+            for (int k = 0; k < (1 << RF); k++) x[k] = sm[pad_idx(g + k * stride)];
+            inv_group_upper<RF>(x, tw, nq, q3);
+            constexpr int d = 1 << (RF - 1);
+#pragma unroll
+            for (int k = 0; k < d; k++) {
+                const u64 u = x[k], v = x[k + d];
+                const u64 lo = mul_shoup_lazy3(u + v, inv_n.op, inv_n.quot, nq);
+                const u64 hi = mul_shoup_lazy3(u + q3 - v, inv_n_w.op, inv_n_w.quot, nq);
+                op[(size_t)(g + k * stride) * C + c] = csub(csub(lo, 2 * q), q);
+                op[(size_t)(g + (k + d) * stride) * C + c] = csub(csub(hi, 2 * q), q);
             }
         }
     }
