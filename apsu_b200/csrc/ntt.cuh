@@ -152,6 +152,15 @@ __device__ __forceinline__ void inv_group_upper(u64 (&x)[1 << R], const ulonglon
     }
 }
 
+// lab switches (tools/lab/ntt_variants.sh): unroll factor of the shared-memory pass loop, CTAs per SM of the N = 8192
+// throughput shape
+#ifndef APSU_NTT_UNROLL
+#define APSU_NTT_UNROLL 1
+#endif
+#ifndef APSU_NTT_MINB13
+#define APSU_NTT_MINB13 3
+#endif
+constexpr int kNttUnroll = APSU_NTT_UNROLL;
 // Shared-memory layout: one pad word after every 16 coefficients.  The butterflies of the late passes
 // touch coefficients at strides 1..8; with the pad a half-warp's 16 eight-byte accesses fall into 16
 // distinct bank pairs instead of colliding 8-way (measured: 54% of LSU wavefronts were bank conflicts).
@@ -164,6 +173,7 @@ __device__ __forceinline__ void smem_pass(u64 *sm, const ulonglong2 *__restrict_
     constexpr int N = 1 << LOGN;
     const int log_stride = LOGN - s - R;
     const unsigned stride = 1u << log_stride;
+#pragma unroll kNttUnroll
     for (unsigned g = threadIdx.x; g < (N >> R); g += blockDim.x) {
         unsigned lo = g & (stride - 1), hi = g >> log_stride;
         unsigned base = (hi << (LOGN - s)) + lo;
@@ -212,6 +222,7 @@ struct MidRunner<LOGN, FWD, S, 0, TWS> {
 // whatever its size (20 us at DIV = 32), so batches of at most one CTA per SM use DIV = 8 (N/8 threads, 16 us).
 constexpr int ntt_min_blocks(int logn, int div)
 {
+    if (logn == 13 && div == 32) return APSU_NTT_MINB13;
     // CTAs per SM: shared memory allows 3 << (13 - logn) (1 at logn = 14); at most 1024 resident threads so that
     // every shape has at least 64 registers per thread
     const int by_smem = logn >= 14 ? 1 : 3 << (13 - (logn >= 14 ? 13 : logn));

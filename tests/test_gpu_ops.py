@@ -81,3 +81,62 @@ def test_multiply_and_relinearize(env):
         for o in range(n_ops):
             exp = ctx.relinearize(got[o], keys.relin)
             assert np.array_equal(rel[o], exp), (L, o)
+
+
+_SHAPE_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import apsu_b200
+from oracle import oracle as O
+from harness import Scenario
+rng = np.random.default_rng(5)
+for name in ("16M-4096", "256K-512", "100K-1"):
+    p = O.Params.load(name)
+    ctx = O.Context.from_params(p)
+    db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(p.to_json()), 0)
+    rx = apsu_b200.Receiver(db)
+    K = len(p.primes)
+    for count in (1, 5, 40):            # batches of count * K polynomials
+        x = np.zeros((count, K, p.N), dtype=np.uint64)
+        for j, q in enumerate(p.primes):
+            x[:, j, :] = rng.integers(0, q, size=(count, p.N), dtype=np.uint64)
+        pat = [rx.modulus_index(0, i) for i in range(K)]
+        y = rx.op_ntt(x, pat, inverse=False)
+        for c in (0, count - 1):
+            for j in range(K):
+                assert np.array_equal(y[c, j], ctx.ntt(j, x[c, j])), (name, count, c, j)
+        assert np.array_equal(rx.op_ntt(y, pat, inverse=True), x), (name, count)
+    db.close()
+# one whole query (graphs replayed twice) under the same launch options
+sc = Scenario("16M-4096", [[50], [], [46, 3], []], planted=4)
+db = apsu_b200.ReceiverDB(apsu_b200.PSUParams.Load(sc.p.to_json()), 0)
+for b in range(sc.p.bundle_idx_count):
+    for c in range(len(sc.degrees[b])):
+        db.add_bin_bundle(b, [a for (_, a) in sc.db.bundle_coeffs(b, c)])
+exp = {{(b, c): ct for b, c, ct in sc.db.run_query(sc.src_powers, sc.cts, sc.relin, sc.masks, threads=4).results()}}
+for _ in range(2):
+    got = {{(r.bundle_idx, r.cache_idx): r.psu_result.reshape(2, -1)
+           for r in apsu_b200.Receiver(db).RunQuery(apsu_b200.Query(sc.src_powers, sc.cts, sc.relin), sc.masks)}}
+    assert set(got) == set(exp)
+    for key in exp:
+        assert np.array_equal(got[key], exp[key]), key
+db.close()
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("env", [{"APSU_B200_NTT_SPLIT": "2"}, {"APSU_B200_NTT_SPLIT": "4"}, {"APSU_B200_NTT_SPLIT": "0"},
+                                 {"APSU_B200_PDL": "1"}], ids=lambda e: ",".join(f"{k[10:]}={v}" for k, v in e.items()))
+def test_alternative_launch_shapes_are_bit_exact(env):
+    """The launch options that are process-wide switches — transforms cut into 2 / 4 cluster CTAs per polynomial
+    (ntt.cuh: ntt_split_kernel; by default only small forward batches are split), never split, and programmatic
+    dependent launch of the query kernels — produce the same words: transforms in both directions at three batch sizes
+    and one whole query replayed twice, each in a fresh process."""
+    import os
+    import pathlib
+    import subprocess
+    import sys
+    root = str(pathlib.Path(__file__).resolve().parent.parent)
+    out = subprocess.run([sys.executable, "-c", _SHAPE_SCRIPT.format(root=root)], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

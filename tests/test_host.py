@@ -262,3 +262,83 @@ def test_seal_wire_compressed_objects(tmp_path):
     out = subprocess.check_output([str(exe), "check"] + [str(f) for f in files], text=True)
     assert out.count("parsed") == len(files) and "compr_mode=1" in out
     assert zs is None or "compr_mode=2" in out
+
+
+def test_split_transform_index_model():
+    """Model of csrc/ntt.cuh ntt_split_kernel in plain integers: a transform cut into C = 2 / 4 slices equals the whole
+    transform when (forward) slice c = positions [c*M, (c+1)*M) runs the M-point passes with tw[(C + c) * 2^s + group]
+    after the first log2 C stages, and (inverse) the positions congruent to c mod C run the M-point inverse with the
+    SAME table indices tw[2^s + group] after their first log2 C stages.  (The kernel itself is checked against the
+    oracle on the GPU: tests/test_gpu_ops.py.)"""
+    import random
+    q, logn = 12289, 6
+    N = 1 << logn
+    bitrev = lambda i: int(format(i, "0%db" % logn)[::-1], 2)
+    psi = next(g for g in range(2, q) if pow(g, N, q) == q - 1)
+    tw = [pow(psi, bitrev(i), q) for i in range(N)]
+    twi = [pow(psi, -bitrev(i), q) for i in range(N)]
+    ninv = pow(N, -1, q)
+
+    def fwd(a, M=N, root=1):
+        a, t, m = a[:], M, 1
+        while m < M:
+            t //= 2
+            for i in range(m):
+                w = tw[root * m + i]
+                for j in range(2 * i * t, 2 * i * t + t):
+                    u, v = a[j], a[j + t] * w % q
+                    a[j], a[j + t] = (u + v) % q, (u - v) % q
+            m *= 2
+        return a
+
+    def inv(a, M=N):
+        a, t, m = a[:], 1, M // 2
+        while m >= 1:
+            for i in range(m):
+                w = twi[m + i]
+                for j in range(2 * i * t, 2 * i * t + t):
+                    u, v = a[j], a[j + t]
+                    a[j], a[j + t] = (u + v) % q, (u - v) * w % q
+            t, m = t * 2, m // 2
+        return [x * ninv % q for x in a]
+
+    rnd = random.Random(7)
+    x = [rnd.randrange(q) for _ in range(N)]
+    y = fwd(x)
+    assert inv(y) == x
+    for LC in (1, 2):
+        C = 1 << LC
+        M, H = N // C, N // 2
+        out = [0] * N
+        for c in range(C):
+            sl = []
+            for j in range(M):
+                xs = [x[j + i * M] for i in range(C)]
+                if LC == 1:
+                    t = xs[1] * tw[1] % q
+                    sl.append((xs[0] - t) % q if c else (xs[0] + t) % q)
+                else:
+                    t2, t3 = xs[2] * tw[1] % q, xs[3] * tw[1] % q
+                    A = (xs[0] - t2) % q if c & 2 else (xs[0] + t2) % q
+                    B = (xs[1] - t3) % q if c & 2 else (xs[1] + t3) % q
+                    v = B * tw[2 + (c >> 1)] % q
+                    sl.append((A - v) % q if c & 1 else (A + v) % q)
+            out[c * M:(c + 1) * M] = fwd(sl, M, C + c)
+        assert out == y, LC
+        out = [0] * N
+        for c in range(C):
+            sl = []
+            for mm in range(M):
+                xs = y[mm * C:(mm + 1) * C]
+                if LC == 1:
+                    sl.append((xs[0] + xs[1]) % q if not c else (xs[0] - xs[1]) * twi[H + mm] % q)
+                else:
+                    if c & 1:
+                        A, B = (xs[0] - xs[1]) * twi[H + 2 * mm] % q, (xs[2] - xs[3]) * twi[H + 2 * mm + 1] % q
+                    else:
+                        A, B = (xs[0] + xs[1]) % q, (xs[2] + xs[3]) % q
+                    sl.append((A + B) % q if not c & 2 else (A - B) * twi[H // 2 + mm] % q)
+            r = inv(sl, M)
+            for mm in range(M):
+                out[mm * C + c] = r[mm]
+        assert out == x, LC
