@@ -83,6 +83,8 @@ SIGNATURES = {
     "apsu_b200_mgpu_info": (C.c_int, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "apsu_b200_mgpu_run_query": (C.c_int, [vp, u32p, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp]),
     "apsu_b200_mgpu_run_query_shared": (C.c_int, [vp, u32p, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp]),
+    "apsu_b200_mgpu_run_query_local": (C.c_int, [vp, u32p, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp]),
+    "apsu_b200_mgpu_local_count": (C.c_int, [vp, C.POINTER(C.c_uint32)]),
     "apsu_b200_mgpu_compute_powers": (C.c_int, [vp]),
     "apsu_b200_ctx_set_stream": (C.c_int, [vp, vp]),
     "apsu_b200_ctx_get_stream": (C.c_int, [vp, C.POINTER(vp)]),

@@ -369,7 +369,7 @@ void compute_powers(apsu_b200_mgpu &m)
 // shared_query: every rank was handed the query (the same host memory: threads of one process, or processes mapping
 // one shared segment) and uploads its own part over its own PCIe link — no scatter, no broadcast
 void run_query(apsu_b200_mgpu &m, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys, const uint64_t *masks_local,
-               uint32_t npack_local, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx, bool shared_query)
+               uint32_t npack_local, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx, bool shared_query, bool local_results = false)
 {
     if (!m.committed) throw std::logic_error("apsu_b200_mgpu_commit has not been called");
     Engine &e = *m.eng;
@@ -381,7 +381,9 @@ void run_query(apsu_b200_mgpu &m, const uint32_t *src_powers, uint32_t nsrc, con
     if (nsrc != p.query_power_count) throw std::invalid_argument("query powers do not match the query_powers of the parameters");
     const size_t ct_words = (size_t)2 * e.ctx.first_L * e.ctx.N, ct_bytes = ct_words * 8, idx_words = (size_t)nsrc * ct_words;
     const size_t key_words = e.ctx.using_keyswitching() ? (size_t)(e.ctx.K - 1) * 2 * e.ctx.K * e.ctx.N : 0;
-    if (is_root && (!cts || (key_words && !relin_keys) || !out)) throw std::invalid_argument("root rank needs the query, the keys and the output buffer");
+    if (local_results && !shared_query) throw std::invalid_argument("local result delivery needs the shared query");
+    if (local_results && m.counts[m.rank] && !out) throw std::invalid_argument("local result delivery: this rank needs an output buffer");
+    if (!local_results && is_root && (!cts || (key_words && !relin_keys) || !out)) throw std::invalid_argument("root rank needs the query, the keys and the output buffer");
     if (shared_query && (!cts || (key_words && !relin_keys))) throw std::invalid_argument("shared query: every rank needs the query and the keys");
     e.query_begin_partial(src_powers, nsrc);
     if (shared_query) {
@@ -466,6 +468,21 @@ void run_query(apsu_b200_mgpu &m, const uint32_t *src_powers, uint32_t nsrc, con
     uint64_t res_bytes = 0;
     e.results_device(&res, &res_bytes);
     const size_t per = (size_t)2 * e.ctx.N;
+    if (local_results) {
+        // every rank hands ITS BinBundles' results to its own host: no gather, the device-to-host copies of all ranks
+        // run in parallel (the reference sends every ResultPackage from the worker that finished it, receiver_ddh.cpp:527-534)
+        const size_t mine = m.counts[m.rank];
+        if (mine) APSU_CUDA_CHECK(cudaMemcpyAsync(out, res, mine * per * 8, cudaMemcpyDeviceToHost, st));
+        e.throw_if_query_invalid(); // synchronises
+        APSU_CUDA_CHECK(cudaStreamSynchronize(st));
+        size_t first = 0;
+        for (uint32_t r = 0; r < m.rank; r++) first += m.counts[r];
+        for (size_t k = 0; k < mine; k++) {
+            if (bundle_idx) bundle_idx[k] = m.all_bundle_idx[first + k];
+            if (cache_idx) cache_idx[k] = m.all_cache_idx[first + k];
+        }
+        return;
+    }
     if (!is_root) {
         if (m.counts[m.rank]) APSU_NCCL_CHECK(nc.Send(res, m.counts[m.rank] * per, ncclUint64, (int)m.root, m.comm, st));
         e.throw_if_query_invalid();
@@ -594,6 +611,26 @@ int apsu_b200_mgpu_run_query_shared(
         if (!m) throw std::invalid_argument("mgpu is null");
         APSU_CUDA_CHECK(cudaSetDevice(m->eng->ctx.device));
         run_query(*m, src_powers, nsrc, cts, relin_keys, masks_local, npack_local, out, bundle_idx, cache_idx, true);
+    });
+}
+
+int apsu_b200_mgpu_run_query_local(
+    apsu_b200_mgpu *m, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys, const uint64_t *masks_local,
+    uint32_t npack_local, uint64_t *out_local, uint32_t *bundle_idx_local, uint32_t *cache_idx_local)
+{
+    return guarded_call([&] {
+        if (!m) throw std::invalid_argument("mgpu is null");
+        APSU_CUDA_CHECK(cudaSetDevice(m->eng->ctx.device));
+        run_query(*m, src_powers, nsrc, cts, relin_keys, masks_local, npack_local, out_local, bundle_idx_local, cache_idx_local, true, true);
+    });
+}
+
+int apsu_b200_mgpu_local_count(const apsu_b200_mgpu *m, uint32_t *count)
+{
+    return guarded_call([&] {
+        if (!m || !m->committed) throw std::logic_error("apsu_b200_mgpu_commit has not been called");
+        if (!count) throw std::invalid_argument("count is null");
+        *count = m->counts[m->rank];
     });
 }
 

@@ -460,24 +460,33 @@ public:
                 at += ct_words;
             }
         }
-        std::uint64_t *out = dbs_[0]->pinned(1, static_cast<std::size_t>(total) * 2 * N);
-        std::vector<std::uint32_t> bidx(total), cidx(total);
+        // every GPU delivers the result ciphertexts of its own BinBundles to its own pinned buffer (no gather: the
+        // device-to-host copies of all GPUs run in parallel), then the packages are handed over in rank order
+        std::vector<std::uint64_t *> out(world(), nullptr);
+        std::vector<std::vector<std::uint32_t>> bidx(world()), cidx(world());
         each_rank([&](std::size_t r) {
-            const bool root = r == 0;
             const std::vector<std::uint64_t> *m = r < masks.size() && !masks[r].empty() ? &masks[r] : nullptr;
+            std::uint32_t mine = 0;
+            detail::check(apsu_b200_mgpu_local_count(mg_[r], &mine));
+            out[r] = dbs_[r]->pinned(1, static_cast<std::size_t>(std::max<std::uint32_t>(mine, 1)) * 2 * N);
+            bidx[r].assign(mine, 0);
+            cidx[r].assign(mine, 0);
             // the ranks are threads of this process: every GPU uploads its own part of the query in parallel
-            detail::check(apsu_b200_mgpu_run_query_shared(
+            detail::check(apsu_b200_mgpu_run_query_local(
                 mg_[r], src.data(), static_cast<std::uint32_t>(src.size()), cts,
                 !query.relin_keys().empty() ? query.relin_keys().data() : nullptr, m ? m->data() : nullptr,
-                m ? static_cast<std::uint32_t>(m->size() / N) : 0, root ? out : nullptr, root ? bidx.data() : nullptr, root ? cidx.data() : nullptr));
+                m ? static_cast<std::uint32_t>(m->size() / N) : 0, out[r], bidx[r].data(), cidx[r].data()));
         });
-        for (std::uint32_t k = 0; k < total; k++) {
-            auto rp = std::make_unique<network::ResultPackage>();
-            rp->bundle_idx = bidx[k];
-            rp->cache_idx = cidx[k];
-            rp->psu_result.assign(out + static_cast<std::size_t>(k) * 2 * N, out + static_cast<std::size_t>(k + 1) * 2 * N);
-            send_rp_fun(std::move(rp));
-        }
+        std::uint32_t delivered = 0;
+        for (std::size_t r = 0; r < world(); r++)
+            for (std::size_t k = 0; k < bidx[r].size(); k++, delivered++) {
+                auto rp = std::make_unique<network::ResultPackage>();
+                rp->bundle_idx = bidx[r][k];
+                rp->cache_idx = cidx[r][k];
+                rp->psu_result.assign(out[r] + k * 2 * N, out[r] + (k + 1) * 2 * N);
+                send_rp_fun(std::move(rp));
+            }
+        if (delivered != total) throw std::logic_error("MultiGpuReceiver: result count mismatch");
     }
 
 private:

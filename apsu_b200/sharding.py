@@ -90,6 +90,27 @@ class MultiGpu:
     def compute_powers(self):
         self._capi.check(self._L.apsu_b200_mgpu_compute_powers(self._h))
 
+    def local_count(self) -> int:
+        n = self._C.c_uint32()
+        self._capi.check(self._L.apsu_b200_mgpu_local_count(self._h, self._C.byref(n)))
+        return n.value
+
+    def run_query_local(self, src_powers, cts, relin_keys, masks_local, out=None, bundle_idx=None, cache_idx=None):
+        """apsu_b200_mgpu_run_query_local: every rank holds the query (as with shared=True) and receives the result
+        ciphertexts of ITS OWN BinBundles in its own host buffer `out` [local_count][2][N]; nothing is gathered.
+        Returns (out, bundle_idx, cache_idx) with the global cache indices, on every rank."""
+        np, ptr = self._np, self._capi.ptr
+        sp = np.ascontiguousarray(list(src_powers), dtype=np.uint32)
+        n = self.local_count()
+        if out is None:
+            out = np.zeros((max(n, 1), 2, self.db.params.poly_modulus_degree()), dtype=np.uint64)
+        if bundle_idx is None:
+            bundle_idx, cache_idx = np.zeros(max(n, 1), dtype=np.uint32), np.zeros(max(n, 1), dtype=np.uint32)
+        npack = 0 if masks_local is None else masks_local.shape[0]
+        self._capi.check(self._L.apsu_b200_mgpu_run_query_local(
+            self._h, sp, len(sp), ptr(cts), ptr(relin_keys), ptr(masks_local), npack, ptr(out), ptr(bundle_idx), ptr(cache_idx)))
+        return out[:n], bundle_idx[:n], cache_idx[:n]
+
     def run_query(self, src_powers, cts, relin_keys, masks_local, out=None, bundle_idx=None, cache_idx=None, shared: bool = False):
         """root (rank 0): cts / relin_keys host arrays and `out` [total][2][N] (allocated when None); other ranks pass
         None — or, with shared=True, the same query (one host buffer every rank can read): every rank then uploads its own

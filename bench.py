@@ -509,6 +509,38 @@ def main():
         e2e_shared_local = (time.perf_counter() - w0) * 1e3 / args.steps
         barrier()
 
+    # ---- e2e at N>1 as the C++ host runs it (apsu::receiver::MultiGpuReceiver): shared query AND every rank delivers the
+    # results of its own BinBundles to its own pinned host buffer (no gather; the D2H copies of all GPUs run in parallel) ----
+    e2e_local_results = 0.0
+    if mg is not None:
+        n_loc = mg.local_count()
+        loc_t = torch.empty((max(n_loc, 1), 2, N), dtype=torch.int64).pin_memory()
+        loc_p = loc_t.numpy().view(np.uint64)
+        lb, lc = np.zeros(max(n_loc, 1), dtype=np.uint32), np.zeros(max(n_loc, 1), dtype=np.uint32)
+
+        def step_local():
+            mg.run_query_local(src_powers, cts_p, relin_p, masks_p, loc_p, lb, lc)
+        for _ in range(args.warmup):
+            step_local()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_local()
+        e2e_local_results = (time.perf_counter() - w0) * 1e3 / args.steps
+        barrier()
+        # the locally delivered ciphertexts must be the ones the gathered call returned (checked below against the oracle)
+        step_shared()
+        import hashlib
+        loc_digests = [None] * world
+        dist.all_gather_object(loc_digests, {(int(lb[k]), int(lc[k])): hashlib.sha256(loc_p[k].tobytes()).hexdigest() for k in range(n_loc)})
+        local_ok = True
+        if rank == 0:
+            merged = {}
+            for d_ in loc_digests:
+                merged.update(d_)
+            local_ok = len(merged) == n_bundles and all(
+                merged.get((int(bidx[k]), int(cidx[k]))) == hashlib.sha256(out_p[k].tobytes()).hexdigest() for k in range(n_bundles))
+
     # ---- e2e, fed as the reference's RunQuery is (N=1): the query as on the wire (seeded ciphertexts and keys: c1 is a
     # 64-byte seed expanded on the device, row f2) and the masks drawn on the device inside the call (row f3) ----
     e2e_seeded = None
@@ -553,11 +585,11 @@ def main():
 
     # max over ranks
     if dist is not None:
-        v = torch.tensor([ms_step_local, e2e_ms_local, e2e_shared_local], device="cuda", dtype=torch.float64)
+        v = torch.tensor([ms_step_local, e2e_ms_local, e2e_shared_local, e2e_local_results], device="cuda", dtype=torch.float64)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        ms_step, e2e_ms, e2e_shared_ms = float(v[0]), float(v[1]), float(v[2])
+        ms_step, e2e_ms, e2e_shared_ms, e2e_local_ms = float(v[0]), float(v[1]), float(v[2]), float(v[3])
     else:
-        ms_step, e2e_ms, e2e_shared_ms = ms_step_local, e2e_ms_local, 0.0
+        ms_step, e2e_ms, e2e_shared_ms, e2e_local_ms = ms_step_local, e2e_ms_local, 0.0, 0.0
 
     if rank == 0:
         # N=1: local cache indices are the global ones (one rank holds everything, in order)
@@ -629,12 +661,22 @@ def main():
             out["e2e_root_scatter"] = dict(out["e2e"], what="apsu_b200_mgpu_run_query: only rank 0 holds the query; it uploads it chunk by chunk (one PCIe "
                                            "link) and the library sends every rank the ciphertexts of its bundle indices (ncclSend/Recv) and the keys (ncclBroadcast); "
                                            "results gathered on rank 0")
-            out["e2e"] = {
+            out["e2e_gathered"] = {
                 "value": n_bundles / (e2e_shared_ms / 1e3), "unit": "BinBundles/s", "ms_per_step": e2e_shared_ms,
                 "h2d_bytes_per_step": int(cts.nbytes + world * nb_keys + masks.nbytes), "d2h_bytes_per_step": int(n_bundles * 2 * N * 8),
                 "what": "apsu_b200_mgpu_run_query_shared: every rank reads the query from host memory and uploads the ciphertexts of its own bundle "
                         "indices + the keys over its own PCIe link in parallel (pinned host buffers, inside the timed region); results gathered on rank 0 "
                         "over NCCL and copied to its host buffer"}
+            out["e2e"] = {
+                "value": n_bundles / (e2e_local_ms / 1e3), "unit": "BinBundles/s", "ms_per_step": e2e_local_ms,
+                "h2d_bytes_per_step": int(cts.nbytes + world * nb_keys + masks.nbytes), "d2h_bytes_per_step": int(n_bundles * 2 * N * 8),
+                "what": "apsu_b200_mgpu_run_query_local (what apsu::receiver::MultiGpuReceiver calls): every rank reads the query from host memory and "
+                        "uploads the ciphertexts of its own bundle indices + the keys over its own PCIe link, and copies the result ciphertexts of its own "
+                        "BinBundles to its own pinned host buffer (H2D and D2H inside the timed region, max over ranks; nothing gathered: each host thread "
+                        "/ process forwards its ResultPackages as the reference's workers do)",
+                "local_results_equal_gathered": bool(local_ok)}
+            if not local_ok:
+                out["INVALID"] = "locally delivered results differ from the gathered ones"
         # ---- parity at every N: the gathered results of the last e2e step against the oracle (one BinBundle per rank,
         # the fullest and the smallest at N=1) and their digest against the N=1 record ----
         got = {(int(bidx[k]), int(cidx[k])): out_p[k] for k in range(n_bundles)}

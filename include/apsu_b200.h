@@ -305,6 +305,17 @@ int apsu_b200_mgpu_run_query(
 int apsu_b200_mgpu_run_query_shared(
     apsu_b200_mgpu *m, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys, const uint64_t *masks_local,
     uint32_t npack_local, uint64_t *out, uint32_t *bundle_idx, uint32_t *cache_idx);
+/* The shared-query call with LOCAL result delivery: every rank copies the result ciphertexts of ITS OWN BinBundles to its
+ * own host buffer — out_local uint64_t[local_count][2][N], bundle_idx_local / cache_idx_local [local_count] with the
+ * GLOBAL cache indices, in the order of the rank's span of the gathered layout — and nothing is gathered: the
+ * device-to-host copies of all GPUs run in parallel.  This is what a host with one thread (or process) per GPU needs when
+ * each of them forwards its ResultPackages itself, as the reference's workers do (receiver/apsu/receiver_ddh.cpp:340-364,
+ * 527-534: send_rp_fun is called by the pool thread that finished the BinBundle). */
+int apsu_b200_mgpu_run_query_local(
+    apsu_b200_mgpu *m, const uint32_t *src_powers, uint32_t nsrc, const uint64_t *cts, const uint64_t *relin_keys, const uint64_t *masks_local,
+    uint32_t npack_local, uint64_t *out_local, uint32_t *bundle_idx_local, uint32_t *cache_idx_local);
+/* number of BinBundles of this rank (after apsu_b200_mgpu_commit) */
+int apsu_b200_mgpu_local_count(const apsu_b200_mgpu *m, uint32_t *count);
 /* ComputePowers of this rank with the per-level exchange of a split PowersDag (query already loaded). */
 int apsu_b200_mgpu_compute_powers(apsu_b200_mgpu *m);
 

@@ -1,6 +1,7 @@
 """Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the C++ multi-GPU path (apsu_b200_mgpu_*, csrc/mgpu.cu) with
 REAL NCCL between two B200s — query scatter (ncclSend/ncclRecv per bundle index + ncclBroadcast of the keys), the
-PowersDag split with its per-level in-place ncclAllGather (collective C2) and the unpadded result gather — compared
+PowersDag split with its per-level in-place ncclAllGather (collective C2), the unpadded result gather and the local
+(ungathered) result delivery — compared
 bit for bit with the CPU oracle.  The two ranks are two threads of this process, each with its own context on its own
 GPU (ctypes releases the GIL, so both block inside NCCL concurrently); bench.py runs the same calls with one process
 per GPU under torchrun."""
@@ -65,14 +66,17 @@ def test_two_gpu_query_matches_oracle(name, degrees, dag_split, expect_group):
             if r == 0:
                 for k in range(3):
                     assert np.array_equal(outs[0][k], outs[2][k])  # results and indices of the scattered and the shared call
-            return info, outs[1]
+            # local delivery: every rank receives the results of its own BinBundles in its own host buffer, nothing gathered
+            loc = mg.run_query_local(sc.src_powers, sc.cts, sc.relin, masks)
+            assert mg.local_count() == len(parts[r]) == loc[0].shape[0]
+            return info, outs[1], loc
         finally:
             if mg is not None:
                 mg.close()
             db.close()
 
     res = _run_ranks(world, rank_main)
-    info0, (out, bidx, cidx) = res[0]
+    info0, (out, bidx, cidx), _ = res[0]
     print("multi-GPU info:", info0)
     assert info0["total_bin_bundles"] == len(exp)
     assert info0["dag_group_size"] == expect_group and res[1][0]["dag_group_size"] == expect_group
@@ -80,6 +84,14 @@ def test_two_gpu_query_matches_oracle(name, degrees, dag_split, expect_group):
     assert set(got) == set(exp)
     for key in exp:
         assert np.array_equal(got[key], exp[key]), key
+    got_local = {}
+    for r in range(world):
+        lout, lb, lc = res[r][2]
+        for k in range(lout.shape[0]):
+            got_local[(int(lb[k]), int(lc[k]))] = lout[k]
+    assert set(got_local) == set(exp)
+    for key in exp:
+        assert np.array_equal(got_local[key], exp[key]), key
 
 
 def test_cpp_multi_gpu_facade_matches_single_gpu(tmp_path):
