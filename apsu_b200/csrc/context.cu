@@ -179,7 +179,12 @@ void DeviceContext::build_levels()
             uint64_t p = bsk[j];
             c.bsk[j] = make_mod(p);
             uint64_t qp = hm::prod_mod(q, p);
-            const uint64_t inv_q = invm(qp, p), inv_mt = invm(mt % p, p);
+            const uint64_t inv_mt = invm(mt % p, p);
+            // fast floor (step 7) constants carry q^-1 and, for the primes of B (j < nb), also the (B/B_j)^-1 of the
+            // Shenoy-Kumaresan conversion that follows (step 8): the kernel then gets g_j = f_j * (B/B_j)^-1 directly
+            uint64_t inv_q = invm(qp, p);
+            if (j < nb) inv_q = mulm(inv_q, invm(hm::prod_mod(B, p, (int)j), p), p);
+            else inv_q = mulm(inv_q, invm(hm::prod_mod(B, p), p), p); // m_sk: times B^-1, see B_punct_mod_msk below
             for (uint32_t i = 0; i < L; i++) {
                 const uint64_t punct = hm::prod_mod(q, p, (int)i);
                 // extension (steps 1-2): the m_tilde^-1 of the Montgomery reduction folded into the conversion
@@ -192,7 +197,8 @@ void DeviceContext::build_levels()
         }
         for (uint32_t k = 0; k < nb; k++) {
             c.inv_punct_B[k] = make_shoup(invm(hm::prod_mod(B, B[k], (int)k), B[k]), B[k]);
-            c.B_punct_mod_msk[k] = make_shoup(hm::prod_mod(B, msk, (int)k), msk);
+            // alpha_sk = (sum_k g_k * (B/B_k) - f_msk) * B^-1 mod m_sk with the B^-1 folded into both sides
+            c.B_punct_mod_msk[k] = make_shoup(mulm(hm::prod_mod(B, msk, (int)k), invm(hm::prod_mod(B, msk), msk), msk), msk);
         }
         c.inv_B_mod_msk = make_shoup(invm(hm::prod_mod(B, msk), msk), msk);
 

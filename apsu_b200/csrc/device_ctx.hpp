@@ -49,12 +49,13 @@ struct LevelConsts {
     DShoup inv_punct_q[kMaxQ];          // (q/q_i)^-1 mod q_i
     DShoup t_inv_punct_q[kMaxQ];        // t * (q/q_i)^-1 mod q_i
     // step 7 fused: f_j = d_j * floor_t_bsk[j] + sum_i tmp_i * floor_punct_bsk[j][i]  (mod Bsk_j) with
-    // floor_t_bsk = t * q^-1, floor_punct_bsk = -(q/q_i) * q^-1
+    // floor_t_bsk = t * q^-1, floor_punct_bsk = -(q/q_i) * q^-1 — both times (B/B_j)^-1 for the primes of B (j < |B|),
+    // which makes f_j the Shenoy-Kumaresan digit of step 8, and times B^-1 for m_sk (inv_punct_B / inv_B_mod_msk: reference only)
     DShoup floor_t_bsk[kMaxBsk];
     DShoup floor_punct_bsk[kMaxBsk][kMaxQ];
     DShoup inv_punct_B[kMaxBsk];           // (B/B_i)^-1 mod B_i
     DShoup B_punct_mod_q[kMaxQ][kMaxBsk];  // (B/B_i) mod q_j
-    DShoup B_punct_mod_msk[kMaxBsk];       // (B/B_i) mod m_sk
+    DShoup B_punct_mod_msk[kMaxBsk];       // (B/B_i) * B^-1 mod m_sk (the floor constants of m_sk carry the same B^-1)
     DShoup inv_B_mod_msk;               // B^-1 mod m_sk
     DShoup B_mod_q[kMaxQ];              // B mod q_j
     DShoup neg_B_mod_q[kMaxQ];          // -B mod q_j

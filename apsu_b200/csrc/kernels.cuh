@@ -117,7 +117,8 @@ k_behz_scale_down(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ d
 #pragma unroll
     for (int i = 0; i < kMaxQ; i++)
         if (i < L) tmp[i] = mul_shoup(d[(size_t)i * N], c.t_inv_punct_q[i], c.q[i].q);
-    // f_j = (t*d_j - FastBConv(t*d_q; q -> Bsk_j)) * q^-1, the q^-1 folded into both constants
+    // f_j = (t*d_j - FastBConv(t*d_q; q -> Bsk_j)) * q^-1, the q^-1 folded into both constants; for the primes of B the
+    // constants also carry (B/B_j)^-1, so f[j] (j < nb) already is the Shenoy-Kumaresan digit g_j = f_j * (B/B_j)^-1
 #pragma unroll
     for (int j = 0; j < kMaxBsk; j++) {
         if (j < S) {
@@ -131,17 +132,14 @@ k_behz_scale_down(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ d
         }
     }
     // Shenoy-Kumaresan
-    u64 g[kMaxBsk];
+    const u64(&g)[kMaxBsk] = f;
     const u64 msk = c.bsk[S - 1].q;
     LazySum aacc;
 #pragma unroll
     for (int k = 0; k < kMaxBsk; k++) {
-        if (k < nb) {
-            g[k] = mul_shoup(f[k], c.inv_punct_B[k], c.bsk[k].q);
-            aacc.add(g[k], c.B_punct_mod_msk[k], msk);
-        }
+        if (k < nb) aacc.add(g[k], c.B_punct_mod_msk[k], msk);
     }
-    u64 alpha = mul_shoup(sub_mod(aacc.get(msk), f[S - 1], msk), c.inv_B_mod_msk, msk);
+    const u64 alpha = sub_mod(aacc.get(msk), f[S - 1], msk); // B^-1 is inside B_punct_mod_msk and the m_sk floor constants
     const bool neg = alpha > (msk >> 1);
     const u64 corr = neg ? msk - alpha : alpha;
 #pragma unroll
