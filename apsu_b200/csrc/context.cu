@@ -161,6 +161,7 @@ void DeviceContext::build_levels()
             if (i + 1 < L) {
                 c.inv_qlast[i] = make_shoup(invm(q[L - 1] % q[i], q[i]), q[i]);
                 c.half_mod[i] = (q[L - 1] >> 1) % q[i];
+                c.last_kind[i] = q[L - 1] <= q[i] ? 0u : (q[L - 1] <= 2 * q[i] ? 1u : 2u);
             }
             uint64_t punct = hm::prod_mod(q, q[i], (int)i);
             uint64_t inv_punct = invm(punct, q[i]);
@@ -212,6 +213,7 @@ void DeviceContext::build_levels()
                 kc.key_mod[i] = make_mod(q[i]);
                 kc.inv_P[i] = make_shoup(invm(P % q[i], q[i]), q[i]);
                 kc.half_P_mod[i] = (P >> 1) % q[i];
+                kc.P_kind[i] = P <= q[i] ? 0u : (P <= 2 * q[i] ? 1u : 2u);
             }
             kc.key_mod[L] = make_mod(P);
             kc.half_P = P >> 1;

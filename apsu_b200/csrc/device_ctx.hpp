@@ -36,6 +36,7 @@ struct LevelConsts {
     // mod_switch_to_next: (q_{L-1})^-1 mod q_j (Shoup), (q_{L-1}>>1) mod q_j
     DShoup inv_qlast[kMaxQ];
     u64 half_mod[kMaxQ];
+    u32 last_kind[kMaxQ];               // reduce_known kind of a residue of q_{L-1} modulo q_j
     // BEHZ step 1: x_i * (m_tilde * (q/q_i)^-1) mod q_i
     DShoup mtilde_inv_punct_q[kMaxQ];
     // steps 1-2 fused: x'_j = sum_i tmp_i * ext_punct_bsk[j][i] + r * ext_q_bsk[j]  (mod Bsk_j) with
@@ -68,6 +69,7 @@ struct KeySwitchConsts {
     DShoup inv_P[kMaxQ];    // P^-1 mod q_i
     u64 half_P;             // P >> 1
     u64 half_P_mod[kMaxQ];  // (P>>1) mod q_i
+    u32 P_kind[kMaxQ];      // reduce_known kind of a residue of P modulo q_i
 };
 
 // fused prologues of the transforms (ntt.cuh)

@@ -67,17 +67,20 @@ k_ms_sum_last(u64 *A, const u32 *__restrict__ sum_idx, const u32 *__restrict__ l
     const u32 comp = blockIdx.y, b = blockIdx.z;
     const int L = c.L;
     const u64 qk = c.q[L - 1].q, half = qk >> 1;
+    // sum_j (a_j mod q_i) is only needed modulo q_i, and that is (sum_j a_j) mod q_i: ONE integer sum of the a_j
+    // (128 bits: nterms * q_k may exceed a word) and one reduction per prime at the end — no multiplication per term
+    // (the first version reduced every a_j modulo every q_i: 2 Barrett reductions per term made this kernel
+    // multiplier-bound, 91 us per 16M-4096 query)
+    Acc128 sum{ 0, 0 };
+    const u64 *t = A + ((size_t)last_idx[b] + comp) * N + n;
+#pragma unroll 8
+    for (u32 j = 0; j < nterms; j++) { // independent loads: unrolled so that eight are in flight
+        const u64 a = add_mod(t[(size_t)j * 2 * N], half, qk);
+        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, 0;" : "+l"(sum.lo), "+l"(sum.hi) : "l"(a));
+    }
     u64 s[kMaxQ];
 #pragma unroll
-    for (int i = 0; i < kMaxQ; i++) s[i] = 0;
-    const u64 *t = A + ((size_t)last_idx[b] + comp) * N + n;
-#pragma unroll 4
-    for (u32 j = 0; j < nterms; j++) { // independent loads: unrolled so that four are in flight
-        const u64 a = add_mod(t[(size_t)j * 2 * N], half, qk);
-#pragma unroll
-        for (int i = 0; i < kMaxQ - 1; i++)
-            if (i + 1 < L) s[i] = add_mod(s[i], barrett64(a, c.q[i]), c.q[i].q);
-    }
+    for (int i = 0; i < kMaxQ - 1; i++) s[i] = (i + 1 < L) ? barrett128(sum.lo, sum.hi, c.q[i]) : 0;
     const u64 *x = A + ((size_t)sum_idx[b] + (size_t)comp * L) * N + n;
     u64 *o = A + ((size_t)dst_idx[b] + (size_t)comp * (L - 1)) * N + n;
 #pragma unroll
@@ -170,7 +173,7 @@ k_finalize(u64 *A, const FinalizeJob *__restrict__ jobs, const LevelConsts *__re
         for (int i = 0; i < kMaxQ - 1; i++) {
             if (i + 1 < L) {
                 const DMod m = c.q[i];
-                u64 tmp = sub_mod(barrett64(a, m), c.half_mod[i], m.q);
+                u64 tmp = sub_mod(reduce_known(a, m, c.last_kind[i]), c.half_mod[i], m.q);
                 v[i] = mul_shoup(sub_mod(v[i], tmp, m.q), c.inv_qlast[i], m.q);
             }
         }

@@ -210,7 +210,7 @@ k_ks_moddown(u64 *A, const u32 *__restrict__ acc_idx, const u32 *__restrict__ ct
     u64 u = add_mod(ac[(size_t)L * N], c.half_P, P);
     for (int i = 0; i < L; i++) {
         const DMod m = c.key_mod[i];
-        u64 delta = sub_mod(barrett64(u, m), c.half_P_mod[i], m.q);
+        u64 delta = sub_mod(reduce_known(u, m, c.P_kind[i]), c.half_P_mod[i], m.q);
         u64 v = mul_shoup(sub_mod(ac[(size_t)i * N], delta, m.q), c.inv_P[i], m.q);
         const u64 r = add_mod(ct[(size_t)i * N], v, m.q);
         A[dst_off + (size_t)i * N] = r;
@@ -276,7 +276,7 @@ k_mod_switch_next(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ d
     const u64 a = add_mod(x[(size_t)(L - 1) * N], ql >> 1, ql);
     for (int i = 0; i + 1 < L; i++) {
         const DMod m = c.q[i];
-        u64 tmp = sub_mod(barrett64(a, m), c.half_mod[i], m.q);
+        u64 tmp = sub_mod(reduce_known(a, m, c.last_kind[i]), c.half_mod[i], m.q);
         o[(size_t)i * N] = mul_shoup(sub_mod(x[(size_t)i * N], tmp, m.q), c.inv_qlast[i], m.q);
     }
 }

@@ -125,6 +125,15 @@ __device__ __forceinline__ u64 barrett64(u64 x, const DMod &m)
     if (r >= m.q) r -= m.q;
     return r;
 }
+// x mod q when the caller knows how large x can be relative to q (decided on the host from the moduli, uniform per
+// launch): kind 0: x < q, 1: x < 2q (one conditional subtraction), 2: anything (Barrett).  The mod-switch and mod-down
+// kernels reduce a residue of one prime modulo the others; for primes of similar size that is not a multiplication.
+__device__ __forceinline__ u64 reduce_known(u64 x, const DMod &m, u32 kind)
+{
+    if (kind == 0) return x;
+    if (kind == 1) return x >= m.q ? x - m.q : x;
+    return barrett64(x, m);
+}
 // (hi:lo) mod q for (hi:lo) < 2^(64+sh), i.e. hi < 2^sh — products of reduced operands and short sums of them.
 // One 64x64 high product instead of barrett128's four: xh = (hi:lo) >> sh fits a word, qhat = floor(xh*mu/2^64)
 // is at most 2 short of the true quotient (both truncations lose less than 1), hence two conditional subtractions.
