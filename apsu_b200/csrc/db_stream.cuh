@@ -344,14 +344,24 @@ __global__ void __launch_bounds__(128) k_pack_tile(const u64 *__restrict__ src, 
 // ciphertext powers from the arena into the tile-major split table one bundle index streams against:
 // dst[((tile*T + t)*2 + comp)*128 + c] = split(A[(src[t*2+comp] + l)*N + n]),  l*N + n = tile*128 + c.
 // src[t*2+comp] = arena index of prime 0 of component comp of term t (its L primes are consecutive polynomials).
-// grid (L*N/128, T*2, tables), block 128; table z: sources src[z*T*2 ..], destination arena index dst_idx[z]
+// grid (L*N/128, ceil(T*2 / kPackPer), tables), block 128; table z: sources src[z*T*2 ..], destination arena index
+// dst_idx[z].  Every thread moves kPackPer words, all loads issued before the first store: with one word per thread the
+// launch was 67 584 CTAs of ten instructions each and bound by the CTA launch rate (38 us, 72 us with the two
+// griddepcontrol instructions of pdl_enter in front), not by the 140 MB it moves.
+constexpr u32 kPackPer = 8;
 __global__ void __launch_bounds__(128) k_pack_powers(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ dst_idx, u32 T, int N, int split)
 {
     pdl_enter();
-    const u32 tile = blockIdx.x, tc = blockIdx.y, z = blockIdx.z, c = threadIdx.x;
+    const u32 tile = blockIdx.x, tc0 = blockIdx.y * kPackPer, z = blockIdx.z, c = threadIdx.x;
     const size_t col = (size_t)tile * kKtCols + c; // l*N + n: consecutive primes are consecutive polynomials
     u64 *dst = A + (size_t)dst_idx[z] * N;
-    dst[((size_t)tile * T * 2 + tc) * kKtCols + c] = split_word(A[(size_t)src[(size_t)z * T * 2 + tc] * N + col], split);
+    u64 w[kPackPer];
+#pragma unroll
+    for (u32 k = 0; k < kPackPer; k++)
+        if (tc0 + k < T * 2) w[k] = A[(size_t)src[(size_t)z * T * 2 + tc0 + k] * N + col];
+#pragma unroll
+    for (u32 k = 0; k < kPackPer; k++)
+        if (tc0 + k < T * 2) dst[((size_t)tile * T * 2 + tc0 + k) * kKtCols + c] = split_word(w[k], split);
 }
 
 } // namespace apsu_b200

@@ -271,7 +271,7 @@ struct ProgramBuilder {
         uint32_t nz = (uint32_t)dst.size();
         Engine *en = &e;
         step([=] {
-            launch_pdl(k_pack_powers, dim3(L * en->ctx.N / kKtCols, T * 2, nz), dim3(kKtCols), 0, en->ctx.stream, en->arena_.buf.p, (const u32 *)en->idx_.at(so),
+            launch_pdl(k_pack_powers, dim3(L * en->ctx.N / kKtCols, (T * 2 + kPackPer - 1) / kPackPer, nz), dim3(kKtCols), 0, en->ctx.stream, en->arena_.buf.p, (const u32 *)en->idx_.at(so),
                        (const u32 *)en->idx_.at(dn), T, (int)en->ctx.N, en->split_);
             APSU_CUDA_CHECK(cudaGetLastError());
             en->ctx.launches++;
