@@ -54,7 +54,7 @@ void Engine::run_scale_down(uint32_t L, uint32_t n, const uint32_t *src, const u
 void Engine::run_ks_mac(uint32_t L, uint32_t n_ops, const uint32_t *dig, const uint32_t *out)
 {
     if (!n_ops) return;
-    launch_pdl(k_ks_mac, dim3(ctx.N / kEwThreads, L + 1, n_ops * 2), dim3(kEwThreads), 0, ctx.stream, arena_.buf.p, dig, out, (const u64 *)relin_keys_.p, ctx.ks[L], (int)ctx.N);
+    launch_pdl(k_ks_mac, dim3(ctx.N / kEwThreads, L + 1, n_ops), dim3(kEwThreads), 0, ctx.stream, arena_.buf.p, dig, out, (const u64 *)relin_keys_.p, ctx.ks[L], (int)ctx.N);
     APSU_LAUNCH_CHECK();
 }
 void Engine::run_ks_moddown(uint32_t L, uint32_t n_ops, const uint32_t *acc, const uint32_t *ct, const uint32_t *dst, bool mirror)

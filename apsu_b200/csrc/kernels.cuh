@@ -156,7 +156,7 @@ k_behz_scale_down(u64 *A, const u32 *__restrict__ src, const u32 *__restrict__ d
 }
 
 // ---- key switching: inner product of the NTT'd digits with the relinearisation keys ----
-// grid (N/256, R, n_ops*2).  digits[o] -> [L][R][N] (digit J, modulus slot I); keys [K-1][2][K][N];
+// grid (N/256, R, n_ops).  digits[o] -> [L][R][N] (digit J, modulus slot I); keys [K-1][2][K][N];
 // out[o] -> [2][R][N].
 __global__ void __launch_bounds__(kEwThreads)
 k_ks_mac(u64 *A, const u32 *__restrict__ dig_idx, const u32 *__restrict__ out_idx, const u64 *__restrict__ keys, KeySwitchConsts c, int N)
@@ -164,23 +164,30 @@ k_ks_mac(u64 *A, const u32 *__restrict__ dig_idx, const u32 *__restrict__ out_id
     pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int I = blockIdx.y, R = c.L + 1;
-    const u32 o = blockIdx.z >> 1, comp = blockIdx.z & 1;
+    const u32 o = blockIdx.z;
     const int key_index = I == c.L ? c.K - 1 : I;
     const u64 *dg = A + ((size_t)dig_idx[o] + I) * N + n;
-    // all 2L loads first, then the products: ncu (profiles/ncu_r02_keyswitch_summary.json) showed the rolled loop waiting on
+    // both components in one thread (they share the digits: one read of them instead of two, half the CTAs), and all
+    // 3L loads first, then the products: ncu (profiles/ncu_r02_keyswitch_summary.json) showed the rolled loop waiting on
     // one load pair at a time (long-scoreboard 6.6 of 9.6 stall cycles per issue, FMA pipe 26 % busy)
-    u64 dv[kMaxQ], kv[kMaxQ];
+    u64 dv[kMaxQ], k0[kMaxQ], k1[kMaxQ];
 #pragma unroll
     for (int J = 0; J < kMaxQ; J++)
         if (J < c.L) {
             dv[J] = dg[(size_t)J * R * N];
-            kv[J] = keys[(((size_t)J * 2 + comp) * c.K + key_index) * N + n];
+            k0[J] = keys[(((size_t)J * 2 + 0) * c.K + key_index) * N + n];
+            k1[J] = keys[(((size_t)J * 2 + 1) * c.K + key_index) * N + n];
         }
-    Acc128 acc{ 0, 0 };
+    Acc128 a0{ 0, 0 }, a1{ 0, 0 };
 #pragma unroll
     for (int J = 0; J < kMaxQ; J++)
-        if (J < c.L) mac128(acc, dv[J], kv[J]);
-    A[((size_t)out_idx[o] + (size_t)comp * R + I) * N + n] = barrett_prod(acc.lo, acc.hi, c.key_mod[I]); // <= 5 products of reduced operands
+        if (J < c.L) {
+            mac128(a0, dv[J], k0[J]);
+            mac128(a1, dv[J], k1[J]);
+        }
+    u64 *out = A + ((size_t)out_idx[o] + I) * N + n;
+    out[0] = barrett_prod(a0.lo, a0.hi, c.key_mod[I]); // <= 5 products of reduced operands
+    out[(size_t)R * N] = barrett_prod(a1.lo, a1.hi, c.key_mod[I]);
 }
 
 // ---- key switching: divide by the special prime with rounding and add to (c0, c1) ----
