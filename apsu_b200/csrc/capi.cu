@@ -386,7 +386,7 @@ int apsu_b200_run_query(
         Engine &e = E(ctx);
         e.query_begin(src_powers, nsrc, cts, false);
         e.set_relin_keys(relin_keys, false);
-        e.set_masks(masks, npack, false);
+        e.set_masks_overlapped(masks, npack); // uploaded behind ComputePowers: only the last kernel of the evaluation reads them
         e.compute_powers();
         e.eval_all();
         e.fetch_results(out, bundle_idx, cache_idx);

@@ -170,7 +170,7 @@ struct ProgramBuilder {
                 }
             }
         Engine *en = &e;
-        if (e.fuse_ && ndst.size() <= e.fuse_max_) {
+        if (e.fuse_ && (e.fuse_mask_ & 1) && ndst.size() <= e.fuse_max_) {
             // one launch: the transform of polynomial (rp, j) computes its own input (ntt.cuh: kNttExtend)
             size_t so = idx.add(esrc), dn = idx.add(ndst);
             const uint32_t count = (uint32_t)ndst.size();
@@ -203,7 +203,7 @@ struct ProgramBuilder {
         }
         size_t ao = idx.add(a), bo = idx.add(b), dof = idx.add(d), so = idx.add(ssrc), sd = idx.add(sdst);
         Engine *en = &e;
-        if (e.fuse_ && (size_t)n_ops * 3 * LS <= e.fuse_max_) {
+        if (e.fuse_ && (e.fuse_mask_ & 2) && (size_t)n_ops * 3 * LS <= e.fuse_max_) {
             // tensor product computed on the way into the inverse transform (ntt.cuh: kNttTensor)
             const std::vector<uint32_t> pat = ctx.pattern_ext(L);
             step([=] {
@@ -238,7 +238,7 @@ struct ProgramBuilder {
         ntt(nsrc, ndst, ctx.pattern_ks(L), false, /*reduce=*/true);
         size_t dg = idx.add(dig), ac = idx.add(acc), ct = idx.add(ct3), ds = idx.add(dst);
         Engine *en = &e;
-        if (e.fuse_ && (size_t)n_ops * 2 * R <= e.fuse_max_) {
+        if (e.fuse_ && (e.fuse_mask_ & 4) && (size_t)n_ops * 2 * R <= e.fuse_max_) {
             // inner product with the keys computed on the way into the inverse transform (ntt.cuh: kNttKsMac)
             const std::vector<uint32_t> pat = ctx.pattern_ks(L);
             step([=] {
@@ -343,6 +343,7 @@ Engine::Engine(const apsu_b200_params &p, int device) : ctx(p, device)
     if (const char *ev = std::getenv("APSU_B200_NO_GRAPH")) use_graphs_ = atoi(ev) == 0;
     if (const char *ev = std::getenv("APSU_B200_CHUNK")) eval_chunk_ = (uint32_t)std::max(1, atoi(ev));
     if (const char *ev = std::getenv("APSU_B200_FUSE")) fuse_ = atoi(ev) != 0; // A/B: element-wise producers fused into the transforms
+    if (const char *ev = std::getenv("APSU_B200_FUSE_MASK")) fuse_mask_ = (unsigned)atoi(ev); // 1 extension, 2 tensor product, 4 key-switch MAC
     if (const char *ev = std::getenv("APSU_B200_FUSE_MAX")) fuse_max_ = (size_t)std::max(0, atoi(ev)); // ... for launches of at most this many polynomials
     for (auto &ev : ev_) APSU_CUDA_CHECK(cudaEventCreate(&ev));
     APSU_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
@@ -356,6 +357,8 @@ Engine::~Engine()
         if (g.copied) cudaEventDestroy(g.copied);
     }
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    if (masks_free_) cudaEventDestroy(masks_free_);
+    if (masks_ready_) cudaEventDestroy(masks_ready_);
     if (flags_host_) cudaFreeHost(flags_host_);
     for (auto &e : ev_)
         if (e) cudaEventDestroy(e);
@@ -618,9 +621,38 @@ void Engine::set_relin_keys(const void *keys, bool on_device)
 void Engine::set_masks(const void *masks, uint32_t npack, bool on_device)
 {
     if (!masks || !npack) throw std::invalid_argument("masks are required");
+    join_masks_upload();
     masks_.ensure((size_t)npack * ctx.N);
     APSU_CUDA_CHECK(cudaMemcpyAsync(masks_.p, masks, (size_t)npack * ctx.N * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
     npack_ = npack;
+}
+
+// The masks are only read by the very last kernel of the evaluation, so their upload does not have to precede
+// ComputePowers: it runs on the copy stream (after everything already queued on the context stream, which may still
+// read the old masks) and eval_all makes the context stream wait for it.
+void Engine::set_masks_overlapped(const void *masks, uint32_t npack)
+{
+    if (!masks || !npack) throw std::invalid_argument("masks are required");
+    masks_.ensure((size_t)npack * ctx.N);
+    if (!copy_stream_) APSU_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    if (!masks_free_) {
+        APSU_CUDA_CHECK(cudaEventCreateWithFlags(&masks_free_, cudaEventDisableTiming));
+        APSU_CUDA_CHECK(cudaEventCreateWithFlags(&masks_ready_, cudaEventDisableTiming));
+    }
+    APSU_CUDA_CHECK(cudaEventRecord(masks_free_, ctx.stream));
+    APSU_CUDA_CHECK(cudaStreamWaitEvent(copy_stream_, masks_free_, 0));
+    APSU_CUDA_CHECK(cudaMemcpyAsync(masks_.p, masks, (size_t)npack * ctx.N * 8, cudaMemcpyHostToDevice, copy_stream_));
+    APSU_CUDA_CHECK(cudaEventRecord(masks_ready_, copy_stream_));
+    masks_pending_ = true;
+    npack_ = npack;
+}
+
+// orders the context stream behind an upload started by set_masks_overlapped (no-op otherwise)
+void Engine::join_masks_upload()
+{
+    if (!masks_pending_) return;
+    APSU_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, masks_ready_, 0));
+    masks_pending_ = false;
 }
 
 void Engine::encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t *out)
@@ -664,6 +696,7 @@ void Engine::generate_masks(const uint8_t *seed64, const uint8_t *padded, uint32
     values.ensure((size_t)npack * N);
     blocks.ensure((size_t)npack * ipb * 2);
     aux_bytes_.ensure(npack);
+    join_masks_upload();
     masks_.ensure((size_t)npack * N);
     aux_idx_.upload(seq, ctx.stream);
     APSU_CUDA_CHECK(cudaMemcpyAsync(aux_bytes_.p, padded, npack, cudaMemcpyHostToDevice, ctx.stream));
@@ -1606,6 +1639,7 @@ void Engine::eval_all()
     ctx.launches = 0;
     mac_events_used_ = 0;
     timed_mac_bytes_ = 0;
+    join_masks_upload();
     APSU_CUDA_CHECK(cudaEventRecord(ev_[2], ctx.stream));
     run_steps(eval_prog_, 0, eval_prog_.size(), eval_graph_);
     APSU_CUDA_CHECK(cudaEventRecord(ev_[3], ctx.stream));

@@ -109,6 +109,9 @@ public:
     }
     void throw_if_query_invalid(); // reads back the is_valid_for flag of the loaded query / keys (synchronises)
     void set_masks(const void *masks, uint32_t npack, bool on_device);
+    // host masks uploaded on the copy stream, behind ComputePowers: eval_all waits for them (apsu_b200_run_query)
+    void set_masks_overlapped(const void *masks, uint32_t npack);
+    void join_masks_upload();
     void encode_masks(const uint64_t *slot_values, uint32_t npack, uint64_t *out);
     void generate_masks(const uint8_t *seed64, const uint8_t *padded, uint32_t npack, uint64_t *blocks_out, uint64_t *values_out, bool synchronise = true);
     void decrypt_results(const uint64_t *secret_ntt_q0, const uint64_t *cts, uint32_t n, uint64_t *values_out, uint64_t *blocks_out, int32_t *budget_out);
@@ -212,10 +215,13 @@ private:
     };
     std::vector<FinGroup> fin_groups_;
     cudaStream_t copy_stream_ = nullptr;
+    cudaEvent_t masks_free_ = nullptr, masks_ready_ = nullptr; // set_masks_overlapped
+    bool masks_pending_ = false;
     // element-wise producers fused into the transforms that consume them (ntt.cuh: NttFuse).  Bit-exact, but measured
     // SLOWER on B200 (16M-4096: 6.38 vs 5.88 ms per query; 256K-512: 0.224 vs 0.209 ms): the prologue runs at the
     // transform's low occupancy and costs a shared-memory pass more than the launch it saves.  Off unless APSU_B200_FUSE=1.
     bool fuse_ = false;
+    unsigned fuse_mask_ = 7; // which producers fuse_ covers: 1 extension, 2 tensor product, 4 key-switch inner product
     size_t fuse_max_ = ~size_t(0); // with fuse_: only launches of at most this many polynomials (the latency-bound ones)
     void run_steps(std::vector<Step> &prog, size_t lo, size_t hi, ProgGraph &g);
     void drop_graphs();

@@ -455,7 +455,7 @@ void run_query(apsu_b200_mgpu &m, const uint32_t *src_powers, uint32_t nsrc, con
         }
     }
     // ---- masks are this rank's own (RunQuery draws them, receiver_ddh.cpp:218-289) ----
-    if (masks_local) e.set_masks(masks_local, npack_local, false);
+    if (masks_local) e.set_masks_overlapped(masks_local, npack_local); // behind ComputePowers: read by the last kernel only
 
     // ---- the evaluation ----
     if (!e.result_order().empty()) {
