@@ -5,6 +5,9 @@ query path at sizes the sanitizer finishes in a minute or two.
 
   compute-sanitizer --tool racecheck python tools/sanitize_small.py
   APSU_B200_NTT_SPLIT=4 compute-sanitizer --tool memcheck python tools/sanitize_small.py
+
+(On the shared B200 pool this round compute-sanitizer was closed by the operators, so the script itself ran — it checks its
+results against the oracle — but no sanitizer report exists; run it on a box where the tool is allowed.)
 """
 import pathlib
 import sys
